@@ -1,0 +1,46 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+def load_golden(name):
+    z = np.load(os.path.join(GOLDEN, name + ".npz"))
+    d = {k: z[k] for k in z.files}
+    sd = {k[3:]: v for k, v in d.items() if k.startswith("sd:")}
+    rest = {k: v for k, v in d.items() if not k.startswith("sd:")}
+    return rest, sd
+
+
+# hyper-parameters of the golden fixtures (must match tests/golden/gen_golden.py)
+GOLDEN_MODELS = {
+    "hifigan_rb1": ("hifigan", dict(resblock="1", upsample_rates=[4, 2], upsample_kernel_sizes=[8, 4],
+                                    upsample_initial_channel=64, resblock_kernel_sizes=[3, 7, 11],
+                                    resblock_dilation_sizes=[[1, 3, 5]] * 3), 16),
+    "hifigan_rb2": ("hifigan", dict(resblock="2", upsample_rates=[4, 4], upsample_kernel_sizes=[8, 8],
+                                    upsample_initial_channel=32, resblock_kernel_sizes=[3, 5, 7],
+                                    resblock_dilation_sizes=[[1, 2], [2, 6], [3, 12]]), 20),
+    "bigvgan_rb1": ("bigvgan", dict(resblock="1", upsample_rates=[4, 2], upsample_kernel_sizes=[8, 4],
+                                    upsample_initial_channel=64, resblock_kernel_sizes=[3, 7, 11],
+                                    resblock_dilation_sizes=[[1, 3, 5]] * 3, activation="snakebeta",
+                                    snake_logscale=True), 20),
+    "bigvgan_rb2": ("bigvgan", dict(resblock="2", upsample_rates=[2, 2], upsample_kernel_sizes=[4, 4],
+                                    upsample_initial_channel=32, resblock_kernel_sizes=[3, 5],
+                                    resblock_dilation_sizes=[[1, 2], [2, 6]], activation="snake",
+                                    snake_logscale=False), 12),
+}
+
+
+@pytest.fixture(scope="session")
+def golden_models():
+    return GOLDEN_MODELS

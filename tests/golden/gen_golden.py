@@ -1,0 +1,204 @@
+"""Generate the golden fixtures in this directory by RUNNING THE REFERENCE.
+
+Run only in the build container (needs /root/reference, which does not exist on
+the GPU box):   python tests/golden/gen_golden.py
+
+What it does: imports the reference's own modules (generator classes,
+Activation1d, utils/mel.py, utils/stft.py, gan_vocoder_inference.py) with
+import-time stubs for packages that are absent here (lhotse, json5, ruamel,
+accelerate, librosa), builds small seeded models, runs them on CPU fp32 and
+stores inputs / state dicts / outputs as ``.npz``.  The librosa stand-in is
+``oracle.mel.slaney_mel_filterbank`` (cross-checked against torchaudio in
+tests/test_oracle.py); the mel basis is stored in the fixture so parity never
+depends on how it was generated.
+"""
+import os
+import sys
+import types
+from types import SimpleNamespace as NS
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REF = "/root/reference"
+sys.path.insert(0, ROOT)
+sys.path.insert(0, REF)
+
+
+class _Stub(types.ModuleType):
+    """Module whose every attribute is a dummy class (never executed)."""
+    __path__ = []
+
+    def __getattr__(self, name):
+        if name.startswith("__"):
+            raise AttributeError(name)
+        return type(name, (), {})
+
+
+for _m in ["lhotse", "lhotse.dataset", "lhotse.dataset.collation", "lhotse.dataset.input_strategies",
+           "lhotse.utils", "json5", "ruamel", "ruamel.yaml", "ruamel_yaml", "accelerate"]:
+    if _m not in sys.modules:
+        sys.modules[_m] = _Stub(_m)
+
+from oracle import mel as omel  # noqa: E402
+
+_librosa = types.ModuleType("librosa")
+_filters = types.ModuleType("librosa.filters")
+_util = types.ModuleType("librosa.util")
+
+
+def _mel(sr=None, n_fft=None, n_mels=128, fmin=0.0, fmax=None, *a, **k):
+    return omel.slaney_mel_filterbank(sr, n_fft, n_mels, fmin, fmax)
+
+
+_filters.mel = _mel
+_util.pad_center = lambda data, size, **k: omel.pad_center(data, size)
+_util.tiny = lambda x: np.finfo(np.float32).tiny
+_util.normalize = lambda x, norm=None: x
+_librosa.filters, _librosa.util = _filters, _util
+sys.modules.update({"librosa": _librosa, "librosa.filters": _filters, "librosa.util": _util})
+
+import warnings  # noqa: E402
+
+warnings.filterwarnings("ignore")
+
+from models.vocoders.gan.generator.hifigan import HiFiGAN  # noqa: E402
+from models.vocoders.gan.generator.bigvgan import BigVGAN  # noqa: E402
+from modules.anti_aliasing.act import Activation1d  # noqa: E402
+from modules.activation_functions.snake import SnakeBeta  # noqa: E402
+import utils.mel as rmel  # noqa: E402
+import utils.stft as rstft  # noqa: E402
+
+
+def sd_np(module):
+    return {k: v.detach().cpu().numpy() for k, v in module.state_dict().items()}
+
+
+def run_with_stage_hooks(model, mel, nk):
+    outs = {}
+    hooks = []
+    for n, rb in enumerate(model.resblocks):
+        hooks.append(rb.register_forward_hook(lambda m, i, o, n=n: outs.__setitem__(n, o.detach().clone())))
+    with torch.no_grad():
+        y = model(mel)
+    for h in hooks:
+        h.remove()
+    stages = []
+    for i in range(len(model.resblocks) // nk):
+        xs = outs[i * nk]
+        for j in range(1, nk):
+            xs = xs + outs[i * nk + j]
+        stages.append((xs / nk).numpy())
+    return y.numpy(), stages
+
+
+def gen_generator(name, kind, hp, n_mel, B, T, seed, mel_dist="randn"):
+    pre = NS(n_mel=n_mel, hop_size=int(np.prod(hp["upsample_rates"])), extract_amplitude_phase=False)
+    cfg = NS(preprocess=pre, model=NS(**{kind: NS(**hp)}))
+    torch.manual_seed(seed)
+    model = (HiFiGAN if kind == "hifigan" else BigVGAN)(cfg).eval()
+    g = torch.Generator().manual_seed(seed + 1)
+    if kind == "bigvgan":
+        with torch.no_grad():
+            for n, p in model.named_parameters():
+                if n.endswith(".alpha") or n.endswith(".beta"):
+                    p.copy_(torch.randn(p.shape, generator=g) * 0.3 + (0.0 if hp["snake_logscale"] else 1.0))
+    if mel_dist == "randn":
+        mel = torch.randn(B, n_mel, T, generator=g)
+    else:  # log-mel range (utils/mel.py:11)
+        mel = torch.rand(B, n_mel, T, generator=g) * 13.5 - 11.5
+    wav, stages = run_with_stage_hooks(model, mel, len(hp["resblock_kernel_sizes"]))
+    out = {"mel": mel.numpy(), "wav": wav}
+    for i, s in enumerate(stages):
+        out[f"stage{i}"] = s
+    for k, v in sd_np(model).items():
+        out["sd:" + k] = v
+    np.savez(os.path.join(HERE, name + ".npz"), **out)
+    print(name, "wav", wav.shape, "absmax", float(np.abs(wav).max()),
+          "bytes", os.path.getsize(os.path.join(HERE, name + ".npz")))
+    return cfg, model
+
+
+HP_HIFIGAN_RB1 = dict(resblock="1", upsample_rates=[4, 2], upsample_kernel_sizes=[8, 4],
+                      upsample_initial_channel=64, resblock_kernel_sizes=[3, 7, 11],
+                      resblock_dilation_sizes=[[1, 3, 5]] * 3)
+HP_HIFIGAN_RB2 = dict(resblock="2", upsample_rates=[4, 4], upsample_kernel_sizes=[8, 8],
+                      upsample_initial_channel=32, resblock_kernel_sizes=[3, 5, 7],
+                      resblock_dilation_sizes=[[1, 2], [2, 6], [3, 12]])
+HP_BIGVGAN_RB1 = dict(resblock="1", upsample_rates=[4, 2], upsample_kernel_sizes=[8, 4],
+                      upsample_initial_channel=64, resblock_kernel_sizes=[3, 7, 11],
+                      resblock_dilation_sizes=[[1, 3, 5]] * 3, activation="snakebeta", snake_logscale=True)
+HP_BIGVGAN_RB2 = dict(resblock="2", upsample_rates=[2, 2], upsample_kernel_sizes=[4, 4],
+                      upsample_initial_channel=32, resblock_kernel_sizes=[3, 5],
+                      resblock_dilation_sizes=[[1, 2], [2, 6]], activation="snake", snake_logscale=False)
+
+
+def gen_activation1d():
+    torch.manual_seed(7)
+    act = Activation1d(activation=SnakeBeta(6, alpha_logscale=True))
+    with torch.no_grad():
+        act.act.alpha.normal_(0, 0.3)
+        act.act.beta.normal_(0, 0.3)
+    x = torch.randn(2, 6, 37) * 2
+    with torch.no_grad():
+        up = act.upsample(x)
+        y = act(x)
+    np.savez(os.path.join(HERE, "activation1d.npz"), x=x.numpy(), up=up.numpy(), y=y.numpy(),
+             alpha=act.act.alpha.detach().numpy(), beta=act.act.beta.detach().numpy(),
+             f_up=act.upsample.filter.numpy().reshape(-1), f_down=act.downsample.lowpass.filter.numpy().reshape(-1))
+    print("activation1d", y.shape, act.upsample.filter.reshape(-1)[:6].tolist())
+
+
+def gen_mel():
+    cfgp = NS(sample_rate=22050, n_fft=1024, n_mel=80, fmin=0, fmax=8000, win_size=1024, hop_size=256)
+    g = torch.Generator().manual_seed(0)
+    y = (torch.rand(2, 8192, generator=g) * 2 - 1) * 0.9
+    out = {"y": y.numpy(), "mel_basis": omel.slaney_mel_filterbank(22050, 1024, 80, 0, 8000)}
+    rmel.mel_basis.clear(); rmel.hann_window.clear()
+    out["extract_mel_features"] = rmel.extract_mel_features(y, cfgp).numpy()
+    rmel.mel_basis.clear(); rmel.hann_window.clear()
+    out["mel_spectrogram_torch"] = rmel.mel_spectrogram_torch(y, cfgp).numpy()
+    out["extract_linear_features"] = rmel.extract_linear_features(y, cfgp).numpy()
+    rmel.mel_basis.clear(); rmel.hann_window.clear()
+    out["extract_mel_features_b1"] = rmel.extract_mel_features(y[:1], cfgp).numpy()   # squeeze(0) case
+    # TacotronSTFT hard-codes .cuda() (utils/stft.py:168-169): identity shim for the CPU run
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    taco = rstft.TacotronSTFT(1024, 256, 1024, 80, 22050, 0, 8000)
+    m, e = taco.mel_spectrogram(y)
+    out["taco_mel"], out["taco_energy"] = m.numpy(), e.numpy()
+    out["taco_mel_basis"] = taco.mel_basis.numpy()
+    # odd geometry: win < n_fft, different hop
+    cfg2 = NS(sample_rate=16000, n_fft=512, n_mel=40, fmin=50, fmax=7600, win_size=400, hop_size=160)
+    y2 = (torch.rand(3, 3000, generator=g) * 2 - 1) * 0.5
+    rmel.mel_basis.clear(); rmel.hann_window.clear()
+    out["y2"] = y2.numpy()
+    out["mel_basis2"] = omel.slaney_mel_filterbank(16000, 512, 40, 50, 7600)
+    out["extract_mel_features2"] = rmel.extract_mel_features(y2, cfg2).numpy()
+    np.savez(os.path.join(HERE, "mel.npz"), **out)
+    print("mel", out["extract_mel_features"].shape, out["taco_mel"].shape, out["extract_mel_features2"].shape)
+
+
+def gen_plumbing(cfg, model):
+    import models.vocoders.gan.gan_vocoder_inference as gvi
+    g = torch.Generator().manual_seed(5)
+    mels = [torch.randn(16, t, generator=g) for t in (9, 14, 5)]
+    auds = gvi.synthesis_audios(cfg, model, mels, batch_size=2)
+    out = {f"mel{i}": m.numpy() for i, m in enumerate(mels)}
+    out.update({f"audio{i}": a.numpy() for i, a in enumerate(auds)})
+    batched = gvi.vocoder_inference(cfg, model, torch.stack([mels[1], mels[1].flip(-1)]), device="cpu")
+    out["batched_in"] = torch.stack([mels[1], mels[1].flip(-1)]).numpy()
+    out["batched_out"] = batched.numpy()
+    np.savez(os.path.join(HERE, "plumbing.npz"), **out)
+    print("plumbing", [a.shape for a in auds], batched.shape)
+
+
+if __name__ == "__main__":
+    cfg, model = gen_generator("hifigan_rb1", "hifigan", HP_HIFIGAN_RB1, 16, 2, 24, seed=1234)
+    gen_plumbing(cfg, model)
+    gen_generator("hifigan_rb2", "hifigan", HP_HIFIGAN_RB2, 20, 1, 19, seed=11, mel_dist="logmel")
+    gen_generator("bigvgan_rb1", "bigvgan", HP_BIGVGAN_RB1, 20, 2, 21, seed=21)
+    gen_generator("bigvgan_rb2", "bigvgan", HP_BIGVGAN_RB2, 12, 1, 33, seed=31)
+    gen_activation1d()
+    gen_mel()

@@ -1,0 +1,104 @@
+"""Pin the CPU oracle against outputs of the reference modules (tests/golden)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN_MODELS, load_golden
+from oracle import generator as og
+from oracle import mel as om
+
+
+@pytest.mark.parametrize("name", sorted(GOLDEN_MODELS))
+def test_generator_matches_reference(name):
+    kind, hp, _ = GOLDEN_MODELS[name]
+    g, sd = load_golden(name)
+    wav, stages = og.generator_forward(kind, sd, hp, g["mel"], return_stages=True)
+    for i, s in enumerate(stages):
+        np.testing.assert_allclose(s, g[f"stage{i}"], atol=2e-6, rtol=1e-5)
+    np.testing.assert_allclose(wav, g["wav"], atol=1e-6, rtol=0)
+
+
+def test_fold_weight_norm_matches_torch():
+    _, sd = load_golden("hifigan_rb1")
+    for name in ["conv_pre", "ups.0", "resblocks.2.convs1.1", "conv_post"]:
+        v, g = torch.from_numpy(sd[name + ".weight_v"]), torch.from_numpy(sd[name + ".weight_g"])
+        ref = torch._weight_norm(v, g, 0).numpy()
+        np.testing.assert_allclose(og.fold_weight_norm(sd[name + ".weight_v"], sd[name + ".weight_g"]),
+                                   ref, rtol=2e-6, atol=1e-9)
+
+
+def test_numpy_primitives_match_torch_primitives():
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal((2, 5, 23)).astype(np.float32)
+    w = rng.standard_normal((4, 5, 7)).astype(np.float32)
+    b = rng.standard_normal(4).astype(np.float32)
+    for d in (1, 3):
+        p = og.get_padding(7, d)
+        np.testing.assert_allclose(og.conv1d_np(x, w, b, d, p), og.conv1d(x, w, b, d, p).numpy(), atol=2e-5)
+    wt = rng.standard_normal((5, 3, 8)).astype(np.float32)
+    bt = rng.standard_normal(3).astype(np.float32)
+    np.testing.assert_allclose(og.conv_transpose1d_np(x, wt, bt, 4, 2),
+                               og.conv_transpose1d(x, wt, bt, 4, 2).numpy(), atol=2e-5)
+    np.testing.assert_allclose(og.conv_transpose1d_np(x, wt[:, :, :4], bt, 2, 1),
+                               og.conv_transpose1d(x, wt[:, :, :4], bt, 2, 1).numpy(), atol=2e-5)
+
+
+def test_activation1d_closed_forms_match_reference():
+    g, _ = load_golden("activation1d")
+    up = og.upsample2x_np(g["x"], g["f_up"])
+    np.testing.assert_allclose(up, g["up"], atol=2e-6)
+    y = og.activation1d_np(g["x"], g["alpha"], g["beta"], True, g["f_up"], g["f_down"])
+    np.testing.assert_allclose(y, g["y"], atol=3e-6)
+    yt = og.activation1d(torch.from_numpy(g["x"]), g["alpha"], g["beta"], True, g["f_up"], g["f_down"]).numpy()
+    np.testing.assert_allclose(yt, g["y"], atol=1e-6)
+    np.testing.assert_allclose(og.kaiser_sinc_filter12(), g["f_up"], atol=1e-8)
+    # short sequences: the replicate clamps overlap (T < filter reach)
+    for t in (1, 2, 3, 7):
+        x = torch.randn(1, 3, t)
+        a = og.activation1d(x, g["alpha"][:3], g["beta"][:3], True, g["f_up"], g["f_down"]).numpy()
+        b = og.activation1d_np(x.numpy(), g["alpha"][:3], g["beta"][:3], True, g["f_up"], g["f_down"])
+        np.testing.assert_allclose(a, b, atol=3e-6)
+
+
+def test_plumbing_matches_reference():
+    kind, hp, _ = GOLDEN_MODELS["hifigan_rb1"]
+    _, sd = load_golden("hifigan_rb1")
+    g, _ = load_golden("plumbing")
+    mels = [g[f"mel{i}"] for i in range(3)]
+    auds = og.synthesis_audios(kind, sd, hp, mels, hop_size=8, batch_size=2)
+    for i, a in enumerate(auds):
+        assert a.shape == g[f"audio{i}"].shape
+        np.testing.assert_allclose(a, g[f"audio{i}"], atol=1e-6)
+    np.testing.assert_allclose(og.vocoder_inference(kind, sd, hp, g["batched_in"]), g["batched_out"], atol=1e-6)
+
+
+def test_mel_oracle_matches_reference():
+    g, _ = load_golden("mel")
+    y, mb = g["y"], g["mel_basis"]
+    lin = om.extract_linear_features(y, 1024, 256, 1024)
+    np.testing.assert_allclose(lin, g["extract_linear_features"], atol=2e-4, rtol=1e-4)
+    m = om.extract_mel_features(y, mb, 1024, 256, 1024, eps=1e-9)
+    np.testing.assert_allclose(m, g["extract_mel_features"], atol=1e-4)
+    m6 = om.extract_mel_features(y, mb, 1024, 256, 1024, eps=1e-6)
+    np.testing.assert_allclose(m6, g["mel_spectrogram_torch"], atol=1e-4)
+    assert g["extract_mel_features_b1"].shape == (80, 32)          # the reference's squeeze(0)
+    np.testing.assert_allclose(m[0], g["extract_mel_features_b1"], atol=1e-4)
+    m2 = om.extract_mel_features(g["y2"], g["mel_basis2"], 512, 160, 400)
+    np.testing.assert_allclose(m2, g["extract_mel_features2"], atol=1e-4)
+
+
+def test_tacotron_oracle_matches_reference():
+    g, _ = load_golden("mel")
+    np.testing.assert_array_equal(g["taco_mel_basis"], g["mel_basis"])
+    mel, energy = om.tacotron_mel(g["y"], g["mel_basis"], 1024, 256, 1024)
+    assert mel.shape == g["taco_mel"].shape == (2, 80, 33)
+    np.testing.assert_allclose(mel, g["taco_mel"], atol=2e-4)
+    np.testing.assert_allclose(energy, g["taco_energy"], rtol=1e-4)
+    with pytest.raises(AssertionError):
+        om.tacotron_mel(g["y"] * 2, g["mel_basis"], 1024, 256, 1024)
+
+
+def test_mel_filterbank_matches_torchaudio():
+    ta = pytest.importorskip("torchaudio")
+    fb = ta.functional.melscale_fbanks(513, 0.0, 8000.0, 80, 22050, norm="slaney", mel_scale="slaney").T.numpy()
+    np.testing.assert_allclose(om.slaney_mel_filterbank(22050, 1024, 80, 0, 8000), fb, atol=5e-7)
