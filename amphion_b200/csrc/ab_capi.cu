@@ -1,0 +1,654 @@
+// C ABI of libamphion_b200: handles, parameter arena, forward plans.
+// See include/amphion_b200.h for the contract and the reference citations.
+#include <stdarg.h>
+#include <string.h>
+
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "ab_common.cuh"
+#include "ab_tc.cuh"
+
+namespace ab {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+}  // namespace ab
+
+using namespace ab;
+
+// ---------------------------------------------------------------------------
+// generator handle
+// ---------------------------------------------------------------------------
+namespace {
+
+enum SlotKind { SLOT_CONV_W, SLOT_CONVT_W, SLOT_VEC };
+
+struct Slot {
+  std::string name;
+  SlotKind kind;
+  int64_t shape[3];   // reference state-dict shape
+  int ndim;
+  size_t offset;      // into the arena (fp32 repacked image)
+  size_t bytes;
+  bool loaded;
+  // tensor-core operand image (built by finalize when precision != fp32)
+  size_t tc_offset;
+  size_t tc_bytes;
+};
+
+struct ConvRef {   // one weight-normed conv of the model
+  int w = -1, b = -1;
+  int cin = 0, cout = 0, k = 0, d = 1;
+};
+
+struct ActRef {    // one Activation1d module
+  int alpha = -1, beta = -1, fup = -1, fdown = -1;
+};
+
+struct BlockRef {  // one ResBlock / AMPBlock
+  int k = 0;
+  std::vector<int> dil;
+  std::vector<ConvRef> c1, c2;  // c2 empty for ResBlock2 / AMPBlock2
+  std::vector<ActRef> acts;     // 2*nd (type 1) or nd (type 2); empty for HiFi-GAN
+};
+
+struct StageRef {
+  ConvRef up;   // cin/cout/k, d unused; stride in `u`
+  int u = 1;
+  int ch = 0;
+  std::vector<BlockRef> blocks;
+};
+
+}  // namespace
+
+struct ab_generator {
+  ab_generator_config cfg;
+  std::vector<Slot> slots;
+  std::unordered_map<std::string, int> index;
+  size_t fp32_bytes = 0;    // arena part holding fp32 images
+  size_t arena_need = 0;    // total (fp32 + worst-case tensor-core images)
+  char* arena = nullptr;
+  size_t arena_bytes = 0;
+  bool finalized = false;
+  int precision = AB_PREC_FP32;
+  int hop = 1;
+  int launches = 0;
+
+  ConvRef conv_pre, conv_post;
+  ActRef act_post;
+  std::vector<StageRef> stages;
+
+  // profiling (ab_generator_set_profiling)
+  bool profiling = false;
+  struct ProfRec { int cls; cudaEvent_t e0, e1; double flops, bytes; };
+  std::vector<ProfRec> prof_recs;
+  std::vector<cudaEvent_t> event_pool;
+  cudaEvent_t get_event() {
+    if (!event_pool.empty()) { cudaEvent_t e = event_pool.back(); event_pool.pop_back(); return e; }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+  }
+  ~ab_generator() {
+    for (auto& r : prof_recs) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+    for (auto e : event_pool) cudaEventDestroy(e);
+  }
+
+  int add_slot(const std::string& name, SlotKind kind, std::initializer_list<int64_t> shape) {
+    Slot s;
+    s.name = name;
+    s.kind = kind;
+    s.ndim = (int)shape.size();
+    size_t n = 1;
+    int i = 0;
+    for (auto v : shape) {
+      s.shape[i++] = v;
+      n *= (size_t)v;
+    }
+    s.offset = fp32_bytes;
+    s.bytes = n * sizeof(float);
+    s.loaded = false;
+    s.tc_offset = 0;
+    s.tc_bytes = 0;
+    fp32_bytes += align_up(s.bytes, 256);
+    slots.push_back(s);
+    index[name] = (int)slots.size() - 1;
+    return (int)slots.size() - 1;
+  }
+  float* fptr(int slot) const { return slot < 0 ? nullptr : reinterpret_cast<float*>(arena + slots[slot].offset); }
+  void* tcptr(int slot) const { return arena + slots[slot].tc_offset; }
+};
+
+namespace {
+
+ConvRef make_conv(ab_generator* g, const std::string& name, int cin, int cout, int k, int d, bool transposed) {
+  ConvRef c;
+  c.cin = cin;
+  c.cout = cout;
+  c.k = k;
+  c.d = d;
+  if (transposed)
+    c.w = g->add_slot(name + ".weight", SLOT_CONVT_W, {cin, cout, k});
+  else
+    c.w = g->add_slot(name + ".weight", SLOT_CONV_W, {cout, cin, k});
+  c.b = g->add_slot(name + ".bias", SLOT_VEC, {cout});
+  return c;
+}
+
+ActRef make_act(ab_generator* g, const std::string& prefix, int ch, bool has_beta) {
+  ActRef a;
+  a.alpha = g->add_slot(prefix + ".act.alpha", SLOT_VEC, {ch});
+  a.beta = has_beta ? g->add_slot(prefix + ".act.beta", SLOT_VEC, {ch}) : a.alpha;
+  a.fup = g->add_slot(prefix + ".upsample.filter", SLOT_VEC, {1, 1, 12});
+  a.fdown = g->add_slot(prefix + ".downsample.lowpass.filter", SLOT_VEC, {1, 1, 12});
+  return a;
+}
+
+int validate_config(const ab_generator_config& c) {
+  if (c.kind != AB_GEN_HIFIGAN && c.kind != AB_GEN_BIGVGAN) return fail(AB_ERR_ARG, "config: unknown generator kind %d", c.kind);
+  if (c.n_mel <= 0 || c.upsample_initial_channel <= 0) return fail(AB_ERR_ARG, "config: n_mel / upsample_initial_channel must be positive");
+  if (c.num_upsamples <= 0 || c.num_upsamples > AB_MAX_STAGES) return fail(AB_ERR_ARG, "config: num_upsamples %d out of range", c.num_upsamples);
+  if (c.num_kernels <= 0 || c.num_kernels > AB_MAX_KERNELS) return fail(AB_ERR_ARG, "config: num_kernels %d out of range", c.num_kernels);
+  if (c.resblock != 1 && c.resblock != 2) return fail(AB_ERR_ARG, "config: resblock must be 1 or 2");
+  if ((c.upsample_initial_channel >> c.num_upsamples) <= 0) return fail(AB_ERR_ARG, "config: upsample_initial_channel too small for %d stages", c.num_upsamples);
+  for (int i = 0; i < c.num_upsamples; ++i) {
+    const int u = c.upsample_rates[i], k = c.upsample_kernel_sizes[i];
+    if (u <= 0 || k < u || ((k - u) & 1)) return fail(AB_ERR_UNSUPPORTED, "config: stage %d: kernel %d / rate %d (need k >= u, k-u even)", i, k, u);
+  }
+  for (int j = 0; j < c.num_kernels; ++j) {
+    if (c.num_dilations[j] <= 0 || c.num_dilations[j] > AB_MAX_DILATIONS) return fail(AB_ERR_ARG, "config: num_dilations[%d] out of range", j);
+    const int k = c.resblock_kernel_sizes[j];
+    if (k <= 0 || !(k & 1)) return fail(AB_ERR_UNSUPPORTED, "config: resblock kernel size %d must be odd", k);
+    for (int p = 0; p < c.num_dilations[j]; ++p)
+      if (c.resblock_dilation_sizes[j][p] <= 0) return fail(AB_ERR_ARG, "config: dilation must be positive");
+  }
+  if (c.kind == AB_GEN_BIGVGAN && c.activation != AB_ACT_SNAKE && c.activation != AB_ACT_SNAKEBETA)
+    return fail(AB_ERR_ARG, "config: BigVGAN activation must be snake or snakebeta");
+  return AB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* ab_last_error(void) { return g_err; }
+int ab_version(void) { return 100; }
+
+int ab_device_is_sm100(void) {
+  int dev = 0, major = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return 0;
+  return major == 10;
+}
+
+int ab_generator_create(const ab_generator_config* cfg, ab_generator** out) {
+  if (!cfg || !out) return fail(AB_ERR_ARG, "ab_generator_create: null argument");
+  int rc = validate_config(*cfg);
+  if (rc != AB_OK) return rc;
+  ab_generator* g = new ab_generator();
+  g->cfg = *cfg;
+  const bool big = cfg->kind == AB_GEN_BIGVGAN;
+  const bool has_beta = cfg->activation == AB_ACT_SNAKEBETA;
+  const int c0 = cfg->upsample_initial_channel;
+  g->conv_pre = make_conv(g, "conv_pre", cfg->n_mel, c0, 7, 1, false);
+  g->hop = 1;
+  int ch = c0;
+  for (int i = 0; i < cfg->num_upsamples; ++i) {
+    StageRef st;
+    const int cin = c0 >> i;
+    ch = c0 >> (i + 1);
+    st.ch = ch;
+    st.u = cfg->upsample_rates[i];
+    g->hop *= st.u;
+    // BigVGAN wraps each transposed conv in a ModuleList: key "ups.{i}.0" (bigvgan.py:254-276)
+    const std::string upname = "ups." + std::to_string(i) + (big ? ".0" : "");
+    st.up = make_conv(g, upname, cin, ch, cfg->upsample_kernel_sizes[i], 1, true);
+    for (int j = 0; j < cfg->num_kernels; ++j) {
+      BlockRef blk;
+      blk.k = cfg->resblock_kernel_sizes[j];
+      const std::string pre = "resblocks." + std::to_string(i * cfg->num_kernels + j);
+      for (int p = 0; p < cfg->num_dilations[j]; ++p) {
+        const int d = cfg->resblock_dilation_sizes[j][p];
+        blk.dil.push_back(d);
+        if (cfg->resblock == 1) {
+          blk.c1.push_back(make_conv(g, pre + ".convs1." + std::to_string(p), ch, ch, blk.k, d, false));
+          blk.c2.push_back(make_conv(g, pre + ".convs2." + std::to_string(p), ch, ch, blk.k, 1, false));
+        } else {
+          blk.c1.push_back(make_conv(g, pre + ".convs." + std::to_string(p), ch, ch, blk.k, d, false));
+        }
+      }
+      if (big) {
+        const int na = cfg->resblock == 1 ? 2 * cfg->num_dilations[j] : cfg->num_dilations[j];
+        for (int a = 0; a < na; ++a)
+          blk.acts.push_back(make_act(g, pre + ".activations." + std::to_string(a), ch, has_beta));
+      }
+      st.blocks.push_back(blk);
+    }
+    g->stages.push_back(st);
+  }
+  if (big) g->act_post = make_act(g, "activation_post", ch, has_beta);
+  g->conv_post = make_conv(g, "conv_post", ch, 1, 7, 1, false);
+
+  // tensor-core operand images live behind the fp32 images; reserve worst case
+  size_t tc = 0;
+  for (auto& s : g->slots) {
+    if (s.kind == SLOT_CONV_W) {
+      s.tc_bytes = tc_weight_image_bytes((int)s.shape[1], (int)s.shape[0], (int)s.shape[2]);
+      s.tc_offset = g->fp32_bytes + tc;
+      tc += align_up(s.tc_bytes, 256);
+    }
+  }
+  g->arena_need = g->fp32_bytes + tc;
+  *out = g;
+  return AB_OK;
+}
+
+void ab_generator_destroy(ab_generator* g) { delete g; }
+
+size_t ab_generator_param_bytes(const ab_generator* g) { return g ? g->arena_need : 0; }
+
+int ab_generator_bind_params(ab_generator* g, void* dev_arena, size_t bytes) {
+  if (!g || !dev_arena) return fail(AB_ERR_ARG, "bind_params: null argument");
+  if (bytes < g->arena_need) return fail(AB_ERR_WORKSPACE, "bind_params: arena %zu B < required %zu B", bytes, g->arena_need);
+  if (reinterpret_cast<uintptr_t>(dev_arena) & 255) return fail(AB_ERR_ARG, "bind_params: arena must be 256-byte aligned");
+  g->arena = static_cast<char*>(dev_arena);
+  g->arena_bytes = bytes;
+  g->finalized = false;
+  for (auto& s : g->slots) s.loaded = false;
+  return AB_OK;
+}
+
+int ab_generator_num_tensors(const ab_generator* g) { return g ? (int)g->slots.size() : 0; }
+
+const char* ab_generator_tensor_name(const ab_generator* g, int i) {
+  if (!g || i < 0 || i >= (int)g->slots.size()) return nullptr;
+  return g->slots[i].name.c_str();
+}
+
+static int load_common(ab_generator* g, const char* name, const float* dev_g, const float* dev_v,
+                       const int64_t* shape, int32_t ndim, void* stream) {
+  if (!g || !name || !dev_v || !shape) return fail(AB_ERR_ARG, "load_tensor: null argument");
+  if (!g->arena) return fail(AB_ERR_STATE, "load_tensor: bind_params first");
+  auto it = g->index.find(name);
+  if (it == g->index.end()) return fail(AB_ERR_ARG, "load_tensor: unknown tensor '%s'", name);
+  Slot& s = g->slots[it->second];
+  size_t n_ref = 1, n_in = 1;
+  for (int i = 0; i < s.ndim; ++i) n_ref *= (size_t)s.shape[i];
+  for (int i = 0; i < ndim; ++i) n_in *= (size_t)shape[i];
+  bool same = ndim == s.ndim;
+  for (int i = 0; same && i < ndim; ++i) same = shape[i] == s.shape[i];
+  // vectors may come with any shape of the right size (e.g. filter [1,1,12] or [12])
+  if (!(same || (s.kind == SLOT_VEC && n_in == n_ref)))
+    return fail(AB_ERR_ARG, "load_tensor: '%s' has the wrong shape (%d dims, %zu elements; expected %zu)", name, ndim, n_in, n_ref);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  float* dst = g->fptr(it->second);
+  if (s.kind == SLOT_VEC) {
+    if (dev_g) return fail(AB_ERR_ARG, "load_weight_norm: '%s' is not a convolution weight", name);
+    AB_CUDA_TRY(cudaMemcpyAsync(dst, dev_v, s.bytes, cudaMemcpyDeviceToDevice, st));
+  } else {
+    int rc = launch_repack_weight(dev_v, dev_g, dst, (int)s.shape[0], (int)s.shape[1], (int)s.shape[2],
+                                  s.kind == SLOT_CONVT_W ? 1 : 0, st);
+    if (rc != AB_OK) return rc;
+  }
+  s.loaded = true;
+  g->finalized = false;
+  return AB_OK;
+}
+
+int ab_generator_load_tensor(ab_generator* g, const char* name, const float* dev_src,
+                             const int64_t* shape, int32_t ndim, void* stream) {
+  return load_common(g, name, nullptr, dev_src, shape, ndim, stream);
+}
+
+int ab_generator_load_weight_norm(ab_generator* g, const char* name, const float* dev_g,
+                                  const float* dev_v, const int64_t* shape, int32_t ndim, void* stream) {
+  if (!dev_g) return fail(AB_ERR_ARG, "load_weight_norm: null weight_g");
+  return load_common(g, name, dev_g, dev_v, shape, ndim, stream);
+}
+
+int ab_generator_finalize(ab_generator* g, int32_t precision, void* stream) {
+  if (!g) return fail(AB_ERR_ARG, "finalize: null handle");
+  if (!g->arena) return fail(AB_ERR_STATE, "finalize: bind_params first");
+  for (auto& s : g->slots)
+    if (!s.loaded) return fail(AB_ERR_STATE, "finalize: tensor '%s' was never loaded", s.name.c_str());
+  if (precision != AB_PREC_FP32 && precision != AB_PREC_TC_F16 && precision != AB_PREC_TC_BF16)
+    return fail(AB_ERR_ARG, "finalize: unknown precision %d", precision);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (precision != AB_PREC_FP32) {
+    if (!ab_device_is_sm100()) return fail(AB_ERR_UNSUPPORTED, "finalize: tensor-core precision needs an sm_100 device");
+    for (size_t i = 0; i < g->slots.size(); ++i) {
+      Slot& s = g->slots[i];
+      if (s.kind != SLOT_CONV_W) continue;
+      int rc = launch_tc_pack_weight(g->fptr((int)i), g->tcptr((int)i), (int)s.shape[1], (int)s.shape[0],
+                                     (int)s.shape[2], precision, st);
+      if (rc != AB_OK) return rc;
+    }
+  }
+  g->precision = precision;
+  g->finalized = true;
+  return AB_OK;
+}
+
+// ---------------------------------------------------------------------------
+// forward
+// ---------------------------------------------------------------------------
+namespace {
+constexpr int NBUF = 7;  // R0 R1 U P0 P1 TMP ACT
+
+size_t stage_max_elems(const ab_generator* g, int64_t B, int64_t T) {
+  size_t mx = (size_t)B * g->cfg.upsample_initial_channel * T;
+  int64_t t = T;
+  for (auto& st : g->stages) {
+    t *= st.u;
+    mx = std::max(mx, (size_t)B * st.ch * t);
+  }
+  return mx;
+}
+}  // namespace
+
+size_t ab_generator_workspace_bytes(const ab_generator* g, int64_t B, int64_t T) {
+  if (!g || B <= 0 || T <= 0) return 0;
+  return NBUF * align_up(stage_max_elems(g, B, T) * sizeof(float), 256);
+}
+
+int ab_generator_last_launches(const ab_generator* g) { return g ? g->launches : 0; }
+
+int ab_generator_set_profiling(ab_generator* g, int32_t enable) {
+  if (!g) return fail(AB_ERR_ARG, "set_profiling: null handle");
+  g->profiling = enable != 0;
+  return AB_OK;
+}
+
+int ab_generator_get_profile(ab_generator* g, ab_profile_entry* out, int32_t max_entries, int32_t* n_out) {
+  if (!g || !out || !n_out) return fail(AB_ERR_ARG, "get_profile: null argument");
+  static const char* kNames[4] = {"tc_conv", "conv1d_fp32", "conv_transpose1d_fp32", "activation1d"};
+  if (max_entries < 4) return fail(AB_ERR_ARG, "get_profile: need room for 4 entries");
+  for (int i = 0; i < 4; ++i) {
+    memset(&out[i], 0, sizeof(out[i]));
+    strncpy(out[i].name, kNames[i], sizeof(out[i].name) - 1);
+  }
+  for (auto& r : g->prof_recs) {
+    AB_CUDA_TRY(cudaEventSynchronize(r.e1));
+    float ms = 0.f;
+    AB_CUDA_TRY(cudaEventElapsedTime(&ms, r.e0, r.e1));
+    out[r.cls].launches += 1;
+    out[r.cls].ms += ms;
+    out[r.cls].flops += r.flops;
+    out[r.cls].bytes += r.bytes;
+    g->event_pool.push_back(r.e0);
+    g->event_pool.push_back(r.e1);
+  }
+  g->prof_recs.clear();
+  *n_out = 4;
+  return AB_OK;
+}
+
+int ab_generator_forward(ab_generator* g, const float* dev_mel, int64_t B, int64_t T,
+                         const int64_t mel_strides[3], float* dev_wav, void* dev_workspace,
+                         size_t workspace_bytes, void* stream) {
+  if (!g || !dev_mel || !dev_wav || !mel_strides) return fail(AB_ERR_ARG, "forward: null argument");
+  if (!g->finalized) return fail(AB_ERR_STATE, "forward: finalize() the generator first");
+  if (B <= 0 || T <= 0) return fail(AB_ERR_ARG, "forward: batch and frames must be positive (got %lld, %lld)", (long long)B, (long long)T);
+  if (B > 65535) return fail(AB_ERR_UNSUPPORTED, "forward: batch %lld > 65535", (long long)B);
+  if ((int64_t)T * g->hop > (1ll << 30)) return fail(AB_ERR_UNSUPPORTED, "forward: sequence too long");
+  const size_t need = ab_generator_workspace_bytes(g, B, T);
+  if (!dev_workspace || workspace_bytes < need) return fail(AB_ERR_WORKSPACE, "forward: workspace %zu B < required %zu B", workspace_bytes, need);
+  if (reinterpret_cast<uintptr_t>(dev_workspace) & 255) return fail(AB_ERR_ARG, "forward: workspace must be 256-byte aligned");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t bufsz = need / NBUF;
+  float* buf[NBUF];
+  for (int i = 0; i < NBUF; ++i) buf[i] = reinterpret_cast<float*>(static_cast<char*>(dev_workspace) + i * bufsz);
+  float *R[2] = {buf[0], buf[1]}, *U = buf[2], *P[2] = {buf[3], buf[4]}, *TMP = buf[5], *ACT = buf[6];
+  const bool big = g->cfg.kind == AB_GEN_BIGVGAN;
+  const bool tc = g->precision != AB_PREC_FP32;
+  const int nk = g->cfg.num_kernels;
+  int launches = 0;
+  int rc;
+  // optional per-launch device timing
+  auto prof_begin = [&](int cls, double flops, double bytes) {
+    if (!g->profiling) return;
+    ab_generator::ProfRec r;
+    r.cls = cls; r.flops = flops; r.bytes = bytes;
+    r.e0 = g->get_event(); r.e1 = g->get_event();
+    cudaEventRecord(r.e0, st);
+    g->prof_recs.push_back(r);
+  };
+  auto prof_end = [&]() {
+    if (!g->profiling) return;
+    cudaEventRecord(g->prof_recs.back().e1, st);
+  };
+
+  auto conv = [&](const ConvRef& c, const float* x, int64_t xsb, int64_t xsc, int64_t xst, float* y,
+                  int Tn, float pre_slope, const float* residual, const float* acc_prev, float out_div,
+                  int post_tanh) -> int {
+    ConvParams p;
+    p.x = x; p.xsb = xsb; p.xsc = xsc; p.xst = xst;
+    p.w_t = g->fptr(c.w); p.bias = g->fptr(c.b);
+    p.residual = residual; p.acc_prev = acc_prev; p.y = y;
+    p.B = (int)B; p.Cin = c.cin; p.Cout = c.cout; p.T = Tn; p.k = c.k; p.d = c.d;
+    p.pre_slope = pre_slope; p.out_div = out_div; p.post_tanh = post_tanh;
+    ++launches;
+    const double el = (double)B * Tn;
+    prof_begin(1, 2.0 * el * c.cout * c.cin * c.k,
+               4.0 * (el * c.cin + el * c.cout * (1 + (residual != nullptr) + (acc_prev != nullptr)) + (double)c.cin * c.cout * c.k));
+    const int r = launch_conv1d_fp32(p, st);
+    prof_end();
+    return r;
+  };
+  auto snake = [&](const ActRef& a, const float* x, float* y, int C, int Tn) -> int {
+    SnakeParams p;
+    p.x = x; p.y = y; p.alpha = g->fptr(a.alpha); p.beta = g->fptr(a.beta);
+    p.f_up = g->fptr(a.fup); p.f_down = g->fptr(a.fdown);
+    p.B = (int)B; p.C = C; p.T = Tn; p.logscale = g->cfg.snake_logscale;
+    ++launches;
+    prof_begin(3, 0.0, 8.0 * (double)B * C * Tn);
+    const int r = launch_activation1d(p, st);
+    prof_end();
+    return r;
+  };
+  // one (conv1 -> conv2 -> + x) pair or a single (conv -> + x) on the tensor cores
+  auto tc_convs = [&](const ConvRef& c1, const ConvRef* c2, const float* x, float* y, int C, int Tn,
+                      float pre_slope, float mid_slope, const float* residual, const float* acc_prev,
+                      float out_div) -> int {
+    TcConvParams p;
+    p.x = x; p.y = y; p.residual = residual; p.acc_prev = acc_prev;
+    p.w1 = g->tcptr(c1.w); p.b1 = g->fptr(c1.b);
+    p.w2 = c2 ? g->tcptr(c2->w) : nullptr; p.b2 = c2 ? g->fptr(c2->b) : nullptr;
+    p.B = (int)B; p.C = C; p.T = Tn; p.k = c1.k; p.d1 = c1.d; p.nconv = c2 ? 2 : 1;
+    p.pre_slope = pre_slope; p.mid_slope = mid_slope; p.out_div = out_div;
+    p.precision = g->precision;
+    ++launches;
+    const double el = (double)B * C * Tn;
+    const int ncv = c2 ? 2 : 1;
+    prof_begin(0, 2.0 * el * C * c1.k * ncv,
+               4.0 * (el * (2 + (residual != nullptr && residual != x) + (acc_prev != nullptr)) + (double)ncv * C * C * c1.k));
+    const int r = launch_tc_conv(p, st);
+    prof_end();
+    return r;
+  };
+
+  // conv_pre (hifigan.py:204, bigvgan.py:314)
+  const int C0 = g->cfg.upsample_initial_channel;
+  rc = conv(g->conv_pre, dev_mel, mel_strides[0], mel_strides[1], mel_strides[2], R[0], (int)T, 1.0f,
+            nullptr, nullptr, 1.0f, 0);
+  if (rc != AB_OK) return rc;
+  int cur_r = 0;
+  int Tn = (int)T;
+  int cin = C0;
+  for (size_t i = 0; i < g->stages.size(); ++i) {
+    const StageRef& sg = g->stages[i];
+    // x = leaky_relu(x, 0.1) (HiFi-GAN only) ; x = ups[i](x)   (hifigan.py:206-207, bigvgan.py:316-318)
+    ConvTParams tp;
+    tp.x = R[cur_r]; tp.w_t = g->fptr(sg.up.w); tp.bias = g->fptr(sg.up.b); tp.y = U;
+    tp.B = (int)B; tp.Cin = cin; tp.Cout = sg.ch; tp.Tin = Tn; tp.k = sg.up.k; tp.u = sg.u;
+    tp.pre_slope = big ? 1.0f : 0.1f;
+    ++launches;
+    {
+      const double eo = (double)B * sg.ch * Tn * sg.u;
+      prof_begin(2, 2.0 * eo * cin * ((double)sg.up.k / sg.u),
+                 4.0 * ((double)B * cin * Tn + eo + (double)cin * sg.ch * sg.up.k));
+    }
+    rc = launch_conv_transpose1d_fp32(tp, st);
+    prof_end();
+    if (rc != AB_OK) return rc;
+    Tn *= sg.u;
+    const int C = sg.ch;
+    float* Rout = R[cur_r ^ 1];
+    const int64_t sb = (int64_t)C * Tn, sc = Tn;
+    const bool use_tc = tc && tc_conv_supported(C, sg.blocks[0].k);
+    for (int j = 0; j < nk; ++j) {
+      const BlockRef& blk = sg.blocks[j];
+      const float* cur = U;
+      int pp = 0;
+      const int nd = (int)blk.dil.size();
+      for (int p = 0; p < nd; ++p) {
+        const bool last = p == nd - 1;
+        float* dst = last ? Rout : P[pp];
+        if (!last) pp ^= 1;
+        // xs = rb_0(x) ; xs += rb_j(x) ; x = xs / num_kernels  (hifigan.py:208-214)
+        const float* accp = (last && j > 0) ? Rout : nullptr;
+        const float div = (last && j == nk - 1) ? (float)nk : 1.0f;
+        const bool pair = !blk.c2.empty();
+        const bool blk_tc = use_tc && tc_conv_supported(C, blk.k);
+        if (!big) {
+          if (blk_tc) {
+            rc = tc_convs(blk.c1[p], pair ? &blk.c2[p] : nullptr, cur, dst, C, Tn, 0.1f, 0.1f, cur, accp, div);
+            if (rc != AB_OK) return rc;
+          } else if (pair) {
+            rc = conv(blk.c1[p], cur, sb, sc, 1, TMP, Tn, 0.1f, nullptr, nullptr, 1.0f, 0);
+            if (rc != AB_OK) return rc;
+            rc = conv(blk.c2[p], TMP, sb, sc, 1, dst, Tn, 0.1f, cur, accp, div, 0);
+            if (rc != AB_OK) return rc;
+          } else {
+            rc = conv(blk.c1[p], cur, sb, sc, 1, dst, Tn, 0.1f, cur, accp, div, 0);
+            if (rc != AB_OK) return rc;
+          }
+        } else {
+          // AMPBlock: anti-aliased snake in front of every conv (bigvgan.py:137-146, :222-228)
+          const ActRef& a1 = pair ? blk.acts[2 * p] : blk.acts[p];
+          rc = snake(a1, cur, ACT, C, Tn);
+          if (rc != AB_OK) return rc;
+          if (pair) {
+            if (blk_tc) rc = tc_convs(blk.c1[p], nullptr, ACT, TMP, C, Tn, 1.0f, 1.0f, nullptr, nullptr, 1.0f);
+            else rc = conv(blk.c1[p], ACT, sb, sc, 1, TMP, Tn, 1.0f, nullptr, nullptr, 1.0f, 0);
+            if (rc != AB_OK) return rc;
+            rc = snake(blk.acts[2 * p + 1], TMP, ACT, C, Tn);
+            if (rc != AB_OK) return rc;
+            if (blk_tc) rc = tc_convs(blk.c2[p], nullptr, ACT, dst, C, Tn, 1.0f, 1.0f, cur, accp, div);
+            else rc = conv(blk.c2[p], ACT, sb, sc, 1, dst, Tn, 1.0f, cur, accp, div, 0);
+            if (rc != AB_OK) return rc;
+          } else {
+            if (blk_tc) rc = tc_convs(blk.c1[p], nullptr, ACT, dst, C, Tn, 1.0f, 1.0f, cur, accp, div);
+            else rc = conv(blk.c1[p], ACT, sb, sc, 1, dst, Tn, 1.0f, cur, accp, div, 0);
+            if (rc != AB_OK) return rc;
+          }
+        }
+        cur = dst;
+      }
+    }
+    cur_r ^= 1;
+    cin = C;
+  }
+  // post: leaky_relu(x) with the DEFAULT slope 0.01 (hifigan.py:215) or
+  // activation_post (bigvgan.py:327); conv_post; tanh
+  const float* xin = R[cur_r];
+  const int64_t sb = (int64_t)cin * Tn, sc = Tn;
+  if (big) {
+    rc = snake(g->act_post, xin, ACT, cin, Tn);
+    if (rc != AB_OK) return rc;
+    rc = conv(g->conv_post, ACT, sb, sc, 1, dev_wav, Tn, 1.0f, nullptr, nullptr, 1.0f, 1);
+  } else {
+    rc = conv(g->conv_post, xin, sb, sc, 1, dev_wav, Tn, 0.01f, nullptr, nullptr, 1.0f, 1);
+  }
+  if (rc != AB_OK) return rc;
+  g->launches = launches;
+  return AB_OK;
+}
+
+// ---------------------------------------------------------------------------
+// standalone building blocks
+// ---------------------------------------------------------------------------
+int ab_activation1d_forward(const float* dev_x, float* dev_y, int64_t B, int64_t C, int64_t T,
+                            const float* dev_alpha, const float* dev_beta, int32_t logscale,
+                            const float* f_up, const float* f_down, void* stream) {
+  if (!dev_x || !dev_y || !dev_alpha || !dev_beta || !f_up || !f_down) return fail(AB_ERR_ARG, "activation1d: null argument");
+  if (T > (1ll << 30)) return fail(AB_ERR_UNSUPPORTED, "activation1d: sequence too long");
+  SnakeParams p;
+  p.x = dev_x; p.y = dev_y; p.alpha = dev_alpha; p.beta = dev_beta; p.f_up = f_up; p.f_down = f_down;
+  p.B = (int)B; p.C = (int)C; p.T = (int)T; p.logscale = logscale;
+  return launch_activation1d(p, static_cast<cudaStream_t>(stream));
+}
+
+size_t ab_conv1d_workspace_bytes(int64_t cin, int64_t cout, int32_t k, int32_t precision) {
+  size_t n = align_up((size_t)cin * cout * k * sizeof(float), 256);
+  if (precision != AB_PREC_FP32) n += align_up(tc_weight_image_bytes((int)cin, (int)cout, k), 256);
+  return n;
+}
+
+int ab_conv1d_forward(const float* dev_x, const float* dev_w, const float* dev_bias,
+                      const float* dev_residual, float* dev_y, int64_t B, int64_t cin, int64_t cout,
+                      int64_t T, int32_t k, int32_t d, float pre_slope, int32_t post_tanh,
+                      int32_t precision, void* ws, size_t ws_bytes, void* stream) {
+  if (!dev_x || !dev_w || !dev_y || !ws) return fail(AB_ERR_ARG, "conv1d: null argument");
+  if (ws_bytes < ab_conv1d_workspace_bytes(cin, cout, k, precision)) return fail(AB_ERR_WORKSPACE, "conv1d: workspace too small");
+  if (T > (1ll << 30)) return fail(AB_ERR_UNSUPPORTED, "conv1d: sequence too long");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  float* w_t = static_cast<float*>(ws);
+  int rc = launch_repack_weight(dev_w, nullptr, w_t, (int)cout, (int)cin, k, 0, st);
+  if (rc != AB_OK) return rc;
+  if (precision == AB_PREC_FP32) {
+    ConvParams p;
+    p.x = dev_x; p.xsb = cin * T; p.xsc = T; p.xst = 1; p.w_t = w_t; p.bias = dev_bias;
+    p.residual = dev_residual; p.acc_prev = nullptr; p.y = dev_y;
+    p.B = (int)B; p.Cin = (int)cin; p.Cout = (int)cout; p.T = (int)T; p.k = k; p.d = d;
+    p.pre_slope = pre_slope; p.out_div = 1.0f; p.post_tanh = post_tanh;
+    return launch_conv1d_fp32(p, st);
+  }
+  if (cin != cout || post_tanh || !tc_conv_supported((int)cin, k))
+    return fail(AB_ERR_UNSUPPORTED, "conv1d: tensor-core path needs Cin == Cout <= %d and no tanh", tc_max_channels());
+  void* img = static_cast<char*>(ws) + align_up((size_t)cin * cout * k * sizeof(float), 256);
+  rc = launch_tc_pack_weight(w_t, img, (int)cin, (int)cout, k, precision, st);
+  if (rc != AB_OK) return rc;
+  TcConvParams p;
+  p.x = dev_x; p.y = dev_y; p.residual = dev_residual; p.acc_prev = nullptr;
+  p.w1 = img; p.b1 = dev_bias; p.w2 = nullptr; p.b2 = nullptr;
+  p.B = (int)B; p.C = (int)cin; p.T = (int)T; p.k = k; p.d1 = d; p.nconv = 1;
+  p.pre_slope = pre_slope; p.mid_slope = 1.0f; p.out_div = 1.0f; p.precision = precision;
+  return launch_tc_conv(p, st);
+}
+
+int ab_conv_transpose1d_forward(const float* dev_x, const float* dev_w, const float* dev_bias,
+                                float* dev_y, int64_t B, int64_t cin, int64_t cout, int64_t Tin,
+                                int32_t k, int32_t u, float pre_slope, void* ws, size_t ws_bytes,
+                                void* stream) {
+  if (!dev_x || !dev_w || !dev_y || !ws) return fail(AB_ERR_ARG, "conv_transpose1d: null argument");
+  if (ws_bytes < (size_t)cin * cout * k * sizeof(float)) return fail(AB_ERR_WORKSPACE, "conv_transpose1d: workspace too small");
+  if (Tin * u > (1ll << 30)) return fail(AB_ERR_UNSUPPORTED, "conv_transpose1d: sequence too long");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  float* w_t = static_cast<float*>(ws);
+  int rc = launch_repack_weight(dev_w, nullptr, w_t, (int)cin, (int)cout, k, 1, st);
+  if (rc != AB_OK) return rc;
+  ConvTParams p;
+  p.x = dev_x; p.w_t = w_t; p.bias = dev_bias; p.y = dev_y;
+  p.B = (int)B; p.Cin = (int)cin; p.Cout = (int)cout; p.Tin = (int)Tin; p.k = k; p.u = u; p.pre_slope = pre_slope;
+  return launch_conv_transpose1d_fp32(p, st);
+}
+
+}  // extern "C"

@@ -1,0 +1,81 @@
+// Shared host/device helpers for libamphion_b200 (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/amphion_b200.h"
+
+namespace ab {
+
+// ---- error plumbing (thread-local message, integer codes across the C ABI) ----
+void set_error(const char* fmt, ...);
+int fail(int code, const char* fmt, ...);
+
+#define AB_CUDA_TRY(expr)                                                              \
+  do {                                                                                 \
+    cudaError_t _e = (expr);                                                           \
+    if (_e != cudaSuccess)                                                             \
+      return ::ab::fail(AB_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), \
+                        __FILE__, __LINE__);                                           \
+  } while (0)
+
+#define AB_LAUNCH_CHECK(what)                                                          \
+  do {                                                                                 \
+    cudaError_t _e = cudaGetLastError();                                               \
+    if (_e != cudaSuccess)                                                             \
+      return ::ab::fail(AB_ERR_CUDA, "launch of %s failed: %s", what, cudaGetErrorString(_e)); \
+  } while (0)
+
+static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// ---- fp32 (CUDA-core) convolution parameters --------------------------------
+// y = post( ((bias + W * lrelu(x, pre_slope)) + residual + acc_prev) / out_div )
+struct ConvParams {
+  const float* x;       // [B, Cin, T] with element strides xsb/xsc/xst
+  int64_t xsb, xsc, xst;
+  const float* w_t;     // repacked [Cin][k][Cout]
+  const float* bias;    // [Cout] or nullptr
+  const float* residual;  // contiguous [B, Cout, T] or nullptr
+  const float* acc_prev;  // contiguous [B, Cout, T] or nullptr (branch accumulation)
+  float* y;             // contiguous [B, Cout, T]
+  int B, Cin, Cout, T;
+  int k, d;
+  float pre_slope;      // 1.0f = no activation
+  float out_div;        // 1.0f = none (IEEE division, as the reference's xs / num_kernels)
+  int post_tanh;
+};
+
+struct ConvTParams {
+  const float* x;       // contiguous [B, Cin, Tin]
+  const float* w_t;     // repacked [Cin][k][Cout]
+  const float* bias;
+  float* y;             // contiguous [B, Cout, Tin*u]
+  int B, Cin, Cout, Tin;
+  int k, u;
+  float pre_slope;
+};
+
+struct SnakeParams {
+  const float* x;       // contiguous [B, C, T]
+  float* y;
+  const float* alpha;   // [C]
+  const float* beta;    // [C] (== alpha for Snake)
+  const float* f_up;    // [12]
+  const float* f_down;  // [12]
+  int B, C, T;
+  int logscale;
+};
+
+// launchers (ab_kernels_fp32.cu)
+int launch_conv1d_fp32(const ConvParams& p, cudaStream_t s);
+int launch_conv_transpose1d_fp32(const ConvTParams& p, cudaStream_t s);
+int launch_activation1d(const SnakeParams& p, cudaStream_t s);
+// Repack a conv weight into [Cin][k][Cout] fp32, folding weight norm if g != nullptr.
+// transposed == 0: src is [Cout][Cin][k] (Conv1d); 1: src is [Cin][Cout][k] (ConvTranspose1d).
+int launch_repack_weight(const float* v, const float* g, float* dst, int d0, int d1, int k,
+                         int transposed, cudaStream_t s);
+
+}  // namespace ab

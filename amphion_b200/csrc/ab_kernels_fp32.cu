@@ -1,0 +1,465 @@
+// CUDA-core fp32 kernels: the exact-arithmetic path (AB_PREC_FP32) and the
+// pieces that are not channel-mixing contractions (anti-aliased Snake, weight
+// repacking).  Reference semantics are cited per kernel (paths relative to the
+// Amphion reference root).
+#include "ab_common.cuh"
+
+namespace ab {
+
+// ===========================================================================
+// conv1d: F.conv1d with "same" zero padding and dilation, fused with the
+// leaky_relu in front of it, bias, residual add, branch accumulation, /nk and
+// tanh  (hifigan.py:93-100 ResBlock1.forward, :139-144 ResBlock2.forward,
+// :208-217 branch mix + conv_post + tanh).
+// Tile: 64 output channels x 128 time steps per CTA, 4x8 outputs per thread.
+// ===========================================================================
+namespace {
+constexpr int CO_T = 64;
+constexpr int TT = 128;
+constexpr int CI_T = 8;
+constexpr int NT = 256;
+
+__global__ void __launch_bounds__(NT) conv1d_fp32_kernel(ConvParams p) {
+  extern __shared__ float smem[];
+  const int halo = (p.k - 1) * p.d;
+  const int XW = TT + halo;
+  float* xs = smem;               // [CI_T][XW]
+  float* ws = smem + CI_T * XW;   // [CI_T][k][CO_T]
+  const int t0 = blockIdx.x * TT, co0 = blockIdx.y * CO_T, b = blockIdx.z;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int pad = halo >> 1;
+  const float slope = p.pre_slope;
+  const float* xb = p.x + (int64_t)b * p.xsb;
+
+  float acc[4][8];
+#pragma unroll
+  for (int c = 0; c < 4; ++c)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[c][i] = 0.f;
+
+  for (int ci0 = 0; ci0 < p.Cin; ci0 += CI_T) {
+    for (int idx = threadIdx.x; idx < CI_T * XW; idx += NT) {
+      const int ci = idx / XW, n = idx - ci * XW;
+      const int t = t0 - pad + n, c = ci0 + ci;
+      float v = 0.f;
+      if (c < p.Cin && t >= 0 && t < p.T) {
+        v = __ldg(xb + (int64_t)c * p.xsc + (int64_t)t * p.xst);
+        v = v >= 0.f ? v : v * slope;
+      }
+      xs[idx] = v;
+    }
+    const int wn = CI_T * p.k * CO_T;
+    for (int idx = threadIdx.x; idx < wn; idx += NT) {
+      const int co = idx & (CO_T - 1);
+      const int r = idx / CO_T;  // ci * k + j
+      const int ci = r / p.k;
+      float v = 0.f;
+      if (ci0 + ci < p.Cin && co0 + co < p.Cout)
+        v = __ldg(p.w_t + ((int64_t)ci0 * p.k + r) * p.Cout + co0 + co);
+      ws[idx] = v;
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int ci = 0; ci < CI_T; ++ci) {
+      const float* xr = xs + ci * XW + tx;
+      const float* wr = ws + ci * p.k * CO_T + ty * 4;
+      for (int j = 0; j < p.k; ++j) {
+        const float4 w = *reinterpret_cast<const float4*>(wr + j * CO_T);
+        const float* xj = xr + j * p.d;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float xv = xj[16 * i];
+          acc[0][i] = fmaf(w.x, xv, acc[0][i]);
+          acc[1][i] = fmaf(w.y, xv, acc[1][i]);
+          acc[2][i] = fmaf(w.z, xv, acc[2][i]);
+          acc[3][i] = fmaf(w.w, xv, acc[3][i]);
+        }
+      }
+    }
+    __syncthreads();
+  }
+
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const int co = co0 + ty * 4 + c;
+    if (co >= p.Cout) continue;
+    const float bv = p.bias ? __ldg(p.bias + co) : 0.f;
+    const int64_t row = ((int64_t)b * p.Cout + co) * p.T;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int t = t0 + tx + 16 * i;
+      if (t >= p.T) continue;
+      float v = acc[c][i] + bv;
+      if (p.residual) v += __ldg(p.residual + row + t);
+      if (p.acc_prev) v += __ldg(p.acc_prev + row + t);
+      if (p.out_div != 1.0f) v = v / p.out_div;
+      if (p.post_tanh) v = tanhf(v);
+      p.y[row + t] = v;
+    }
+  }
+}
+
+// Few output channels (conv_post: C -> 1, hifigan.py:199,216): one CTA per
+// (batch, 1024-sample tile), all Cout (<= 4) per thread; HBM-bound.
+constexpr int PT = 1024;
+constexpr int PCI = 8;
+__global__ void __launch_bounds__(NT) conv1d_fewout_fp32_kernel(ConvParams p) {
+  extern __shared__ float smem[];
+  const int halo = (p.k - 1) * p.d;
+  const int XW = PT + halo;
+  float* xs = smem;              // [PCI][XW]
+  float* ws = smem + PCI * XW;   // [Cin][k][Cout] (whole filter)
+  const int t0 = blockIdx.x * PT, b = blockIdx.z;
+  const int pad = halo >> 1;
+  const float slope = p.pre_slope;
+  const float* xb = p.x + (int64_t)b * p.xsb;
+  for (int idx = threadIdx.x; idx < p.Cin * p.k * p.Cout; idx += NT) ws[idx] = __ldg(p.w_t + idx);
+
+  float acc[4][4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c)
+#pragma unroll
+    for (int r = 0; r < 4; ++r) acc[c][r] = 0.f;
+
+  for (int ci0 = 0; ci0 < p.Cin; ci0 += PCI) {
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < PCI * XW; idx += NT) {
+      const int ci = idx / XW, n = idx - ci * XW;
+      const int t = t0 - pad + n, c = ci0 + ci;
+      float v = 0.f;
+      if (c < p.Cin && t >= 0 && t < p.T) {
+        v = __ldg(xb + (int64_t)c * p.xsc + (int64_t)t * p.xst);
+        v = v >= 0.f ? v : v * slope;
+      }
+      xs[idx] = v;
+    }
+    __syncthreads();
+    const int nci = min(PCI, p.Cin - ci0);
+    for (int ci = 0; ci < nci; ++ci) {
+      for (int j = 0; j < p.k; ++j) {
+        const float* wv = ws + ((ci0 + ci) * p.k + j) * p.Cout;
+        const float* xr = xs + ci * XW + j * p.d + threadIdx.x;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const float xv = xr[NT * r];
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            if (c < p.Cout) acc[c][r] = fmaf(wv[c], xv, acc[c][r]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    if (c >= p.Cout) continue;
+    const float bv = p.bias ? __ldg(p.bias + c) : 0.f;
+    const int64_t row = ((int64_t)b * p.Cout + c) * p.T;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int t = t0 + threadIdx.x + NT * r;
+      if (t >= p.T) continue;
+      float v = acc[c][r] + bv;
+      if (p.residual) v += __ldg(p.residual + row + t);
+      if (p.acc_prev) v += __ldg(p.acc_prev + row + t);
+      if (p.out_div != 1.0f) v = v / p.out_div;
+      if (p.post_tanh) v = tanhf(v);
+      p.y[row + t] = v;
+    }
+  }
+}
+}  // namespace
+
+int launch_conv1d_fp32(const ConvParams& p, cudaStream_t s) {
+  if (p.B <= 0 || p.Cin <= 0 || p.Cout <= 0 || p.T <= 0 || p.k <= 0 || p.d <= 0)
+    return fail(AB_ERR_ARG, "conv1d: bad shape B=%d Cin=%d Cout=%d T=%d k=%d d=%d", p.B, p.Cin,
+                p.Cout, p.T, p.k, p.d);
+  if (((p.k - 1) * p.d) & 1)
+    return fail(AB_ERR_UNSUPPORTED, "conv1d: (k-1)*dilation must be even for 'same' padding (k=%d d=%d)",
+                p.k, p.d);
+  if (p.B > 65535) return fail(AB_ERR_UNSUPPORTED, "conv1d: batch %d > 65535", p.B);
+  const int halo = (p.k - 1) * p.d;
+  if (p.Cout <= 4) {
+    const size_t smem = sizeof(float) * ((size_t)PCI * (PT + halo) + (size_t)p.Cin * p.k * p.Cout);
+    if (smem > 200 * 1024) return fail(AB_ERR_UNSUPPORTED, "conv1d(few-out): filter too large for smem");
+    static size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+      AB_CUDA_TRY(cudaFuncSetAttribute(conv1d_fewout_fp32_kernel,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      configured = 200 * 1024;
+    }
+    dim3 grid((unsigned)ceil_div(p.T, PT), 1, (unsigned)p.B);
+    conv1d_fewout_fp32_kernel<<<grid, NT, smem, s>>>(p);
+    AB_LAUNCH_CHECK("conv1d_fewout_fp32_kernel");
+    return AB_OK;
+  }
+  const size_t smem = sizeof(float) * ((size_t)CI_T * (TT + halo) + (size_t)CI_T * p.k * CO_T);
+  if (smem > 200 * 1024)
+    return fail(AB_ERR_UNSUPPORTED, "conv1d: k=%d dilation=%d needs %zu B of shared memory", p.k, p.d, smem);
+  static bool configured = false;
+  if (smem > 48 * 1024 && !configured) {
+    AB_CUDA_TRY(cudaFuncSetAttribute(conv1d_fp32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     200 * 1024));
+    configured = true;
+  }
+  if (ceil_div(p.Cout, CO_T) > 65535) return fail(AB_ERR_UNSUPPORTED, "conv1d: too many channels");
+  dim3 grid((unsigned)ceil_div(p.T, TT), (unsigned)ceil_div(p.Cout, CO_T), (unsigned)p.B);
+  conv1d_fp32_kernel<<<grid, NT, smem, s>>>(p);
+  AB_LAUNCH_CHECK("conv1d_fp32_kernel");
+  return AB_OK;
+}
+
+// ===========================================================================
+// ConvTranspose1d(stride=u, padding=(k-u)/2) fused with the leaky_relu in
+// front of it (hifigan.py:206-207; bigvgan.py:316-318 has no activation):
+//   y[co,t] = b[co] + sum_ci sum_{j = (t+p) mod u, +u, ... < k} x[ci,(t+p-j)/u] * W[ci,co,j]
+// ===========================================================================
+namespace {
+__global__ void __launch_bounds__(NT) convT_fp32_kernel(ConvTParams p, int XW, int M) {
+  extern __shared__ float smem[];
+  float* xs = smem;               // [CI_T][XW]
+  float* ws = smem + CI_T * XW;   // [CI_T][k][CO_T]
+  const int Tout = p.Tin * p.u;
+  const int t0 = blockIdx.x * TT, co0 = blockIdx.y * CO_T, b = blockIdx.z;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int pd = (p.k - p.u) >> 1;
+  const int s_min = (t0 + pd) / p.u - (M - 1);
+  const float slope = p.pre_slope;
+  const float* xb = p.x + (int64_t)b * p.Cin * p.Tin;
+
+  int phi[8], sl[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int q = t0 + tx + 16 * i + pd;
+    phi[i] = q % p.u;
+    sl[i] = q / p.u - s_min;
+  }
+  float acc[4][8];
+#pragma unroll
+  for (int c = 0; c < 4; ++c)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[c][i] = 0.f;
+
+  for (int ci0 = 0; ci0 < p.Cin; ci0 += CI_T) {
+    for (int idx = threadIdx.x; idx < CI_T * XW; idx += NT) {
+      const int ci = idx / XW, n = idx - ci * XW;
+      const int sidx = s_min + n, c = ci0 + ci;
+      float v = 0.f;
+      if (c < p.Cin && sidx >= 0 && sidx < p.Tin) {
+        v = __ldg(xb + (int64_t)c * p.Tin + sidx);
+        v = v >= 0.f ? v : v * slope;
+      }
+      xs[idx] = v;
+    }
+    const int wn = CI_T * p.k * CO_T;
+    for (int idx = threadIdx.x; idx < wn; idx += NT) {
+      const int co = idx & (CO_T - 1);
+      const int r = idx / CO_T;
+      const int ci = r / p.k;
+      float v = 0.f;
+      if (ci0 + ci < p.Cin && co0 + co < p.Cout)
+        v = __ldg(p.w_t + ((int64_t)ci0 * p.k + r) * p.Cout + co0 + co);
+      ws[idx] = v;
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int ci = 0; ci < CI_T; ++ci) {
+      const float* xr = xs + ci * XW;
+      const float* wr = ws + ci * p.k * CO_T + ty * 4;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        for (int m = 0; m < M; ++m) {
+          const int j = phi[i] + m * p.u;
+          if (j < p.k) {
+            const float4 w = *reinterpret_cast<const float4*>(wr + j * CO_T);
+            const float xv = xr[sl[i] - m];
+            acc[0][i] = fmaf(w.x, xv, acc[0][i]);
+            acc[1][i] = fmaf(w.y, xv, acc[1][i]);
+            acc[2][i] = fmaf(w.z, xv, acc[2][i]);
+            acc[3][i] = fmaf(w.w, xv, acc[3][i]);
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const int co = co0 + ty * 4 + c;
+    if (co >= p.Cout) continue;
+    const float bv = p.bias ? __ldg(p.bias + co) : 0.f;
+    const int64_t row = ((int64_t)b * p.Cout + co) * Tout;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int t = t0 + tx + 16 * i;
+      if (t < Tout) p.y[row + t] = acc[c][i] + bv;
+    }
+  }
+}
+}  // namespace
+
+int launch_conv_transpose1d_fp32(const ConvTParams& p, cudaStream_t s) {
+  if (p.B <= 0 || p.Cin <= 0 || p.Cout <= 0 || p.Tin <= 0 || p.k <= 0 || p.u <= 0)
+    return fail(AB_ERR_ARG, "conv_transpose1d: bad shape");
+  if (p.k < p.u || ((p.k - p.u) & 1))
+    return fail(AB_ERR_UNSUPPORTED,
+                "conv_transpose1d: kernel %d / stride %d: need k >= stride and (k - stride) even", p.k, p.u);
+  if (p.B > 65535) return fail(AB_ERR_UNSUPPORTED, "conv_transpose1d: batch %d > 65535", p.B);
+  const int M = (p.k + p.u - 1) / p.u;
+  const int XW = TT / p.u + 2 + M;
+  const size_t smem = sizeof(float) * ((size_t)CI_T * XW + (size_t)CI_T * p.k * CO_T);
+  if (smem > 200 * 1024) return fail(AB_ERR_UNSUPPORTED, "conv_transpose1d: kernel %d too large", p.k);
+  static bool configured = false;
+  if (smem > 48 * 1024 && !configured) {
+    AB_CUDA_TRY(cudaFuncSetAttribute(convT_fp32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     200 * 1024));
+    configured = true;
+  }
+  const int64_t Tout = (int64_t)p.Tin * p.u;
+  dim3 grid((unsigned)ceil_div(Tout, TT), (unsigned)ceil_div(p.Cout, CO_T), (unsigned)p.B);
+  convT_fp32_kernel<<<grid, NT, smem, s>>>(p, XW, M);
+  AB_LAUNCH_CHECK("convT_fp32_kernel");
+  return AB_OK;
+}
+
+// ===========================================================================
+// Activation1d(Snake|SnakeBeta): up-FIR x2 -> snake -> down-FIR /2, replicate
+// edges, never materialising the 2x-rate tensor in HBM.
+//   up   (resample.py:36-45):  u[2q]   = 2 sum_m f[11-2m] xh[q-3+m]
+//                              u[2q+1] = 2 sum_m f[10-2m] xh[q-2+m],  xh = replicate(x)
+//   act  (snake.py:51-61,110-122): v = u + 1/(b+1e-9) * sin(u*a)^2
+//   down (filter.py:92-99):    y[t] = sum_j f[j] v[clamp(2t+j-5, 0, 2T-1)]
+// One CTA per (batch, channel, 1024-sample tile).  HBM-bound by design
+// (4 B read + 4 B written per element).
+// ===========================================================================
+namespace {
+constexpr int AT = 1024;
+
+__device__ __forceinline__ float snake_eval(float u, float a, float invb) {
+  // sin(u*a)^2 with explicit range reduction to [-pi, pi] before the MUFU
+  const float arg = u * a;
+  const float kf = rintf(arg * 0.15915494309189535f);
+  float r = fmaf(-kf, 6.2831854820251465f, arg);
+  r = fmaf(-kf, -1.7484555314695172e-07f, r);
+  const float sv = __sinf(r);
+  return fmaf(invb, sv * sv, u);
+}
+
+__global__ void __launch_bounds__(NT) activation1d_kernel(SnakeParams p) {
+  __shared__ float xs[AT + 13];
+  __shared__ float ve[AT + 6];
+  __shared__ float vo[AT + 6];
+  __shared__ float fu[12], fd[12];
+  const int t0 = blockIdx.x * AT, c = blockIdx.y, b = blockIdx.z;
+  const int T = p.T;
+  const float* xr = p.x + ((int64_t)b * p.C + c) * T;
+  float* yr = p.y + ((int64_t)b * p.C + c) * T;
+  if (threadIdx.x < 12) {
+    fu[threadIdx.x] = __ldg(p.f_up + threadIdx.x);
+    fd[threadIdx.x] = __ldg(p.f_down + threadIdx.x);
+  }
+  float a = __ldg(p.alpha + c), bb = __ldg(p.beta + c);
+  if (p.logscale) {
+    a = expf(a);
+    bb = expf(bb);
+  }
+  const float invb = 1.0f / (bb + 1e-9f);
+  for (int n = threadIdx.x; n < AT + 13; n += NT) {
+    int t = t0 - 6 + n;
+    t = min(max(t, 0), T - 1);
+    xs[n] = __ldg(xr + t);
+  }
+  __syncthreads();
+  const int i0 = 2 * t0 - 5;
+  const int imax = 2 * T - 1;
+  for (int n = threadIdx.x; n < 2 * AT + 12; n += NT) {
+    const int ic = min(max(i0 + n, 0), imax);
+    const int q = ic >> 1, odd = ic & 1;
+    const float* xp = xs + (q + 3 + odd - t0);
+    const float* fp = fu + (11 - odd);
+    float u = 0.f;
+#pragma unroll
+    for (int m = 0; m < 6; ++m) u = fmaf(fp[-2 * m], xp[m], u);
+    u *= 2.0f;
+    const float v = snake_eval(u, a, invb);
+    if (n & 1) vo[n >> 1] = v; else ve[n >> 1] = v;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < AT / NT; ++r) {
+    const int tl = threadIdx.x + NT * r;
+    const int t = t0 + tl;
+    if (t >= T) continue;
+    float y = 0.f;
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+      y = fmaf(fd[2 * j], ve[tl + j], y);
+      y = fmaf(fd[2 * j + 1], vo[tl + j], y);
+    }
+    yr[t] = y;
+  }
+}
+}  // namespace
+
+int launch_activation1d(const SnakeParams& p, cudaStream_t s) {
+  if (p.B <= 0 || p.C <= 0 || p.T <= 0) return fail(AB_ERR_ARG, "activation1d: bad shape");
+  if (p.C > 65535 || p.B > 65535) return fail(AB_ERR_UNSUPPORTED, "activation1d: B or C > 65535");
+  dim3 grid((unsigned)ceil_div(p.T, AT), (unsigned)p.C, (unsigned)p.B);
+  activation1d_kernel<<<grid, NT, 0, s>>>(p);
+  AB_LAUNCH_CHECK("activation1d_kernel");
+  return AB_OK;
+}
+
+// ===========================================================================
+// Weight repack (+ weight-norm fold, old-style torch.nn.utils.weight_norm with
+// dim=0: w = g * v / ||v||_{dims != 0}; hifigan.py:157-199):
+// src row r = dim 0.  Conv1d: src [Cout][Cin][k]; ConvTranspose1d: [Cin][Cout][k].
+// dst is always [Cin][k][Cout] so the conv kernels read it coalesced.
+// ===========================================================================
+namespace {
+__global__ void __launch_bounds__(256) repack_weight_kernel(const float* __restrict__ v,
+                                                            const float* __restrict__ g,
+                                                            float* __restrict__ dst, int d0, int d1,
+                                                            int k, int transposed) {
+  __shared__ float red[8];
+  __shared__ float scale_s;
+  const int r = blockIdx.x;
+  const int n = d1 * k;
+  const float* row = v + (int64_t)r * n;
+  float scale = 1.0f;
+  if (g != nullptr) {
+    float ss = 0.f;
+    for (int i = threadIdx.x; i < n; i += 256) {
+      const float x = row[i];
+      ss = fmaf(x, x, ss);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float tot = 0.f;
+      for (int w = 0; w < 8; ++w) tot += red[w];
+      scale_s = g[r] / sqrtf(tot);
+    }
+    __syncthreads();
+    scale = scale_s;
+  }
+  const int Cout = transposed ? d1 : d0;
+  for (int i = threadIdx.x; i < n; i += 256) {
+    const int inner = i / k, j = i - inner * k;
+    const int ci = transposed ? r : inner;
+    const int co = transposed ? inner : r;
+    dst[((int64_t)ci * k + j) * Cout + co] = row[i] * scale;
+  }
+}
+}  // namespace
+
+int launch_repack_weight(const float* v, const float* g, float* dst, int d0, int d1, int k,
+                         int transposed, cudaStream_t s) {
+  if (d0 <= 0 || d1 <= 0 || k <= 0) return fail(AB_ERR_ARG, "repack_weight: bad shape");
+  repack_weight_kernel<<<d0, 256, 0, s>>>(v, g, dst, d0, d1, k, transposed);
+  AB_LAUNCH_CHECK("repack_weight_kernel");
+  return AB_OK;
+}
+
+}  // namespace ab

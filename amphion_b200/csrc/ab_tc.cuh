@@ -1,0 +1,35 @@
+// Tensor-core (tcgen05 / TMEM / bulk-TMA) convolution path — interface.
+#pragma once
+#include "ab_common.cuh"
+
+namespace ab {
+
+// One launch = nconv (1 or 2) k-tap "same" convolutions over C channels:
+//   nconv == 2:  y = ((conv2(lrelu(conv1(lrelu(x,pre),d1)+b1, mid), 1)+b2) + residual + acc_prev) / out_div
+//   nconv == 1:  y = ((conv1(lrelu(x,pre),d1)+b1) + residual + acc_prev) / out_div
+// i.e. one (c1, c2) step of ResBlock1.forward (hifigan.py:93-100) or one step
+// of ResBlock2.forward (:139-144), plus the branch mix of hifigan.py:208-214.
+struct TcConvParams {
+  const float* x;         // contiguous [B, C, T] fp32
+  float* y;               // contiguous [B, C, T] fp32
+  const float* residual;  // nullable
+  const float* acc_prev;  // nullable
+  const void* w1;         // operand image built by launch_tc_pack_weight
+  const float* b1;
+  const void* w2;         // nullable when nconv == 1
+  const float* b2;
+  int B, C, T;
+  int k, d1, nconv;
+  float pre_slope, mid_slope, out_div;
+  int precision;          // AB_PREC_TC_F16 | AB_PREC_TC_BF16
+};
+
+int tc_max_channels();
+bool tc_conv_supported(int C, int k);
+size_t tc_weight_image_bytes(int cin, int cout, int k);
+// w_t: fp32 [Cin][k][Cout] (the repacked fp32 image) -> 16-bit operand image
+int launch_tc_pack_weight(const float* w_t, void* image, int cin, int cout, int k, int precision,
+                          cudaStream_t s);
+int launch_tc_conv(const TcConvParams& p, cudaStream_t s);
+
+}  // namespace ab

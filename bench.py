@@ -1,0 +1,306 @@
+#!/usr/bin/env python
+"""bench.py — vocoder audio samples/s on B200 (BASELINE.json metric, config 2).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port)
+
+Workload (config.workload): HiFi-GAN V1 22.05 kHz generator forward, batch 64
+per GPU, 80x1024 synthetic mel (random-init weights, torch.manual_seed(1234)).
+A "step" is one generator forward over the per-GPU batch (+ one NCCL all-gather
+of the wav shards when N > 1; weak scaling: the utterance batch grows with N).
+`value` times the device-resident path with CUDA events; `e2e` times the
+reference-facing call (vocoder_inference) with pinned HOST buffers, H2D and D2H
+inside the timed region.  One JSON line on stdout (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "vocoder_audio_samples_per_sec_22.05kHz"
+UNIT = "samples/s"
+HP_V1 = dict(resblock="1", upsample_rates=[8, 8, 2, 2], upsample_kernel_sizes=[16, 16, 4, 4],
+             upsample_initial_channel=512, resblock_kernel_sizes=[3, 7, 11],
+             resblock_dilation_sizes=[[1, 3, 5]] * 3)
+N_MEL, HOP = 80, 256
+FLOP_PER_SAMPLE = 2398848          # conv FLOPs per output sample, HiFi-GAN V1
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--batch", type=int, default=64, help="utterances per GPU")
+    ap.add_argument("--frames", type=int, default=1024)
+    ap.add_argument("--precision", default=os.environ.get("AMPHION_B200_PRECISION", "tc_f16"))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def make_cfg():
+    from types import SimpleNamespace as NS
+    pre = NS(n_mel=N_MEL, hop_size=HOP, extract_amplitude_phase=False)
+    return NS(preprocess=pre, model=NS(generator="hifigan", hifigan=NS(**HP_V1)))
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tensor_burst=d["bf16_tflops"], tensor=d["bf16_tflops_sustained"],
+                    source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm=6650.0, tensor_burst=1590.0, tensor=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+# --------------------------------------------------------------------------
+# CPU baseline: the oracle port (oracle/generator.py follows the reference's
+# hifigan.py:203-219 op for op with the same torch CPU primitives)
+# --------------------------------------------------------------------------
+def cpu_oracle_samples_per_sec(frames, batch=2, repeats=2):
+    import torch
+    from oracle import generator as og
+    from amphion_b200.vocoders.hifigan import HiFiGAN
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(1234)
+    model = HiFiGAN(make_cfg())
+    sd = {k: v.detach().numpy() for k, v in model.state_dict().items()}
+    params = {}
+    for k in list(sd):  # fold weight norm once, like remove_weight_norm(), outside the timed region
+        if k.endswith(".weight_v"):
+            params[k[:-2]] = og.fold_weight_norm(sd[k], sd[k[:-2] + "_g"])
+        elif not k.endswith(".weight_g"):
+            params[k] = sd[k]
+    mel = torch.randn(batch, N_MEL, frames, generator=torch.Generator().manual_seed(0))
+    og.hifigan_forward(params, HP_V1, mel[:1, :, : min(frames, 64)])      # warm-up
+    best = float("inf")
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        og.hifigan_forward(params, HP_V1, mel)
+        best = min(best, time.perf_counter() - t0)
+    return batch * frames * HOP / best, cores, best, f"B={batch} slice at full T={frames}, best of {repeats}"
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return 0
+    vals = []
+    for _ in range(max(1, args.warmup) - 1):
+        pass
+    total_t = 0.0
+    v = cores = None
+    sample = ""
+    steps = max(1, args.steps)
+    per = []
+    for i in range(steps):
+        v, cores, dt, sample = cpu_oracle_samples_per_sec(args.frames, batch=1, repeats=1)
+        per.append(dt)
+        total_t += dt
+        if total_t > 150:      # keep the whole run within a few minutes
+            steps = i + 1
+            break
+    ms = statistics.mean(per) * 1e3
+    value = args.frames * HOP / (ms / 1e3)
+    line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=args.gpus, steps=steps, warmup=args.warmup,
+                ms_per_step=ms, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
+                data="synthetic", impl="reference",
+                config=dict(workload="HiFi-GAN V1 22.05kHz generator forward, 80x%d mel" % args.frames,
+                            sample="each step = one B=1 utterance at full T on the host CPU (conv cost is linear in B)"),
+                cpu_baseline=dict(value=value, unit=UNIT, cores=cores, kind="port",
+                                  sample="B=1 utterance at full T=%d per step, all host threads" % args.frames),
+                e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line))
+    return 0
+
+
+# --------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu, self.proc, self.path = gpu_index, None, f"/tmp/ab_clocks_{os.getpid()}.csv"
+
+    def start(self):
+        try:
+            self.f = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.f.close()
+        sm, mx, reasons, pw = [], [], set(), []
+        for ln in open(self.path):
+            c = [x.strip() for x in ln.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1])); mx.append(float(c[2])); pw.append(float(c[3]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        try:
+            os.remove(self.path)
+        except OSError:
+            pass
+        if not sm:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["no samples"])
+        return dict(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons),
+                    power_w_max=max(pw), samples=len(sm))
+
+
+def run_native(args, rank, local_rank, world):
+    import torch
+    import torch.distributed as dist
+    from amphion_b200.vocoders import vocoder_inference
+    from amphion_b200.vocoders.hifigan import HiFiGAN
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    cfg = make_cfg()
+    torch.manual_seed(1234)
+    model = HiFiGAN(cfg).to(dev).eval()
+    model.precision = args.precision
+    B, T = args.batch, args.frames
+    mel = torch.randn(B, N_MEL, T, generator=torch.Generator().manual_seed(rank)).to(dev)
+    samples_step = world * B * T * HOP
+    gathered = torch.empty(world * B, 1, T * HOP, device=dev) if world > 1 else None
+
+    def step():
+        wav = model(mel)
+        if world > 1:   # the path's one collective: final gather of the wav shards
+            dist.all_gather_into_tensor(gathered, wav)
+        return wav
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    with torch.no_grad():
+        for _ in range(max(args.warmup, 3)):
+            step()
+        torch.cuda.synchronize()
+        sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sampler.start()
+        model.set_profiling(True)
+        model.get_profile()
+        barrier(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            step()
+        e1.record()
+        torch.cuda.synchronize(); barrier()
+        ms_total = e0.elapsed_time(e1)
+        prof = model.get_profile()
+        model.set_profiling(False)
+        clocks = sampler.stop() if rank == 0 else None
+        launches = model.last_launches * args.steps
+
+        # ---- end to end through the reference-facing call, host buffers ----
+        mel_host = mel.cpu().pin_memory()
+        for _ in range(2):
+            vocoder_inference(cfg, model, mel_host, device=dev)
+        barrier(); torch.cuda.synchronize()
+        t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+        t0.record()
+        for _ in range(args.steps):
+            out_host = vocoder_inference(cfg, model, mel_host, device=dev)   # H2D + forward + D2H (+sync)
+            if world > 1:
+                dist.all_gather_into_tensor(gathered, out_host.to(dev, non_blocking=True).unsqueeze(1))
+        t1.record()
+        torch.cuda.synchronize(); barrier()
+        e2e_ms_total = t0.elapsed_time(t1)
+
+    tms = torch.tensor([ms_total, e2e_ms_total], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    ms_total, e2e_ms_total = tms.tolist()
+    ms_step = ms_total / args.steps
+    value = samples_step / (ms_step / 1e3)
+    e2e_value = samples_step / (e2e_ms_total / args.steps / 1e3)
+
+    if rank == 0:
+        pk = peaks()
+        dom = "tc_conv" if prof["tc_conv"]["launches"] else "conv1d_fp32"
+        d = prof[dom]
+        tf = d["flops"] / (d["ms"] / 1e3) / 1e12 if d["ms"] > 0 else 0.0
+        gbs = d["bytes"] / (d["ms"] / 1e3) / 1e9 if d["ms"] > 0 else 0.0
+        roofline = dict(bound="tensor", kernel=dom + "_kernel", achieved=tf, peak=pk["tensor"], unit="TFLOP/s",
+                        frac=tf / pk["tensor"], traffic=None, peak_source=pk["source"] + ", bf16 sustained",
+                        launches=d["launches"], avg_launch_ms=d["ms"] / max(d["launches"], 1),
+                        share_of_step=d["ms"] / ms_total,
+                        hbm=dict(achieved=gbs, peak=pk["hbm"], unit="GB/s", frac=gbs / pk["hbm"],
+                                 note="algorithmic bytes of the fused pair (x read + y write + weights once)"),
+                        whole_step=dict(tflops=samples_step / world * FLOP_PER_SAMPLE / (ms_step / 1e3) / 1e12,
+                                        frac_of_tensor_peak=samples_step / world * FLOP_PER_SAMPLE / (ms_step / 1e3) / 1e12 / pk["tensor"]),
+                        classes={k: dict(launches=v["launches"], ms=round(v["ms"], 3)) for k, v in prof.items()})
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            v, cores, dt, sample = cpu_oracle_samples_per_sec(T, batch=2, repeats=2)
+            cpu = dict(value=v, unit=UNIT, cores=cores, kind="port", sample=sample, seconds=dt)
+        dt = {"fp32": "f32", "tc_f16": "f16 operands, f32 accumulate (tcgen05); f32 elsewhere",
+              "tc_bf16": "bf16 operands, f32 accumulate (tcgen05); f32 elsewhere"}[args.precision]
+        line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
+                    ms_per_step=ms_step, higher_is_better=True, scaling="weak", vs_baseline=None, dtype=dt,
+                    data="synthetic",
+                    config=dict(workload="HiFi-GAN V1 22.05kHz generator forward, batch=%d per GPU, 80x%d synthetic mel"
+                                         % (B, T), global_batch=world * B, frames=T, hop=HOP, precision=args.precision,
+                                parallelism="utterance-batch sharding dp%d, NCCL all-gather of wav" % world,
+                                l2="no explicit flush: each step streams >8 GB of stage tensors (>> 126 MB L2)"),
+                    e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=world * B * N_MEL * T * 4,
+                             d2h_bytes_per_step=world * B * T * HOP * 4, ms_per_step=e2e_ms_total / args.steps),
+                    gpu_launches=launches, clocks=clocks, roofline=roofline, cpu_baseline=cpu, impl="native")
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.gpus > 1 and world == 1 and "RANK" not in os.environ:
+        # convenience: re-launch under torchrun exactly as the driver does
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", os.environ.get("MASTER_PORT", "29533"),
+               os.path.abspath(__file__)] + sys.argv[1:]
+        return subprocess.call(cmd)
+    if args.impl == "reference":
+        return run_reference(args, rank)
+    return run_native(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,202 @@
+/*
+ * amphion_b200 — C ABI of the B200-native vocoder-inference hot path.
+ *
+ * The reference (open-mmlab/Amphion) is pure Python: it has no FFI.  Its
+ * "operator API" for this path is the duck-typed Python surface listed in
+ * SURVEY.md §8(b).  Each entry point below names the reference interface it
+ * sits under (paths relative to the reference root); the Python mirror of that
+ * interface lives in amphion_b200/ and is the only caller.  INTEGRATION.md
+ * shows the ctypes stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - plain C types only; every pointer named dev_* is a CUDA device pointer
+ *     owned by the caller (allocated by PyTorch) and outlives the call.  The
+ *     library never allocates or frees device memory and never synchronises:
+ *     all work is enqueued on the `stream` argument (a cudaStream_t passed as
+ *     void*, 0 = legacy default stream).
+ *   - every function returns AB_OK (0) or a negative AB_ERR_* code;
+ *     ab_last_error() returns a thread-local, human readable message.
+ *   - a handle may be used by one host thread at a time.
+ */
+#ifndef AMPHION_B200_H_
+#define AMPHION_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AB_OK 0
+#define AB_ERR_ARG (-1)         /* null pointer, bad shape, unknown tensor name */
+#define AB_ERR_UNSUPPORTED (-2) /* valid request this build cannot serve */
+#define AB_ERR_CUDA (-3)        /* a CUDA runtime / cuFFT call failed */
+#define AB_ERR_STATE (-4)       /* call order violated (e.g. forward before finalize) */
+#define AB_ERR_WORKSPACE (-5)   /* workspace / arena too small */
+
+#define AB_MAX_STAGES 8
+#define AB_MAX_KERNELS 8
+#define AB_MAX_DILATIONS 8
+
+enum ab_generator_kind { AB_GEN_HIFIGAN = 0, AB_GEN_BIGVGAN = 1 };
+enum ab_activation { AB_ACT_LRELU = 0, AB_ACT_SNAKE = 1, AB_ACT_SNAKEBETA = 2 };
+/* arithmetic of the k-tap channel-mixing convolutions */
+enum ab_precision {
+  AB_PREC_FP32 = 0,   /* CUDA-core FFMA, fp32 operands and accumulation */
+  AB_PREC_TC_F16 = 1, /* tcgen05.mma kind::f16, fp16 operands (saturating cvt), fp32 accumulation in TMEM */
+  AB_PREC_TC_BF16 = 2 /* tcgen05.mma kind::f16, bf16 operands, fp32 accumulation in TMEM */
+};
+
+const char* ab_last_error(void);
+int ab_version(void);
+/* 1 if the current device is compute capability 10.x (tcgen05 path usable) */
+int ab_device_is_sm100(void);
+
+/* ------------------------------------------------------------------------
+ * Generator: HiFiGAN.forward  (models/vocoders/gan/generator/hifigan.py:203-219)
+ *            BigVGAN.forward  (models/vocoders/gan/generator/bigvgan.py:313-331)
+ * The config mirrors cfg.model.{hifigan,bigvgan}.* + cfg.preprocess.n_mel
+ * (hifigan.py:151-201, bigvgan.py:232-311).
+ * ---------------------------------------------------------------------- */
+typedef struct ab_generator ab_generator;
+
+typedef struct ab_generator_config {
+  int32_t kind;                                 /* ab_generator_kind */
+  int32_t n_mel;                                /* cfg.preprocess.n_mel */
+  int32_t upsample_initial_channel;
+  int32_t num_upsamples;
+  int32_t upsample_rates[AB_MAX_STAGES];
+  int32_t upsample_kernel_sizes[AB_MAX_STAGES];
+  int32_t resblock;                             /* 1 = ResBlock1/AMPBlock1, 2 = ResBlock2/AMPBlock2 */
+  int32_t num_kernels;
+  int32_t resblock_kernel_sizes[AB_MAX_KERNELS];
+  int32_t num_dilations[AB_MAX_KERNELS];
+  int32_t resblock_dilation_sizes[AB_MAX_KERNELS][AB_MAX_DILATIONS];
+  int32_t activation;                           /* ab_activation; LRELU for HiFi-GAN */
+  int32_t snake_logscale;                       /* cfg.model.bigvgan.snake_logscale */
+} ab_generator_config;
+
+int ab_generator_create(const ab_generator_config* cfg, ab_generator** out);
+void ab_generator_destroy(ab_generator* g);
+
+/* Parameter arena: the caller allocates ab_generator_param_bytes() of device
+ * memory (256-byte aligned) and binds it; load_* calls repack into it. */
+size_t ab_generator_param_bytes(const ab_generator* g);
+int ab_generator_bind_params(ab_generator* g, void* dev_arena, size_t bytes);
+
+/* Number / names of the tensors the generator expects, in reference
+ * state-dict naming with weight norm folded away: "conv_pre.weight",
+ * "conv_pre.bias", "ups.0.weight" ("ups.0.0.weight" for BigVGAN),
+ * "resblocks.3.convs1.2.weight", "resblocks.3.activations.4.act.alpha",
+ * "resblocks.3.activations.4.upsample.filter", .... */
+int ab_generator_num_tensors(const ab_generator* g);
+const char* ab_generator_tensor_name(const ab_generator* g, int index);
+
+/* Load one fp32 tensor (contiguous, device) by name.  shape must match the
+ * reference state-dict shape. */
+int ab_generator_load_tensor(ab_generator* g, const char* name, const float* dev_src,
+                             const int64_t* shape, int32_t ndim, void* stream);
+/* Load "<name>" from its weight-norm decomposition (old-style
+ * torch.nn.utils.weight_norm, dim=0: hifigan.py:157-199): w = g*v/||v||,
+ * norm over all dims but 0.  shape is the shape of v. */
+int ab_generator_load_weight_norm(ab_generator* g, const char* name, const float* dev_g,
+                                  const float* dev_v, const int64_t* shape, int32_t ndim, void* stream);
+/* After all tensors are loaded: pick the conv arithmetic and build the packed
+ * operand images it needs.  Fails with AB_ERR_STATE if a tensor is missing. */
+int ab_generator_finalize(ab_generator* g, int32_t precision, void* stream);
+
+size_t ab_generator_workspace_bytes(const ab_generator* g, int64_t batch, int64_t frames);
+/* mel [B, n_mel, T] fp32 with arbitrary element strides (the reference feeds
+ * transposed views: models/vocoders/vocoder_inference.py:349,505)
+ * -> wav [B, 1, T*prod(upsample_rates)] fp32 contiguous. */
+int ab_generator_forward(ab_generator* g, const float* dev_mel, int64_t batch, int64_t frames,
+                         const int64_t mel_strides[3], float* dev_wav, void* dev_workspace,
+                         size_t workspace_bytes, void* stream);
+/* number of kernels the last forward enqueued (bench.py's gpu_launches) */
+int ab_generator_last_launches(const ab_generator* g);
+
+/* Per-kernel-class device timing for the roofline report: when enabled, every
+ * launch inside ab_generator_forward is bracketed by CUDA events on `stream`.
+ * ab_generator_get_profile synchronises on the recorded events, accumulates
+ * (launches, milliseconds, algorithmic FLOPs, algorithmic HBM bytes) per class
+ * since the last call, and resets.  Classes: "tc_conv", "conv1d_fp32",
+ * "conv_transpose1d_fp32", "activation1d". */
+typedef struct ab_profile_entry {
+  char name[32];
+  int32_t launches;
+  float ms;
+  double flops;   /* 2*MACs of the convolutions as the reference defines them */
+  double bytes;   /* compulsory fp32 tensor reads+writes of the launch + its weights once */
+} ab_profile_entry;
+int ab_generator_set_profiling(ab_generator* g, int32_t enable);
+int ab_generator_get_profile(ab_generator* g, ab_profile_entry* out, int32_t max_entries, int32_t* n_out);
+
+/* ------------------------------------------------------------------------
+ * Activation1d(Snake|SnakeBeta).forward  (modules/anti_aliasing/act.py:31-36,
+ * resample.py:36-45,62-65, filter.py:92-99, activation_functions/snake.py:51-61,110-122)
+ * standalone: x [B,C,T] -> y [B,C,T], both contiguous fp32.  beta may alias alpha (Snake).
+ * ---------------------------------------------------------------------- */
+int ab_activation1d_forward(const float* dev_x, float* dev_y, int64_t batch, int64_t channels,
+                            int64_t length, const float* dev_alpha, const float* dev_beta,
+                            int32_t logscale, const float* dev_filter_up12,
+                            const float* dev_filter_down12, void* stream);
+
+/* ------------------------------------------------------------------------
+ * Building blocks exposed for parity tests (each is one launch of the kernel
+ * the generator itself uses).
+ * conv1d:  y = post( (bias + W * pre(x)) [+ residual] ), "same" zero padding,
+ *          F.conv1d semantics of hifigan.py:96-99.  w is [Cout, Cin, k].
+ * conv_transpose1d: nn.ConvTranspose1d(stride=u, padding=(k-u)/2) of
+ *          hifigan.py:176-186.  w is [Cin, Cout, k].
+ * pre_slope: 1.0 = no activation, otherwise leaky_relu negative slope.
+ * ---------------------------------------------------------------------- */
+int ab_conv1d_forward(const float* dev_x, const float* dev_w, const float* dev_bias,
+                      const float* dev_residual, float* dev_y, int64_t batch, int64_t cin,
+                      int64_t cout, int64_t length, int32_t ksize, int32_t dilation,
+                      float pre_slope, int32_t post_tanh, int32_t precision,
+                      void* dev_workspace, size_t workspace_bytes, void* stream);
+size_t ab_conv1d_workspace_bytes(int64_t cin, int64_t cout, int32_t ksize, int32_t precision);
+int ab_conv_transpose1d_forward(const float* dev_x, const float* dev_w, const float* dev_bias,
+                                float* dev_y, int64_t batch, int64_t cin, int64_t cout,
+                                int64_t length_in, int32_t ksize, int32_t stride, float pre_slope,
+                                void* dev_workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------
+ * Mel front end:
+ *   extract_mel_features / mel_spectrogram_torch / extract_linear_features
+ *     (utils/mel.py:20-170): pad = (n_fft-hop)/2, eps = 1e-9 / 1e-6
+ *   TacotronSTFT.mel_spectrogram (utils/stft.py:259-278 over STFT.transform
+ *     :152-181): pad = n_fft/2, eps = 0, with_energy
+ * Pipeline: reflect-pad + frame + window kernel -> cuFFT R2C (the libcufft.so.11
+ * already loaded in the process, i.e. the one torch.stft uses) -> fused
+ * |.|, mel filterbank, log(clamp) kernel.
+ * ---------------------------------------------------------------------- */
+typedef struct ab_mel ab_mel;
+
+typedef struct ab_mel_config {
+  int32_t n_fft;
+  int32_t hop;
+  int32_t win;      /* window length; the window is centred in n_fft (torch.stft / pad_center) */
+  int32_t n_mel;    /* 0 = magnitude only (extract_linear_features) */
+  int32_t pad;      /* reflect padding per side */
+  float eps;        /* added under the sqrt */
+  float clamp;      /* log(clamp(x, min=clamp)); 1e-5 in the reference */
+} ab_mel_config;
+
+int ab_mel_create(const ab_mel_config* cfg, ab_mel** out);
+void ab_mel_destroy(ab_mel* m);
+int64_t ab_mel_num_frames(const ab_mel* m, int64_t samples);
+size_t ab_mel_workspace_bytes(const ab_mel* m, int64_t batch, int64_t samples);
+/* wav [B,T] contiguous; window [win]; mel_basis [n_mel, n_fft/2+1];
+ * outputs (each may be NULL): magnitude [B, n_fft/2+1, F], mel [B, n_mel, F],
+ * energy [B, F] (l2 norm of the magnitude over bins, utils/stft.py:276). */
+int ab_mel_forward(ab_mel* m, const float* dev_wav, int64_t batch, int64_t samples,
+                   const float* dev_window, const float* dev_mel_basis, float* dev_magnitude,
+                   float* dev_mel, float* dev_energy, void* dev_workspace, size_t workspace_bytes,
+                   void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AMPHION_B200_H_ */

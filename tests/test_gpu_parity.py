@@ -1,0 +1,355 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI / the Python
+mirrors of the reference interface) against the CPU oracle and the committed
+reference-generated golden fixtures.  Tolerances are stated per test; the
+north-star bar is 1e-3 max-abs on the generator output, fp32."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN_MODELS, load_golden
+from helpers import HP_BIGVGAN_BASE, HP_V1, build_model, golden_model, make_cfg, randomize_snake, sd_numpy
+from oracle import generator as og
+from oracle import mel as om
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _ws(nbytes):
+    t = torch.empty(nbytes + 256, dtype=torch.uint8, device=DEV)
+    return t, C.c_void_p((t.data_ptr() + 255) // 256 * 256)
+
+
+def run_conv1d(x, w, b, res, k, d, pre_slope, tanh, precision="fp32"):
+    from amphion_b200 import _capi
+    B, cin, T = x.shape
+    cout = w.shape[0]
+    xd, wd = torch.from_numpy(x).to(DEV), torch.from_numpy(w).to(DEV)
+    bd = torch.from_numpy(b).to(DEV) if b is not None else None
+    rd = torch.from_numpy(res).to(DEV) if res is not None else None
+    y = torch.empty(B, cout, T, device=DEV)
+    prec = _capi.PRECISIONS[precision]
+    n = _capi.lib.ab_conv1d_workspace_bytes(cin, cout, k, prec)
+    keep, ws = _ws(n)
+    _capi.check(_capi.lib.ab_conv1d_forward(_capi.ptr(xd), _capi.ptr(wd), _capi.ptr(bd), _capi.ptr(rd), _capi.ptr(y),
+                                            B, cin, cout, T, k, d, pre_slope, int(tanh), prec, ws, n,
+                                            _capi.stream_ptr()), "ab_conv1d_forward")
+    torch.cuda.synchronize()
+    return y.cpu().numpy()
+
+
+def oracle_conv1d(x, w, b, res, k, d, pre_slope, tanh, operand_dtype=None):
+    xa = og.leaky_relu_np(x, pre_slope) if pre_slope != 1.0 else x
+    wa = w
+    if operand_dtype is not None:  # model the tensor path: operands rounded, fp32+ accumulation
+        xa = torch.from_numpy(xa).to(operand_dtype).double().numpy()
+        wa = torch.from_numpy(w).to(operand_dtype).double().numpy()
+        y = torch.nn.functional.conv1d(torch.from_numpy(xa), torch.from_numpy(wa), None, dilation=d,
+                                       padding=og.get_padding(k, d)).numpy()
+        y = y + (b[None, :, None].astype(np.float64) if b is not None else 0)
+    else:
+        y = og.conv1d(xa, wa, b, d, og.get_padding(k, d)).numpy().astype(np.float64)
+    if res is not None:
+        y = y + res
+    if tanh:
+        y = np.tanh(y)
+    return y.astype(np.float32)
+
+
+CONV_CASES = [
+    # B, cin, cout, T, k, d, pre_slope, residual, tanh
+    (2, 5, 7, 50, 3, 1, 1.0, False, False),
+    (1, 16, 64, 300, 7, 3, 0.1, True, False),
+    (2, 80, 96, 129, 7, 1, 1.0, False, False),       # conv_pre-like, cout not a multiple of 64
+    (1, 32, 32, 1000, 11, 5, 0.1, True, False),
+    (2, 24, 24, 77, 5, 12, 0.1, True, False),        # ResBlock2-style wide dilation, T < halo*2
+    (3, 32, 1, 2500, 7, 1, 0.01, False, True),       # conv_post + tanh (few-out kernel, multi-tile)
+    (1, 9, 2, 5, 7, 1, 1.0, False, False),           # T shorter than the filter
+    (1, 4, 4, 1, 3, 1, 0.1, True, False),            # single sample
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv1d_fp32_matches_oracle(case):
+    B, cin, cout, T, k, d, slope, use_res, tanh = case
+    rng = np.random.default_rng(hash(case) % 2**32)
+    x = rng.standard_normal((B, cin, T)).astype(np.float32)
+    w = (rng.standard_normal((cout, cin, k)) / np.sqrt(cin * k)).astype(np.float32)
+    b = rng.standard_normal(cout).astype(np.float32)
+    res = rng.standard_normal((B, cout, T)).astype(np.float32) if use_res else None
+    got = run_conv1d(x, w, b, res, k, d, slope, tanh)
+    want = oracle_conv1d(x, w, b, res, k, d, slope, tanh)
+    np.testing.assert_allclose(got, want, atol=2e-5, rtol=1e-5)   # fp32, summation order only
+
+
+@pytest.mark.parametrize("case", [(2, 6, 5, 40, 8, 4), (1, 64, 32, 130, 16, 8), (2, 32, 16, 257, 4, 2),
+                                  (1, 8, 8, 1, 4, 2), (1, 16, 70, 33, 8, 4), (1, 12, 12, 50, 7, 3)])
+@pytest.mark.parametrize("slope", [1.0, 0.1])
+def test_conv_transpose1d_matches_oracle(case, slope):
+    from amphion_b200 import _capi
+    B, cin, cout, T, k, u = case
+    rng = np.random.default_rng(sum(case))
+    x = rng.standard_normal((B, cin, T)).astype(np.float32)
+    w = (rng.standard_normal((cin, cout, k)) / np.sqrt(cin)).astype(np.float32)
+    b = rng.standard_normal(cout).astype(np.float32)
+    xd, wd, bd = (torch.from_numpy(a).to(DEV) for a in (x, w, b))
+    y = torch.empty(B, cout, T * u, device=DEV)
+    keep, ws = _ws(w.nbytes)
+    _capi.check(_capi.lib.ab_conv_transpose1d_forward(_capi.ptr(xd), _capi.ptr(wd), _capi.ptr(bd), _capi.ptr(y), B, cin,
+                                                      cout, T, k, u, slope, ws, w.nbytes, _capi.stream_ptr()),
+                "ab_conv_transpose1d_forward")
+    want = og.conv_transpose1d(og.leaky_relu_np(x, slope), w, b, u, (k - u) // 2).numpy()
+    np.testing.assert_allclose(y.cpu().numpy(), want, atol=2e-5, rtol=1e-5)
+
+
+def test_conv_transpose1d_rejects_odd_geometry():
+    from amphion_b200 import _capi
+    x = torch.zeros(1, 2, 4, device=DEV)
+    w = torch.zeros(2, 2, 5, device=DEV)
+    y = torch.zeros(1, 2, 8, device=DEV)
+    keep, ws = _ws(1024)
+    rc = _capi.lib.ab_conv_transpose1d_forward(_capi.ptr(x), _capi.ptr(w), None, _capi.ptr(y), 1, 2, 2, 4, 5, 2, 1.0,
+                                               ws, 1024, _capi.stream_ptr())
+    assert rc == -2 and "even" in _capi.last_error()
+
+
+def test_activation1d_matches_reference_fixture_and_oracle():
+    from amphion_b200.vocoders.activations import Activation1d, SnakeBeta, Snake
+    g, _ = load_golden("activation1d")
+    act = Activation1d(SnakeBeta(6, alpha_logscale=True)).to(DEV)
+    with torch.no_grad():
+        act.act.alpha.copy_(torch.from_numpy(g["alpha"]))
+        act.act.beta.copy_(torch.from_numpy(g["beta"]))
+    y = act(torch.from_numpy(g["x"]).to(DEV)).cpu().numpy()
+    np.testing.assert_allclose(y, g["y"], atol=5e-6)     # reference module output
+    rng = np.random.default_rng(1)
+    for (B, Cn, T, logscale, cls) in [(1, 3, 1, True, SnakeBeta), (2, 2, 2, False, Snake), (1, 5, 7, True, Snake),
+                                      (2, 4, 1024, True, SnakeBeta), (1, 3, 2049, False, SnakeBeta),
+                                      (1, 2, 5000, True, SnakeBeta)]:
+        a = Activation1d(cls(Cn, alpha_logscale=logscale)).to(DEV)
+        with torch.no_grad():
+            a.act.alpha.normal_(0.0 if logscale else 1.0, 0.3)
+            if cls is SnakeBeta:
+                a.act.beta.normal_(0.0 if logscale else 1.0, 0.3)
+        x = (rng.standard_normal((B, Cn, T)) * 3).astype(np.float32)
+        got = a(torch.from_numpy(x).to(DEV)).cpu().numpy()
+        beta = a.act.beta if cls is SnakeBeta else a.act.alpha
+        want = og.activation1d_np(x, a.act.alpha.detach().cpu().numpy(), beta.detach().cpu().numpy(), logscale,
+                                  g["f_up"], g["f_down"])
+        np.testing.assert_allclose(got, want, atol=2e-5, rtol=1e-5)
+
+
+@pytest.mark.parametrize("name", sorted(GOLDEN_MODELS))
+def test_generator_fp32_matches_reference_fixture(name):
+    kind, hp, g, sd, model = golden_model(name)
+    model = model.to(DEV)
+    model.precision = "fp32"
+    wav = model(torch.from_numpy(g["mel"]).to(DEV))
+    assert wav.shape == g["wav"].shape and wav.dtype == torch.float32 and wav.is_cuda
+    np.testing.assert_allclose(wav.cpu().numpy(), g["wav"], atol=2e-5)   # bar: 1e-3
+    assert model.last_launches > 0
+
+
+@pytest.mark.parametrize("name", sorted(GOLDEN_MODELS))
+def test_generator_tensor_core_matches_reference_fixture(name):
+    kind, hp, g, sd, model = golden_model(name)
+    model = model.to(DEV)
+    for prec, tol in (("tc_f16", 2e-4), ("tc_bf16", 1e-3)):
+        model.precision = prec
+        wav = model(torch.from_numpy(g["mel"]).to(DEV)).cpu().numpy()
+        assert np.isfinite(wav).all()
+        assert np.abs(wav - g["wav"]).max() <= tol, (prec, np.abs(wav - g["wav"]).max())
+
+
+TC_CASES = [
+    # C, T, k, d   (single conv through the tcgen05 kernel)
+    (64, 128, 1, 1),      # pure GEMM: no tap shifts
+    (64, 200, 3, 1),      # tap shifts of one row
+    (32, 1000, 3, 3),
+    (128, 700, 7, 3),
+    (256, 600, 11, 5),    # V1 stage-0 worst case, multi-tile
+    (48, 333, 5, 2),      # channels padded 48 -> 48 (16-multiple), K chunk of 16 left over
+    (24, 90, 3, 1),       # channels padded 24 -> 32
+    (256, 50, 11, 1),     # sequence shorter than one tile
+]
+
+
+@pytest.mark.parametrize("case", TC_CASES)
+@pytest.mark.parametrize("prec", ["tc_f16", "tc_bf16"])
+def test_tc_conv1d_matches_operand_rounded_oracle(case, prec):
+    C_, T, k, d = case
+    rng = np.random.default_rng(C_ * 1000 + T + k)
+    x = rng.standard_normal((2, C_, T)).astype(np.float32)
+    w = (rng.standard_normal((C_, C_, k)) / np.sqrt(C_ * k)).astype(np.float32)
+    b = rng.standard_normal(C_).astype(np.float32)
+    res = rng.standard_normal((2, C_, T)).astype(np.float32)
+    got = run_conv1d(x, w, b, res, k, d, 0.1, False, precision=prec)
+    dt = torch.float16 if prec == "tc_f16" else torch.bfloat16
+    want = oracle_conv1d(x, w, b, res, k, d, 0.1, False, operand_dtype=dt)
+    # identical operands, fp32 accumulation in a different order: tight
+    np.testing.assert_allclose(got, want, atol=3e-5, rtol=1e-5)
+    exact = oracle_conv1d(x, w, b, res, k, d, 0.1, False)
+    assert np.abs(got - exact).max() < (3e-3 if prec == "tc_f16" else 3e-2)
+
+
+def _full_size_case(kind, hp, n_mel, B, T, seed):
+    model = build_model(kind, hp, n_mel, seed=seed)
+    if kind == "bigvgan":
+        randomize_snake(model, seed + 1, hp["snake_logscale"])
+    g = torch.Generator().manual_seed(seed + 2)
+    mel = torch.randn(B, n_mel, T, generator=g)
+    want = og.generator_forward(kind, sd_numpy(model), hp, mel.numpy())
+    return model.to(DEV), mel, want
+
+
+@pytest.mark.parametrize("prec,tol", [("fp32", 5e-5), ("tc_f16", 1e-3)])
+def test_hifigan_v1_full_width_matches_oracle(prec, tol):
+    """BASELINE config 1/2 architecture (512 ch, rates 8.8.2.2) at a CPU-checkable size."""
+    model, mel, want = _full_size_case("hifigan", HP_V1, 80, 2, 40, seed=1234)
+    model.precision = prec
+    got = model(mel.to(DEV)).cpu().numpy()
+    assert got.shape == (2, 1, 40 * 256)
+    assert np.abs(got - want).max() <= tol, np.abs(got - want).max()
+
+
+@pytest.mark.parametrize("prec,tol", [("fp32", 1e-4), ("tc_f16", 1e-3)])
+def test_bigvgan_base_full_width_matches_oracle(prec, tol):
+    """BASELINE config 3 architecture (snakebeta, logscale, 100 mels) at a CPU-checkable size."""
+    model, mel, want = _full_size_case("bigvgan", HP_BIGVGAN_BASE, 100, 1, 24, seed=77)
+    model.precision = prec
+    got = model(mel.to(DEV)).cpu().numpy()
+    assert np.abs(got - want).max() <= tol, np.abs(got - want).max()
+
+
+@pytest.mark.parametrize("prec", ["fp32", "tc_f16"])
+def test_generator_properties_at_scale(prec):
+    """Size-independent properties on a batch the CPU oracle cannot afford:
+    batch independence, strided (transposed-view) input == contiguous input,
+    time-tiling invariance (a long sequence equals the oracle on a window far
+    from the edges is covered above; here: same mel twice in a batch gives
+    bit-identical rows), output range of tanh."""
+    model = build_model("hifigan", HP_V1, 80, seed=5).to(DEV)
+    model.precision = prec
+    g = torch.Generator().manual_seed(9)
+    mel = torch.randn(4, 80, 512, generator=g).to(DEV)
+    mel[3] = mel[1]
+    wav = model(mel)
+    assert wav.shape == (4, 1, 512 * 256)
+    assert torch.isfinite(wav).all() and wav.abs().max() <= 1.0
+    assert torch.equal(wav[3], wav[1])                                   # batch independence, deterministic
+    single = model(mel[2:3])
+    assert torch.equal(single[0], wav[2])                                # B=1 == row of the batch
+    tview = mel.transpose(1, 2).contiguous().transpose(1, 2)             # [B,T,n_mel] storage, as vocoder_inference.py:349
+    assert not tview.is_contiguous()
+    assert torch.equal(model(tview), wav)
+    # zero-padding on the right only changes samples near the pad (receptive field), SURVEY Q12
+    padded = torch.nn.functional.pad(mel[:1], (0, 64))
+    wp = model(padded)[..., : 512 * 256]
+    far = (512 - 40) * 256
+    assert torch.equal(wp[..., :far], wav[:1, :, :far])
+
+
+def test_plumbing_matches_reference_fixture():
+    from amphion_b200.vocoders import synthesis_audios, vocoder_inference
+    kind, hp, g0, sd, model = golden_model("hifigan_rb1")
+    model = model.to(DEV)
+    model.precision = "fp32"
+    g, _ = load_golden("plumbing")
+    cfg = model.cfg
+    mels = [torch.from_numpy(g[f"mel{i}"]) for i in range(3)]
+    auds = synthesis_audios(cfg, model, mels, batch_size=2)
+    for i, a in enumerate(auds):
+        assert a.device.type == "cpu" and a.dtype == torch.float32
+        assert a.shape == g[f"audio{i}"].shape
+        np.testing.assert_allclose(a.numpy(), g[f"audio{i}"], atol=2e-5)
+    out = vocoder_inference(cfg, model, torch.from_numpy(g["batched_in"]), device=DEV)
+    assert out.device.type == "cpu" and out.shape == g["batched_out"].shape
+    np.testing.assert_allclose(out.numpy(), g["batched_out"], atol=2e-5)
+
+
+def test_synthesis_loads_reference_checkpoint_formats(tmp_path):
+    from amphion_b200.vocoders.vocoder_inference import synthesis
+    kind, hp, g0, sd, model = golden_model("hifigan_rb1")
+    cfg = model.cfg
+    cfg.model.generator = "hifigan"
+    tsd = {("module." + k): torch.from_numpy(v) for k, v in sd.items()}
+    p = tmp_path / "legacy.pt"
+    torch.save({"generator_state_dict": tsd}, p)
+    g, _ = load_golden("plumbing")
+    pred = [g[f"mel{i}"].T.copy() for i in range(3)]            # [T, n_mel] as the recipes pass them
+    auds = synthesis(cfg, str(p), 3, pred, batch_size=2)
+    for i, a in enumerate(auds):
+        assert np.abs(a.numpy() - g[f"audio{i}"]).max() < 1e-3  # default precision (tensor cores)
+
+
+def test_mel_matches_reference_fixture():
+    from types import SimpleNamespace as NS
+    from amphion_b200 import mel
+    g, _ = load_golden("mel")
+    cfgp = NS(sample_rate=22050, n_fft=1024, n_mel=80, fmin=0, fmax=8000, win_size=1024, hop_size=256)
+    y = torch.from_numpy(g["y"]).to(DEV)
+    m = mel.extract_mel_features(y, cfgp)
+    assert m.shape == (2, 80, 32) and m.is_cuda
+    np.testing.assert_allclose(m.cpu().numpy(), g["extract_mel_features"], atol=2e-4)
+    np.testing.assert_allclose(mel.mel_spectrogram_torch(y, cfgp).cpu().numpy(), g["mel_spectrogram_torch"], atol=2e-4)
+    np.testing.assert_allclose(mel.extract_linear_features(y, cfgp).cpu().numpy(), g["extract_linear_features"],
+                               atol=2e-4, rtol=1e-4)
+    assert mel.extract_mel_features(y[:1], cfgp).shape == (80, 32)       # the reference's squeeze(0)
+    cfg2 = NS(sample_rate=16000, n_fft=512, n_mel=40, fmin=50, fmax=7600, win_size=400, hop_size=160)
+    m2 = mel.extract_mel_features(torch.from_numpy(g["y2"]).to(DEV), cfg2)
+    np.testing.assert_allclose(m2.cpu().numpy(), g["extract_mel_features2"], atol=2e-4)
+
+
+def test_mel_magnitude_is_bit_identical_to_torch_stft_on_device():
+    """North-star: 'mel extractor bit-pattern-equal given identical FFT backend'.
+    Same fp32 window multiply, same cuFFT, same |.| arithmetic as utils/mel.py:145-166
+    executed by torch on this GPU."""
+    from types import SimpleNamespace as NS
+    from amphion_b200 import mel
+    cfgp = NS(sample_rate=22050, n_fft=1024, n_mel=80, fmin=0, fmax=8000, win_size=1024, hop_size=256)
+    g = torch.Generator().manual_seed(3)
+    y = ((torch.rand(4, 22050, generator=g) * 2 - 1) * 0.9).to(DEV)
+    win = torch.hann_window(1024).to(DEV)
+    yp = torch.nn.functional.pad(y.unsqueeze(1), (384, 384), mode="reflect").squeeze(1)
+    spec = torch.stft(yp, 1024, hop_length=256, win_length=1024, window=win, center=False, pad_mode="reflect",
+                      normalized=False, onesided=True, return_complex=True)
+    ref = torch.sqrt(torch.view_as_real(spec).pow(2).sum(-1) + 1e-9)
+    got = mel.extract_linear_features(y, cfgp)
+    assert got.shape == ref.shape
+    nbad = int((got != ref).sum())
+    assert nbad == 0, f"{nbad} of {ref.numel()} magnitudes differ, max abs {float((got - ref).abs().max())}"
+    basis = mel.librosa_mel_fn(22050, 1024, 80, 0, 8000).to(DEV)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    ref_mel = torch.log(torch.clamp(torch.matmul(basis, ref), min=1e-5))
+    assert (mel.extract_mel_features(y, cfgp) - ref_mel).abs().max() <= 1e-5   # cuBLAS summation order only
+
+
+def test_tacotron_stft_matches_reference_fixture():
+    from amphion_b200.stft import TacotronSTFT
+    g, _ = load_golden("mel")
+    taco = TacotronSTFT(1024, 256, 1024, 80, 22050, 0, 8000)
+    np.testing.assert_allclose(taco.mel_basis.numpy(), g["taco_mel_basis"], atol=1e-7)
+    m, e = taco.mel_spectrogram(torch.from_numpy(g["y"]))                # CPU in, CPU out, like the reference
+    assert m.device.type == "cpu" and m.shape == (2, 80, 33) and e.shape == (2, 33)
+    np.testing.assert_allclose(m.numpy(), g["taco_mel"], atol=3e-4)
+    np.testing.assert_allclose(e.numpy(), g["taco_energy"], rtol=2e-4)
+    with pytest.raises(AssertionError):
+        taco.mel_spectrogram(torch.from_numpy(g["y"]) * 2)
+
+
+def test_mel_full_size_properties():
+    """BASELINE config 4 shape: 64 x 10 s @ 22.05 kHz -> mel [64, 80, 862]."""
+    from amphion_b200.stft import TacotronSTFT
+    g = torch.Generator().manual_seed(0)
+    y = (torch.rand(64, 220500, generator=g) * 2 - 1) * 0.9
+    taco = TacotronSTFT(1024, 256, 1024, 80, 22050, 0, 8000)
+    m, e = taco.mel_spectrogram(y)
+    assert m.shape == (64, 80, 862) and e.shape == (64, 862)
+    assert torch.isfinite(m).all() and m.min() >= np.log(1e-5) - 1e-6
+    mo, eo = om.tacotron_mel(y[:1, :8192].numpy(), taco.mel_basis.numpy(), 1024, 256, 1024)
+    # frames whose support lies inside the first 8192-512 samples are identical to the short run
+    np.testing.assert_allclose(m[0, :, :28].numpy(), mo[0, :, :28], atol=3e-4)
+    m2, _ = taco.mel_spectrogram(y[5:6])
+    assert torch.equal(m2[0], m[5])                                       # batch independence

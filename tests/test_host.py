@@ -1,0 +1,140 @@
+"""CPU-only checks of the host side: the C-ABI library loads and exports every
+symbol the header declares, argument errors surface as exceptions, the module
+mirrors keep the reference's parameter names / init order, and nothing falls
+back to the CPU."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN_MODELS, ROOT, load_golden
+from helpers import build_model, make_cfg
+
+
+def test_library_exports_every_declared_symbol():
+    from amphion_b200 import _capi
+    header = open(os.path.join(ROOT, "include", "amphion_b200.h")).read()
+    declared = set(re.findall(r"\b(ab_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    assert declared == set(_capi.SIGNATURES), declared ^ set(_capi.SIGNATURES)
+    for name in declared:
+        assert hasattr(_capi.lib, name), name
+    assert _capi.lib.ab_version() >= 100
+    assert os.path.dirname(_capi.LIB_PATH).endswith("amphion_b200")  # in-tree, not site-packages
+
+
+def test_create_rejects_bad_configs():
+    from amphion_b200 import _capi
+    h = C.c_void_p()
+    cfg = _capi.GeneratorConfig()
+    assert _capi.lib.ab_generator_create(C.byref(cfg), C.byref(h)) == -1
+    assert "n_mel" in _capi.last_error()
+    with pytest.raises(RuntimeError, match="ab_generator_create"):
+        _capi.check(_capi.lib.ab_generator_create(C.byref(cfg), C.byref(h)), "ab_generator_create")
+    assert _capi.lib.ab_generator_create(None, C.byref(h)) == -1
+    m = C.c_void_p()
+    assert _capi.lib.ab_mel_create(C.byref(_capi.MelConfig(1023, 256, 1024, 80, 0, 0.0, 1e-5)), C.byref(m)) == -1
+
+
+def test_handle_lifecycle_and_tensor_table_without_gpu():
+    from amphion_b200 import _capi
+    kind, hp, n_mel = GOLDEN_MODELS["bigvgan_rb1"]
+    model = build_model(kind, hp, n_mel)
+    h = model._ensure_handle()
+    names = [_capi.lib.ab_generator_tensor_name(h, i).decode() for i in range(_capi.lib.ab_generator_num_tensors(h))]
+    sd = model.state_dict()
+    for n in names:  # every tensor the library wants exists in the module (folded or weight-normed)
+        assert n in sd or (n + "_v" in sd and n + "_g" in sd), n
+    assert "ups.0.0.weight" in names and "resblocks.5.activations.5.act.beta" in names
+    assert _capi.lib.ab_generator_param_bytes(h) > sum(v.numel() * 4 for k, v in sd.items() if k.endswith("_v"))
+    assert _capi.lib.ab_generator_workspace_bytes(h, 2, 21) > 0
+    # forward before bind/finalize is a state error, not a crash
+    rc = _capi.lib.ab_generator_forward(h, C.c_void_p(8), 1, 4, _capi.shape_array((1, 1, 1)), C.c_void_p(8),
+                                        C.c_void_p(256), 1 << 30, None)
+    assert rc == -4 and "finalize" in _capi.last_error()
+
+
+@pytest.mark.parametrize("name", sorted(GOLDEN_MODELS))
+def test_state_dict_keys_and_shapes_match_reference(name):
+    kind, hp, n_mel = GOLDEN_MODELS[name]
+    _, sd = load_golden(name)
+    model = build_model(kind, hp, n_mel)
+    msd = model.state_dict()
+    assert list(msd.keys()) == list(sd.keys())          # same names, same order
+    for k in sd:
+        assert tuple(msd[k].shape) == sd[k].shape, k
+    model.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()}, strict=True)
+
+
+def test_seeded_init_reproduces_reference_weights():
+    # the reference fixture was built with torch.manual_seed(1234); HiFiGAN(cfg):
+    # same construction order => same RNG stream => identical parameters
+    kind, hp, n_mel = GOLDEN_MODELS["hifigan_rb1"]
+    _, sd = load_golden("hifigan_rb1")
+    model = build_model(kind, hp, n_mel, seed=1234)
+    for k, v in model.state_dict().items():
+        np.testing.assert_array_equal(v.numpy(), sd[k], err_msg=k)
+
+
+def test_remove_weight_norm_keeps_loadable_names(capsys):
+    kind, hp, n_mel = GOLDEN_MODELS["hifigan_rb2"]
+    model = build_model(kind, hp, n_mel, seed=3)
+    w = torch._weight_norm(model.conv_pre.weight_v, model.conv_pre.weight_g, 0).detach().clone()
+    model.remove_weight_norm()
+    assert "conv_pre.weight" in model.state_dict() and "conv_pre.weight_v" not in model.state_dict()
+    torch.testing.assert_close(model.conv_pre.weight.detach(), w)
+    assert "Removing weight norm" in capsys.readouterr().out
+
+
+def test_no_cpu_fallback():
+    kind, hp, n_mel = GOLDEN_MODELS["hifigan_rb1"]
+    model = build_model(kind, hp, n_mel, seed=0)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        model(torch.zeros(1, n_mel, 8))
+    from amphion_b200.vocoders.activations import Activation1d, SnakeBeta
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        Activation1d(SnakeBeta(4))(torch.zeros(1, 4, 8))
+    from amphion_b200 import mel
+    cfgp = make_cfg("hifigan", hp, 80).preprocess
+    cfgp.sample_rate, cfgp.n_fft, cfgp.fmin, cfgp.fmax, cfgp.win_size = 22050, 1024, 0, 8000, 1024
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        mel.extract_mel_features(torch.zeros(1, 4096), cfgp)
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "amphion_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), os.path.join(dirpath, f)
+
+
+def test_pad_mels_to_tensors_matches_reference_layout():
+    from amphion_b200.util import pad_mels_to_tensors
+    from oracle import generator as og
+    mels = [torch.randn(5, t) for t in (7, 3, 9, 4, 6)]
+    for bs in (None, 2, 5, 8):
+        ts, fr = pad_mels_to_tensors(mels, bs)
+        ots, ofr = og.pad_mels([m.numpy() for m in mels], bs)
+        assert len(ts) == len(ots)
+        for a, b, f, of in zip(ts, ots, fr, ofr):
+            np.testing.assert_array_equal(a.numpy(), b)
+            np.testing.assert_array_equal(f.numpy(), of)
+    assert pad_mels_to_tensors([], 4) == ([], [])
+
+
+def test_kaiser_filter_matches_reference_buffer():
+    from amphion_b200.vocoders.activations import kaiser_sinc_filter1d
+    g, _ = load_golden("activation1d")
+    np.testing.assert_allclose(kaiser_sinc_filter1d(0.25, 0.3, 12).reshape(-1).numpy(), g["f_up"], atol=1e-8)
+
+
+def test_mel_filterbank_host_matches_oracle():
+    from amphion_b200 import mel
+    from oracle import mel as om
+    for args in [(22050, 1024, 80, 0, 8000), (16000, 512, 40, 50, 7600), (24000, 1024, 100, 0, None)]:
+        np.testing.assert_allclose(mel.librosa_mel_fn(*args).numpy(), om.slaney_mel_filterbank(*args), atol=1e-7)
