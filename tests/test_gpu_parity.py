@@ -352,4 +352,5 @@ def test_mel_full_size_properties():
     # frames whose support lies inside the first 8192-512 samples are identical to the short run
     np.testing.assert_allclose(m[0, :, :28].numpy(), mo[0, :, :28], atol=3e-4)
     m2, _ = taco.mel_spectrogram(y[5:6])
-    assert torch.equal(m2[0], m[5])                                       # batch independence
+    # batch independence (cuFFT may pick a different plan for another batch count: not bit-equal)
+    torch.testing.assert_close(m2[0], m[5], atol=2e-5, rtol=0)
