@@ -75,8 +75,9 @@ SIGNATURES = {
     "ab_conv1d_forward": (C.c_int, [_P, _P, _P, _P, _P, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int32,
                                     C.c_int32, C.c_float, C.c_int32, C.c_int32, _P, C.c_size_t, _P]),
     "ab_conv1d_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int64, C.c_int32, C.c_int32]),
+    "ab_conv_transpose1d_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32]),
     "ab_conv_transpose1d_forward": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_int64, C.c_int64, C.c_int64,
-                                              C.c_int32, C.c_int32, C.c_float, _P, C.c_size_t, _P]),
+                                              C.c_int32, C.c_int32, C.c_float, C.c_int32, _P, C.c_size_t, _P]),
     "ab_mel_create": (C.c_int, [C.POINTER(MelConfig), C.POINTER(_P)]),
     "ab_mel_destroy": (None, [_P]),
     "ab_mel_num_frames": (C.c_int64, [_P, C.c_int64]),

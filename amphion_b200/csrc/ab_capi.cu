@@ -51,6 +51,7 @@ struct Slot {
   // tensor-core operand image (built by finalize when precision != fp32)
   size_t tc_offset;
   size_t tc_bytes;
+  int stride;         // ConvTranspose1d stride (SLOT_CONVT_W)
 };
 
 struct ConvRef {   // one weight-normed conv of the model
@@ -127,6 +128,7 @@ struct ab_generator {
     s.loaded = false;
     s.tc_offset = 0;
     s.tc_bytes = 0;
+    s.stride = 1;
     fp32_bytes += align_up(s.bytes, 256);
     slots.push_back(s);
     index[name] = (int)slots.size() - 1;
@@ -220,6 +222,7 @@ int ab_generator_create(const ab_generator_config* cfg, ab_generator** out) {
     // BigVGAN wraps each transposed conv in a ModuleList: key "ups.{i}.0" (bigvgan.py:254-276)
     const std::string upname = "ups." + std::to_string(i) + (big ? ".0" : "");
     st.up = make_conv(g, upname, cin, ch, cfg->upsample_kernel_sizes[i], 1, true);
+    g->slots[st.up.w].stride = st.u;
     for (int j = 0; j < cfg->num_kernels; ++j) {
       BlockRef blk;
       blk.k = cfg->resblock_kernel_sizes[j];
@@ -251,6 +254,10 @@ int ab_generator_create(const ab_generator_config* cfg, ab_generator** out) {
   for (auto& s : g->slots) {
     if (s.kind == SLOT_CONV_W) {
       s.tc_bytes = tc_weight_image_bytes((int)s.shape[1], (int)s.shape[0], (int)s.shape[2]);
+      s.tc_offset = g->fp32_bytes + tc;
+      tc += align_up(s.tc_bytes, 256);
+    } else if (s.kind == SLOT_CONVT_W) {
+      s.tc_bytes = gc_weight_image_bytes(1, (int)s.shape[0], (int)s.shape[1], (int)s.shape[2], s.stride);
       s.tc_offset = g->fp32_bytes + tc;
       tc += align_up(s.tc_bytes, 256);
     }
@@ -335,9 +342,13 @@ int ab_generator_finalize(ab_generator* g, int32_t precision, void* stream) {
     if (!ab_device_is_sm100()) return fail(AB_ERR_UNSUPPORTED, "finalize: tensor-core precision needs an sm_100 device");
     for (size_t i = 0; i < g->slots.size(); ++i) {
       Slot& s = g->slots[i];
-      if (s.kind != SLOT_CONV_W) continue;
-      int rc = launch_tc_pack_weight(g->fptr((int)i), g->tcptr((int)i), (int)s.shape[1], (int)s.shape[0],
-                                     (int)s.shape[2], precision, st);
+      int rc = AB_OK;
+      if (s.kind == SLOT_CONV_W)
+        rc = launch_tc_pack_weight(g->fptr((int)i), g->tcptr((int)i), (int)s.shape[1], (int)s.shape[0],
+                                   (int)s.shape[2], precision, st);
+      else if (s.kind == SLOT_CONVT_W && s.tc_bytes)
+        rc = launch_gc_pack_weight(g->fptr((int)i), g->tcptr((int)i), 1, (int)s.shape[0], (int)s.shape[1],
+                                   (int)s.shape[2], s.stride, precision, st);
       if (rc != AB_OK) return rc;
     }
   }
@@ -378,9 +389,9 @@ int ab_generator_set_profiling(ab_generator* g, int32_t enable) {
 
 int ab_generator_get_profile(ab_generator* g, ab_profile_entry* out, int32_t max_entries, int32_t* n_out) {
   if (!g || !out || !n_out) return fail(AB_ERR_ARG, "get_profile: null argument");
-  static const char* kNames[4] = {"tc_conv", "conv1d_fp32", "conv_transpose1d_fp32", "activation1d"};
-  if (max_entries < 4) return fail(AB_ERR_ARG, "get_profile: need room for 4 entries");
-  for (int i = 0; i < 4; ++i) {
+  static const char* kNames[5] = {"tc_conv", "conv1d_fp32", "conv_transpose1d_fp32", "activation1d", "tc_gemmconv"};
+  if (max_entries < 5) return fail(AB_ERR_ARG, "get_profile: need room for 5 entries");
+  for (int i = 0; i < 5; ++i) {
     memset(&out[i], 0, sizeof(out[i]));
     strncpy(out[i].name, kNames[i], sizeof(out[i].name) - 1);
   }
@@ -396,7 +407,7 @@ int ab_generator_get_profile(ab_generator* g, ab_profile_entry* out, int32_t max
     g->event_pool.push_back(r.e1);
   }
   g->prof_recs.clear();
-  *n_out = 4;
+  *n_out = 5;
   return AB_OK;
 }
 
@@ -505,7 +516,16 @@ int ab_generator_forward(ab_generator* g, const float* dev_mel, int64_t B, int64
       prof_begin(2, 2.0 * eo * cin * ((double)sg.up.k / sg.u),
                  4.0 * ((double)B * cin * Tn + eo + (double)cin * sg.ch * sg.up.k));
     }
-    rc = launch_conv_transpose1d_fp32(tp, st);
+    if (tc && g->slots[sg.up.w].tc_bytes) {
+      GcParams gp;
+      gp.x = R[cur_r]; gp.y = U; gp.w = g->tcptr(sg.up.w); gp.bias = g->fptr(sg.up.b); gp.residual = nullptr;
+      gp.B = (int)B; gp.Cin = cin; gp.Cout = sg.ch; gp.Tin = Tn; gp.mode = 1; gp.k = sg.up.k; gp.d = 1; gp.u = sg.u;
+      gp.pre_slope = tp.pre_slope; gp.post_tanh = 0; gp.precision = g->precision;
+      if (g->profiling) g->prof_recs.back().cls = 4;
+      rc = launch_gemmconv(gp, st);
+    } else {
+      rc = launch_conv_transpose1d_fp32(tp, st);
+    }
     prof_end();
     if (rc != AB_OK) return rc;
     Tn *= sg.u;
@@ -634,17 +654,34 @@ int ab_conv1d_forward(const float* dev_x, const float* dev_w, const float* dev_b
   return launch_tc_conv(p, st);
 }
 
+size_t ab_conv_transpose1d_workspace_bytes(int64_t cin, int64_t cout, int32_t k, int32_t u, int32_t precision) {
+  size_t n = align_up((size_t)cin * cout * k * sizeof(float), 256);
+  if (precision != AB_PREC_FP32) n += align_up(gc_weight_image_bytes(1, (int)cin, (int)cout, k, u), 256);
+  return n;
+}
+
 int ab_conv_transpose1d_forward(const float* dev_x, const float* dev_w, const float* dev_bias,
                                 float* dev_y, int64_t B, int64_t cin, int64_t cout, int64_t Tin,
-                                int32_t k, int32_t u, float pre_slope, void* ws, size_t ws_bytes,
-                                void* stream) {
+                                int32_t k, int32_t u, float pre_slope, int32_t precision, void* ws,
+                                size_t ws_bytes, void* stream) {
   if (!dev_x || !dev_w || !dev_y || !ws) return fail(AB_ERR_ARG, "conv_transpose1d: null argument");
-  if (ws_bytes < (size_t)cin * cout * k * sizeof(float)) return fail(AB_ERR_WORKSPACE, "conv_transpose1d: workspace too small");
+  if (ws_bytes < ab_conv_transpose1d_workspace_bytes(cin, cout, k, u, precision)) return fail(AB_ERR_WORKSPACE, "conv_transpose1d: workspace too small");
   if (Tin * u > (1ll << 30)) return fail(AB_ERR_UNSUPPORTED, "conv_transpose1d: sequence too long");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   float* w_t = static_cast<float*>(ws);
   int rc = launch_repack_weight(dev_w, nullptr, w_t, (int)cin, (int)cout, k, 1, st);
   if (rc != AB_OK) return rc;
+  if (precision != AB_PREC_FP32) {
+    void* img = static_cast<char*>(ws) + align_up((size_t)cin * cout * k * sizeof(float), 256);
+    if (gc_weight_image_bytes(1, (int)cin, (int)cout, k, u) == 0) return fail(AB_ERR_UNSUPPORTED, "conv_transpose1d: %s", ab_last_error());
+    rc = launch_gc_pack_weight(w_t, img, 1, (int)cin, (int)cout, k, u, precision, st);
+    if (rc != AB_OK) return rc;
+    GcParams gp;
+    gp.x = dev_x; gp.y = dev_y; gp.w = img; gp.bias = dev_bias; gp.residual = nullptr;
+    gp.B = (int)B; gp.Cin = (int)cin; gp.Cout = (int)cout; gp.Tin = (int)Tin; gp.mode = 1; gp.k = k; gp.d = 1; gp.u = u;
+    gp.pre_slope = pre_slope; gp.post_tanh = 0; gp.precision = precision;
+    return launch_gemmconv(gp, st);
+  }
   ConvTParams p;
   p.x = dev_x; p.w_t = w_t; p.bias = dev_bias; p.y = dev_y;
   p.B = (int)B; p.Cin = (int)cin; p.Cout = (int)cout; p.Tin = (int)Tin; p.k = k; p.u = u; p.pre_slope = pre_slope;

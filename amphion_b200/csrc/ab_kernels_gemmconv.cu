@@ -1,0 +1,442 @@
+// tcgen05 implicit-GEMM kernel with N blocking: ConvTranspose1d (polyphase) and wide Conv1d.
+//
+//   D[row, n] = sum_{tap} sum_{ci} A[row + shift(tap), ci] * W[nb][tap][n, ci]
+//   M = time rows (128 per MMA, m M-tiles per CTA), K = C_in per tap, N = one block of <= 256
+//   "virtual output channels"; the CTA walks NB such blocks over ONE resident activation tile.
+//
+// ConvTranspose1d(stride u, padding (k-u)/2)  (hifigan.py:176-186, 206-207; bigvgan.py:254-276):
+//   y[co, s*u - p + phi] = b[co] + sum_m sum_ci act(x)[ci, s - m] * W[ci, co, phi + u*m]
+//   -> rows = input times s, virtual channel n = co_local*u + phi, taps m = 0..ceil(k/u)-1,
+//   so every MAC is a useful one (no zero-stuffing) and a thread's TMEM row holds u consecutive
+//   output samples of each channel.
+// Conv1d ("same", dilation d): rows = output times, n = co, taps j = 0..k-1, shift j*d.
+//
+// TMEM is double buffered across N blocks (when NB > 1) so the epilogue of block nb overlaps the
+// MMAs of block nb+1.  Operand layouts and the warp roles are those of ab_kernels_tc.cu.
+#include <stdlib.h>
+
+#include <algorithm>
+
+#include "ab_tc.cuh"
+#include "ab_tc_ptx.cuh"
+
+namespace ab {
+
+using namespace tcx;
+
+namespace {
+
+constexpr int GC_WORKER_WARPS = 8;
+constexpr int GC_WORKERS = GC_WORKER_WARPS * 32;
+constexpr int GC_THREADS = GC_WORKERS + 64;
+constexpr int GC_MAX_STAGES = 8;
+constexpr uint32_t GC_SMEM_LIMIT = 227 * 1024;
+
+struct GcGeom {
+  int mode;        // 0 conv, 1 conv-transpose
+  int Kp, nkc;     // padded C_in, 32-channel chunks
+  int Nb, NB;      // N block width (multiple of 16) and count
+  int cc;          // convT: output channels per N block
+  int ntaps;
+  int m, nbuf;
+  int rowsA;
+  int tiles;       // per sequence
+  int nstages;
+  uint32_t stage_bytes;
+  uint32_t off_w, off_bias, off_bar, smem_bytes;
+  int row0_time;   // time of A row 0 is tile_origin - row0_time
+  int Tout;        // output length
+  int pad;         // convT: (k-u)/2
+  uint32_t idesc;
+  int layout;
+};
+
+__global__ void __launch_bounds__(GC_THREADS, 1) gemmconv_kernel(GcParams p, GcGeom g) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x / g.tiles, tile = blockIdx.x - b * g.tiles;
+  const int R0 = tile * g.m * 128;   // first output row (time for conv, input time s for convT)
+  const int bf16 = p.precision == AB_PREC_TC_BF16;
+
+  const uint32_t sA = smem_u32(smem);
+  const uint32_t sW = sA + g.off_w;
+  float* bias_s = reinterpret_cast<float*>(smem + g.off_bias);   // [Cout padded]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + g.off_bar);
+  const uint32_t bar0 = smem_u32(bars);
+  auto bar_full = [&](int s) { return bar0 + 8u * s; };
+  auto bar_empty = [&](int s) { return bar0 + 8u * (GC_MAX_STAGES + s); };
+  const uint32_t bar_aready = bar0 + 8u * (2 * GC_MAX_STAGES);
+  auto bar_accfull = [&](int q) { return bar0 + 8u * (2 * GC_MAX_STAGES + 1 + q); };
+  auto bar_accempty = [&](int q) { return bar0 + 8u * (2 * GC_MAX_STAGES + 3 + q); };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * GC_MAX_STAGES + 5);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < g.nstages; ++s) {
+      mbar_init(bar_full(s), 1);
+      mbar_init(bar_empty(s), 1);
+    }
+    mbar_init(bar_aready, GC_WORKERS);
+    for (int q = 0; q < 2; ++q) {
+      mbar_init(bar_accfull(q), 1);
+      mbar_init(bar_accempty(q), GC_WORKERS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    fence_proxy_async();
+  }
+  if (warp == GC_WORKER_WARPS + 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const int ncols_buf = g.m * g.Nb;
+
+  if (warp < GC_WORKER_WARPS) {
+    // ===================== workers =====================
+    const int nbias = g.mode ? g.NB * g.cc : g.NB * g.Nb;
+    for (int i = threadIdx.x; i < nbias; i += GC_WORKERS)
+      bias_s[i] = (p.bias != nullptr && i < p.Cout) ? __ldg(p.bias + i) : 0.f;
+    {
+      const int ngrp = (g.rowsA + 127) >> 7;
+      const int c8n = g.Kp >> 3;
+      const float* xb = p.x + (int64_t)b * p.Cin * p.Tin;
+      for (int item = warp; item < c8n * ngrp; item += GC_WORKER_WARPS) {
+        const int c8 = item / ngrp, grp = item - c8 * ngrp;
+        const int row0 = (grp << 7) + lane;
+        float v[4][8];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const int row = row0 + 32 * r;
+          const int t = R0 - g.row0_time + row;
+          const bool ok = row < g.rowsA && t >= 0 && t < p.Tin;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const int c = c8 * 8 + e;
+            v[r][e] = (ok && c < p.Cin) ? __ldg(xb + (int64_t)c * p.Tin + t) : 0.f;
+          }
+        }
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const int row = row0 + 32 * r;
+          if (row < g.rowsA) {
+            uint4 q;
+            q.x = pack2(lrelu(v[r][0], p.pre_slope), lrelu(v[r][1], p.pre_slope), bf16);
+            q.y = pack2(lrelu(v[r][2], p.pre_slope), lrelu(v[r][3], p.pre_slope), bf16);
+            q.z = pack2(lrelu(v[r][4], p.pre_slope), lrelu(v[r][5], p.pre_slope), bf16);
+            q.w = pack2(lrelu(v[r][6], p.pre_slope), lrelu(v[r][7], p.pre_slope), bf16);
+            *reinterpret_cast<uint4*>(smem + unit_offset(g.layout, g.rowsA, c8, row)) = q;
+          }
+        }
+      }
+    }
+    fence_proxy_async();
+    mbar_arrive(bar_aready);
+
+    const int q4 = warp & 3, hsel = warp >> 2;
+    const int nch = g.Nb >> 4;
+    for (int nb = 0; nb < g.NB; ++nb) {
+      const int buf = nb % g.nbuf;
+      mbar_wait(bar_accfull(buf), (uint32_t)(nb / g.nbuf) & 1u, 10);
+      tc_fence_after();
+      for (int i = 0; i < g.m; ++i) {
+        const int row = i * 128 + q4 * 32 + lane;
+        const uint32_t tbase = tmem + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(buf * ncols_buf + i * g.Nb);
+        for (int ch = hsel; ch < nch; ch += 2) {
+          uint32_t r[16];
+          tc_ld16(tbase + (uint32_t)(ch * 16), r);
+          tc_wait_ld();
+          if (g.mode == 0) {
+            const int t = R0 + row;
+            if (t < p.Tin) {
+#pragma unroll
+              for (int e = 0; e < 16; ++e) {
+                const int co = nb * g.Nb + ch * 16 + e;
+                if (co < p.Cout) {
+                  const int64_t idx = ((int64_t)b * p.Cout + co) * p.Tin + t;
+                  float v = __uint_as_float(r[e]) + bias_s[co];
+                  if (p.residual) v += __ldg(p.residual + idx);
+                  if (p.post_tanh) v = tanhf(v);
+                  p.y[idx] = v;
+                }
+              }
+            }
+          } else {
+            // row = input time s; columns n = co_local*u + phi hold y[co, s*u - pad + phi]
+            const int s = R0 + row;
+            const int tb = s * p.u - g.pad;
+            if (p.u == 8) {
+#pragma unroll
+              for (int half = 0; half < 2; ++half) {
+                const int col = nb * g.cc + ((ch * 16 + half * 8) >> 3);
+                if (col < p.Cout && col < (nb + 1) * g.cc) {
+                  float* yr = p.y + ((int64_t)b * p.Cout + col) * g.Tout;
+                  const float bv = bias_s[col];
+                  float o[8];
+#pragma unroll
+                  for (int e = 0; e < 8; ++e) o[e] = __uint_as_float(r[half * 8 + e]) + bv;
+                  if (tb >= 0 && tb + 8 <= g.Tout && ((tb & 3) == 0)) {
+                    *reinterpret_cast<float4*>(yr + tb) = make_float4(o[0], o[1], o[2], o[3]);
+                    *reinterpret_cast<float4*>(yr + tb + 4) = make_float4(o[4], o[5], o[6], o[7]);
+                  } else {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e)
+                      if (tb + e >= 0 && tb + e < g.Tout) yr[tb + e] = o[e];
+                  }
+                }
+              }
+            } else {
+#pragma unroll
+              for (int e = 0; e < 16; ++e) {
+                const int n = ch * 16 + e;
+                const int col = n / p.u, phi = n - col * p.u;
+                const int co = nb * g.cc + col;
+                const int t = tb + phi;
+                if (col < g.cc && co < p.Cout && t >= 0 && t < g.Tout)
+                  p.y[((int64_t)b * p.Cout + co) * g.Tout + t] = __uint_as_float(r[e]) + bias_s[co];
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(bar_accempty(buf));
+    }
+  } else if (warp == GC_WORKER_WARPS) {
+    // ===================== TMA weight producer =====================
+    if (lane == 0) {
+      const int total = g.NB * g.ntaps * g.nkc;
+      for (int it = 0; it < total; ++it) {
+        const int s = it % g.nstages;
+        const uint32_t ph = (uint32_t)(it / g.nstages) & 1u;
+        mbar_wait(bar_empty(s), ph ^ 1u, 20);
+        mbar_arrive_expect_tx(bar_full(s), g.stage_bytes);
+        bulk_g2s(sW + (uint32_t)s * g.stage_bytes, static_cast<const uint8_t*>(p.w) + (size_t)it * g.stage_bytes,
+                 g.stage_bytes, bar_full(s));
+      }
+    }
+  } else {
+    // ===================== MMA issuer =====================
+    const uint32_t elected = elect_one_sync();
+    const int nks_total = g.Kp >> 4;
+    const uint32_t rows16 = (uint32_t)g.rowsA, nb16 = (uint32_t)g.Nb;
+    uint64_t hiA, hiB;
+    uint32_t lboA_f, lboB_f, rowunit;
+    const uint32_t kstepA = 2u * rows16, kstepB = 2u * nb16;
+    if (g.layout == 0) {
+      hiA = hiB = (uint64_t)(8u | (1u << 14)) << 32;
+      lboA_f = rows16 << 16;
+      lboB_f = nb16 << 16;
+      rowunit = 1u;
+    } else {
+      hiA = hiB = ((uint64_t)(16u | (1u << 14)) << 32) | (6ull << 61);
+      lboA_f = lboB_f = 1u << 16;
+      rowunit = 2u;
+    }
+    const uint32_t a16 = sA >> 4, w16 = sW >> 4, stage16 = g.stage_bytes >> 4;
+    mbar_wait(bar_aready, 0, 30);
+    tc_fence_after();
+    int it = 0;
+    for (int nb = 0; nb < g.NB; ++nb) {
+      const int buf = nb % g.nbuf;
+      mbar_wait(bar_accempty(buf), ((uint32_t)(nb / g.nbuf) & 1u) ^ 1u, 32);
+      tc_fence_after();
+      for (int tap = 0; tap < g.ntaps; ++tap) {
+        const int shift = g.mode ? (g.ntaps - 1 - tap) : tap * p.d;
+        for (int kc = 0; kc < g.nkc; ++kc, ++it) {
+          const int s = it % g.nstages;
+          const uint32_t ph = (uint32_t)(it / g.nstages) & 1u;
+          mbar_wait(bar_full(s), ph, 31);
+          tc_fence_after();
+          const bool two = nks_total - kc * 2 >= 2;
+          uint32_t alo = (a16 + (uint32_t)(kc * 2) * kstepA + (uint32_t)shift * rowunit) | lboA_f;
+          const uint32_t blo = (w16 + (uint32_t)s * stage16) | lboB_f;
+          const uint32_t acc0 = (tap | kc) != 0 ? 1u : 0u;
+          uint32_t td = tmem + (uint32_t)(buf * ncols_buf);
+          for (int i = 0; i < g.m; ++i) {
+            if (elected) {
+              tc_mma_f16(td, hiA | alo, hiB | blo, g.idesc, acc0);
+              if (two) tc_mma_f16(td, hiA | (alo + kstepA), hiB | (blo + kstepB), g.idesc, 1u);
+            }
+            alo += 128u * rowunit;
+            td += (uint32_t)g.Nb;
+          }
+          if (elected) tc_commit(bar_empty(s));
+          __syncwarp();
+        }
+      }
+      if (elected) tc_commit(bar_accfull(buf));
+      __syncwarp();
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == GC_WORKER_WARPS + 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+  }
+}
+
+// image: [nb][tap][kc] stages, each [Nb rows x 32 channels] in the operand layout of ab_tc_ptx.cuh
+__global__ void gc_pack_weight_kernel(const float* __restrict__ w_t, uint16_t* __restrict__ img, GcGeom g,
+                                      int cin, int cout, int k, int d_or_u, int bf16) {
+  const int64_t per_stage = (int64_t)g.Nb * 32;
+  const int64_t total = (int64_t)g.NB * g.ntaps * g.nkc * per_stage;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int e = (int)(idx & 7);
+    int64_t r = idx >> 3;
+    const int n = (int)(r % g.Nb);
+    r /= g.Nb;
+    const int c8l = (int)(r & 3);
+    r >>= 2;
+    const int kc = (int)(r % g.nkc);
+    r /= g.nkc;
+    const int tap = (int)(r % g.ntaps);
+    const int nb = (int)(r / g.ntaps);
+    const int ci = kc * 32 + c8l * 8 + e;
+    float v = 0.f;
+    if (g.mode == 0) {
+      const int co = nb * g.Nb + n;
+      if (ci < cin && co < cout) v = w_t[((int64_t)ci * k + tap) * cout + co];
+    } else {
+      const int u = d_or_u;
+      const int col = n / u, phi = n - col * u;
+      const int co = nb * g.cc + col;
+      const int j = phi + u * tap;
+      if (ci < cin && col < g.cc && co < cout && j < k) v = w_t[((int64_t)ci * k + j) * cout + co];
+    }
+    uint16_t bits;
+    if (bf16) {
+      __nv_bfloat16 h = __float2bfloat16_rn(v);
+      bits = *reinterpret_cast<uint16_t*>(&h);
+    } else {
+      v = fminf(fmaxf(v, -65504.f), 65504.f);
+      __half h = __float2half_rn(v);
+      bits = *reinterpret_cast<uint16_t*>(&h);
+    }
+    const int64_t stage = ((int64_t)nb * g.ntaps + tap) * g.nkc + kc;
+    int64_t off;
+    if (g.layout == 0) {
+      off = stage * per_stage + ((int64_t)c8l * g.Nb + n) * 8 + e;
+    } else {
+      const int unit = (c8l & 1) ^ ((n >> 2) & 1);
+      off = stage * per_stage + (int64_t)(c8l >> 1) * g.Nb * 16 + (int64_t)n * 16 + unit * 8 + e;
+    }
+    img[off] = bits;
+  }
+}
+
+int rup(int x, int a) { return (x + a - 1) / a * a; }
+
+// geometry that depends only on the layer (not on B / T): used for packing and image sizing
+int gc_layer_geom(int mode, int cin, int cout, int k, int d_or_u, GcGeom& g) {
+  if (cin <= 0 || cout <= 0 || k <= 0 || d_or_u <= 0) return fail(AB_ERR_ARG, "gemmconv: bad layer shape");
+  g.mode = mode;
+  g.Kp = rup(cin, 16);
+  g.nkc = (g.Kp + 31) / 32;
+  g.layout = tc_layout();
+  if (mode == 0) {
+    if (!(k & 1)) return fail(AB_ERR_UNSUPPORTED, "gemmconv: conv kernel size must be odd");
+    const int Np = rup(cout, 16);
+    g.NB = (Np + 255) / 256;
+    g.Nb = rup((Np + g.NB - 1) / g.NB, 16);
+    g.cc = g.Nb;
+    g.ntaps = k;
+    g.pad = 0;
+  } else {
+    const int u = d_or_u;
+    if (k < u || ((k - u) & 1)) return fail(AB_ERR_UNSUPPORTED, "gemmconv: conv-transpose needs k >= stride, k-stride even");
+    if (u > 64) return fail(AB_ERR_UNSUPPORTED, "gemmconv: stride %d too large", u);
+    int cc = 256 / u;
+    if (cc > cout) cc = cout;
+    g.cc = cc;
+    g.Nb = rup(cc * u, 16);
+    g.NB = (cout + cc - 1) / cc;
+    g.ntaps = (k + u - 1) / u;
+    g.pad = (k - u) / 2;
+  }
+  g.stage_bytes = (uint32_t)g.Nb * 64u;
+  return AB_OK;
+}
+
+int gc_full_geom(const GcParams& p, GcGeom& g) {
+  int rc = gc_layer_geom(p.mode, p.Cin, p.Cout, p.k, p.mode ? p.u : p.d, g);
+  if (rc != AB_OK) return rc;
+  g.nbuf = g.NB > 1 ? 2 : 1;
+  const int maxshift = p.mode ? (g.ntaps - 1) : (p.k - 1) * p.d;
+  g.row0_time = p.mode ? (g.ntaps - 1) : maxshift / 2;
+  if (!p.mode && (maxshift & 1)) return fail(AB_ERR_UNSUPPORTED, "gemmconv: (k-1)*dilation must be even");
+  const int rows_total = p.mode ? p.Tin + 1 : p.Tin;
+  g.Tout = p.mode ? p.Tin * p.u : p.Tin;
+  int m = 512 / (g.nbuf * g.Nb);
+  if (m < 1) return fail(AB_ERR_UNSUPPORTED, "gemmconv: N block %d too wide", g.Nb);
+  if (m > 16) m = 16;
+  while (m > 1 && (m - 1) * 128 >= rows_total) --m;
+  const int nbias = rup(p.mode ? g.NB * g.cc : g.NB * g.Nb, 4);
+  const uint32_t misc = (uint32_t)nbias * 4u + 8u * (2 * GC_MAX_STAGES + 5) + 16u;
+  for (;; --m) {
+    if (m < 1) return fail(AB_ERR_UNSUPPORTED, "gemmconv: Cin=%d does not fit shared memory", p.Cin);
+    g.rowsA = rup(m * 128 + maxshift, 8);
+    const uint32_t abytes = (uint32_t)g.rowsA * (uint32_t)g.Kp * 2u;
+    if (abytes + 2u * g.stage_bytes + misc + 1280u > GC_SMEM_LIMIT) continue;
+    g.m = m;
+    int ns = (int)((GC_SMEM_LIMIT - abytes - misc - 1280u) / g.stage_bytes);
+    g.nstages = std::min(ns, GC_MAX_STAGES);
+    g.off_w = (abytes + 1023u) & ~1023u;
+    g.off_bias = g.off_w + (uint32_t)g.nstages * g.stage_bytes;
+    g.off_bar = (g.off_bias + (uint32_t)nbias * 4u + 15u) & ~15u;
+    g.smem_bytes = g.off_bar + 8u * (2 * GC_MAX_STAGES + 5) + 16u;
+    break;
+  }
+  g.tiles = (rows_total + g.m * 128 - 1) / (g.m * 128);
+  const uint32_t fmt = p.precision == AB_PREC_TC_BF16 ? 1u : 0u;
+  g.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(g.Nb >> 3) << 17) | ((128u >> 4) << 24);
+  return AB_OK;
+}
+
+}  // namespace
+
+size_t gc_weight_image_bytes(int mode, int cin, int cout, int k, int d_or_u) {
+  GcGeom g;
+  if (gc_layer_geom(mode, cin, cout, k, d_or_u, g) != AB_OK) return 0;
+  return (size_t)g.NB * g.ntaps * g.nkc * g.stage_bytes;
+}
+
+int launch_gc_pack_weight(const float* w_t, void* image, int mode, int cin, int cout, int k, int d_or_u,
+                          int precision, cudaStream_t s) {
+  GcGeom g;
+  int rc = gc_layer_geom(mode, cin, cout, k, d_or_u, g);
+  if (rc != AB_OK) return rc;
+  const int64_t total = (int64_t)g.NB * g.ntaps * g.nkc * g.Nb * 32;
+  const int blocks = (int)std::min<int64_t>((total + 255) / 256, 148 * 8);
+  gc_pack_weight_kernel<<<blocks, 256, 0, s>>>(w_t, static_cast<uint16_t*>(image), g, cin, cout, k, d_or_u,
+                                               precision == AB_PREC_TC_BF16 ? 1 : 0);
+  AB_LAUNCH_CHECK("gc_pack_weight_kernel");
+  return AB_OK;
+}
+
+int launch_gemmconv(const GcParams& p, cudaStream_t s) {
+  if (!p.x || !p.y || !p.w) return fail(AB_ERR_ARG, "gemmconv: null argument");
+  if (p.B <= 0 || p.Tin <= 0) return fail(AB_ERR_ARG, "gemmconv: bad shape");
+  if (p.precision != AB_PREC_TC_F16 && p.precision != AB_PREC_TC_BF16) return fail(AB_ERR_ARG, "gemmconv: bad precision");
+  GcGeom g;
+  int rc = gc_full_geom(p, g);
+  if (rc != AB_OK) return rc;
+  static bool configured = false;
+  if (!configured) {
+    AB_CUDA_TRY(cudaFuncSetAttribute(gemmconv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GC_SMEM_LIMIT));
+    configured = true;
+  }
+  const int64_t grid = (int64_t)p.B * g.tiles;
+  if (grid > 0x7fffffffll) return fail(AB_ERR_UNSUPPORTED, "gemmconv: grid too large");
+  const uint32_t smem = std::max<uint32_t>(g.smem_bytes, 120u * 1024u);
+  gemmconv_kernel<<<(unsigned)grid, GC_THREADS, smem, s>>>(p, g);
+  AB_LAUNCH_CHECK("gemmconv_kernel");
+  return AB_OK;
+}
+
+}  // namespace ab

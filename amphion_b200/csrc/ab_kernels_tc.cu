@@ -17,9 +17,20 @@
 #include <cuda_fp16.h>
 #include <stdlib.h>
 
+#include <vector>
+
 #include "ab_tc.cuh"
+#include "ab_tc_ptx.cuh"
 
 namespace ab {
+
+using namespace tcx;
+
+// operand layout knob (debug): AB_TC_LAYOUT=0 -> no-swizzle interleaved, default SWIZZLE_32B
+int tc_layout() {
+  static const int v = [] { const char* e = getenv("AB_TC_LAYOUT"); return (e && e[0] == '0') ? 0 : 1; }();
+  return v;
+}
 
 namespace {
 
@@ -45,111 +56,20 @@ struct TcGeom {
   int h2;          // time of the intermediate row 0 is T0 - h2 (pair mode)
   uint32_t idesc;
   int swap_lbo_sbo;  // debug knob
+  int layout;        // 0 = no-swizzle interleaved core matrices, 1 = SWIZZLE_32B rows
+  int base_off;      // debug knob: fill the descriptor base_offset field from the start address
+  int stagger_groups;        // first-wave CTAs are delayed by (smid % groups) * stagger_cycles so that the
+  long long stagger_cycles;  // HBM-bound phases of different SMs do not run in lock-step
+  long long* dbg;    // debug: per-CTA phase timestamps (AB_TC_DEBUG_TIMING=1), else nullptr
 };
 
-// ---------------------------------------------------------------------------
-// PTX helpers
-// ---------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
-}
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity)
-      : "memory");
-  return ok;
-}
-// Bounded wait: a protocol bug traps (-> cudaErrorLaunchFailure) instead of hanging the GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int tag) {
-  uint32_t spins = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 22)) {
-      printf("amphion_b200: mbarrier timeout tag=%d block=%d thread=%d parity=%u\n", tag, blockIdx.x,
-             threadIdx.x, parity);
-      __trap();
-    }
-  }
-}
-__device__ __forceinline__ void fence_proxy_async() {
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-}
-__device__ __forceinline__ void tc_fence_before() {
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-}
-__device__ __forceinline__ void tc_fence_after() {
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-      "l"(src), "r"(bytes), "r"(bar)
-      : "memory");
-}
-__device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                           uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void tc_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
-               : "memory");
-}
-__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&r)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// no-swizzle K-major shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
-//   [0,14) start>>4 | [16,30) LBO>>4 (next core matrix along K) | [32,46) SBO>>4
-//   (next 8-row group along M/N) | [46,48) version=1 | [61,64) layout=0 (none)
-__device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t lbo, uint32_t sbo) {
-  return (uint64_t)((addr >> 4) & 0x3FFFu) | ((uint64_t)((lbo >> 4) & 0x3FFFu) << 16) |
-         ((uint64_t)((sbo >> 4) & 0x3FFFu) << 32) | (1ull << 46);
-}
-
-__device__ __forceinline__ uint32_t pack2(float a, float b, int bf16) {
-  if (bf16) {
-    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-    return *reinterpret_cast<uint32_t*>(&h);
-  }
-  // saturating: fp16 operands must never become inf
-  a = fminf(fmaxf(a, -65504.f), 65504.f);
-  b = fminf(fmaxf(b, -65504.f), 65504.f);
-  __half2 h = __floats2half2_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&h);
-}
-
-__device__ __forceinline__ float lrelu(float v, float slope) { return v >= 0.f ? v : v * slope; }
+constexpr int DBG_BLOCKS = 2048, DBG_SLOTS = 8;
 
 // ---------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(TcConvParams p, TcGeom g) {
-  extern __shared__ __align__(128) uint8_t smem[];
+  extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.x / g.tiles, tile = blockIdx.x - b * g.tiles;
   const int T0 = tile * g.V;
@@ -187,6 +107,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(TcConvParams p, 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  auto stamp = [&](int slot) {
+    if (g.dbg != nullptr && threadIdx.x == 0 && blockIdx.x < DBG_BLOCKS)
+      g.dbg[blockIdx.x * DBG_SLOTS + slot] = clock64();
+  };
+  if (g.stagger_groups > 1 && blockIdx.x < gridDim.x && blockIdx.x < 148u) {
+    uint32_t smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    const long long wait = (long long)(smid % (uint32_t)g.stagger_groups) * g.stagger_cycles;
+    const long long t0 = clock64();
+    while (clock64() - t0 < wait) __nanosleep(200);
+  }
+  stamp(0);
 
   const uint32_t lboA = (uint32_t)g.rowsA * 16u;   // next 8-channel group
   const uint32_t lboB = (uint32_t)g.Np * 16u;
@@ -200,34 +132,43 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(TcConvParams p, 
       bias_s[i] = (src != nullptr && c < p.C) ? __ldg(src + c) : 0.f;
     }
     // ---- prologue: A[row][ci] = lrelu(x[b, ci, T0 - hh + row]) (zero outside [0,T) and for ci >= C)
+    // one item = 8 channels x 128 rows; each lane keeps 32 independent loads in flight
     {
-      const int nrb = g.rowsA >> 5, rem = g.rowsA & 31;
-      const int nblocks = nrb + (rem ? 1 : 0);
+      const int ngrp = (g.rowsA + 127) >> 7;
       const int c8n = g.Np >> 3;
       const float* xb = p.x + (int64_t)b * p.C * p.T;
-      for (int item = warp; item < c8n * nblocks; item += TC_WORKER_WARPS) {
-        const int c8 = item / nblocks, rb = item - c8 * nblocks;
-        const int row = (rb << 5) + lane;
-        const int t = T0 - g.hh + row;
-        const bool ok = row < g.rowsA && t >= 0 && t < p.T;
-        float v[8];
+      for (int item = warp; item < c8n * ngrp; item += TC_WORKER_WARPS) {
+        const int c8 = item / ngrp, grp = item - c8 * ngrp;
+        const int row0 = (grp << 7) + lane;
+        float v[4][8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const int c = c8 * 8 + e;
-          v[e] = (ok && c < p.C) ? __ldg(xb + (int64_t)c * p.T + t) : 0.f;
+        for (int r = 0; r < 4; ++r) {
+          const int row = row0 + 32 * r;
+          const int t = T0 - g.hh + row;
+          const bool ok = row < g.rowsA && t >= 0 && t < p.T;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const int c = c8 * 8 + e;
+            v[r][e] = (ok && c < p.C) ? __ldg(xb + (int64_t)c * p.T + t) : 0.f;
+          }
         }
-        if (row < g.rowsA) {
-          uint4 q;
-          q.x = pack2(lrelu(v[0], p.pre_slope), lrelu(v[1], p.pre_slope), bf16);
-          q.y = pack2(lrelu(v[2], p.pre_slope), lrelu(v[3], p.pre_slope), bf16);
-          q.z = pack2(lrelu(v[4], p.pre_slope), lrelu(v[5], p.pre_slope), bf16);
-          q.w = pack2(lrelu(v[6], p.pre_slope), lrelu(v[7], p.pre_slope), bf16);
-          *reinterpret_cast<uint4*>(smem + (size_t)c8 * lboA + (size_t)row * 16) = q;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const int row = row0 + 32 * r;
+          if (row < g.rowsA) {
+            uint4 q;
+            q.x = pack2(lrelu(v[r][0], p.pre_slope), lrelu(v[r][1], p.pre_slope), bf16);
+            q.y = pack2(lrelu(v[r][2], p.pre_slope), lrelu(v[r][3], p.pre_slope), bf16);
+            q.z = pack2(lrelu(v[r][4], p.pre_slope), lrelu(v[r][5], p.pre_slope), bf16);
+            q.w = pack2(lrelu(v[r][6], p.pre_slope), lrelu(v[r][7], p.pre_slope), bf16);
+            *reinterpret_cast<uint4*>(smem + unit_offset(g.layout, g.rowsA, c8, row)) = q;
+          }
         }
       }
     }
     fence_proxy_async();
     mbar_arrive(bar_aready);
+    stamp(1);
 
     const int q4 = warp & 3, hsel = warp >> 2;
     const int nch = g.Np >> 4;  // 16-column chunks
@@ -235,6 +176,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(TcConvParams p, 
       // ---- epilogue 1: intermediate = lrelu(conv1 + b1) -> A (aliased), zero outside [0,T)
       mbar_wait(bar_accfull, 0, 10);
       tc_fence_after();
+      stamp(2);
       for (int i = 0; i < g.m; ++i) {
         const int row = i * 128 + q4 * 32 + lane;
         const int t = T0 - g.h2 + row;
@@ -256,49 +198,58 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(TcConvParams p, 
             q.y = pack2(v[8 * h + 2], v[8 * h + 3], bf16);
             q.z = pack2(v[8 * h + 4], v[8 * h + 5], bf16);
             q.w = pack2(v[8 * h + 6], v[8 * h + 7], bf16);
-            *reinterpret_cast<uint4*>(smem + (size_t)(ch * 2 + h) * lboA + (size_t)row * 16) = q;
+            *reinterpret_cast<uint4*>(smem + unit_offset(g.layout, g.rowsA, ch * 2 + h, row)) = q;
           }
         }
       }
       tc_fence_before();
       fence_proxy_async();
       mbar_arrive(bar_aready);
+      stamp(3);
     }
     // ---- epilogue 2: y = ((acc + bias) + residual + acc_prev) / out_div
     mbar_wait(bar_accfull, (uint32_t)(p.nconv - 1), 11);
     tc_fence_after();
+    stamp(4);
     const float* bias2 = bias_s + (p.nconv == 2 ? g.Np : 0);
     for (int i = 0; i < g.m; ++i) {
       const int row = i * 128 + q4 * 32 + lane;
       const int t = T0 + row;
       const bool ok = row < g.V && t < p.T;
-      for (int ch = hsel; ch < nch; ch += 2) {
-        uint32_t r[16];
-        tc_ld16(tmem + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(i * g.Np + ch * 16), r);
-        tc_wait_ld();
-        float res[16], acp[16];
+      const float* rrow = p.residual ? p.residual + (int64_t)b * p.C * p.T + t : nullptr;
+      const float* arow = p.acc_prev ? p.acc_prev + (int64_t)b * p.C * p.T + t : nullptr;
+      float* yrow = p.y + (int64_t)b * p.C * p.T + t;
+      // this warp's column chunks: hsel, hsel+2, ... ; two chunks (32 columns) per iteration
+      for (int ch = hsel; ch < nch; ch += 4) {
+        const bool two = ch + 2 < nch;
+        uint32_t r0[16], r1[16];
+        const uint32_t tbase = tmem + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(i * g.Np);
+        tc_ld16(tbase + (uint32_t)(ch * 16), r0);
+        if (two) tc_ld16(tbase + (uint32_t)((ch + 2) * 16), r1);
+        float res[32], acp[32];
 #pragma unroll
-        for (int e = 0; e < 16; ++e) {
-          const int co = ch * 16 + e;
-          const int64_t idx = ((int64_t)b * p.C + co) * p.T + t;
-          const bool w = ok && co < p.C;
-          res[e] = (w && p.residual) ? __ldg(p.residual + idx) : 0.f;
-          acp[e] = (w && p.acc_prev) ? __ldg(p.acc_prev + idx) : 0.f;
+        for (int e = 0; e < 32; ++e) {
+          const int co = (e < 16 ? ch : ch + 2) * 16 + (e & 15);
+          const bool w = ok && co < p.C && (e < 16 || two);
+          res[e] = (w && rrow) ? __ldg(rrow + (int64_t)co * p.T) : 0.f;
+          acp[e] = (w && arow) ? __ldg(arow + (int64_t)co * p.T) : 0.f;
         }
+        tc_wait_ld();
 #pragma unroll
-        for (int e = 0; e < 16; ++e) {
-          const int co = ch * 16 + e;
-          if (ok && co < p.C) {
-            float v = __uint_as_float(r[e]) + bias2[co];
+        for (int e = 0; e < 32; ++e) {
+          const int co = (e < 16 ? ch : ch + 2) * 16 + (e & 15);
+          if (ok && co < p.C && (e < 16 || two)) {
+            float v = __uint_as_float(e < 16 ? r0[e & 15] : r1[e & 15]) + bias2[co];
             v += res[e];
             v += acp[e];
             if (p.out_div != 1.0f) v = v / p.out_div;
-            p.y[((int64_t)b * p.C + co) * p.T + t] = v;
+            yrow[(int64_t)co * p.T] = v;
           }
         }
       }
     }
     tc_fence_before();
+    stamp(5);
   } else if (warp == TC_WORKER_WARPS) {
     // ===================== TMA weight producer =====================
     if (lane == 0) {
@@ -316,7 +267,33 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(TcConvParams p, 
     }
   } else {
     // ===================== MMA issuer =====================
+    // All 32 lanes run the warp-uniform loops; one elected lane issues tcgen05.mma / commit.
+    // Descriptors (cute::UMMA::SmemDescriptor, no swizzle, K-major): hi word is constant
+    // (SBO = 128 B between 8-row groups, version 1); lo word = addr>>4 | (LBO>>4)<<16.
+    const uint32_t elected = elect_one_sync();
     const int nks_total = g.Np >> 4;  // 16-channel K steps per tap
+    const uint32_t rows16 = (uint32_t)g.rowsA;          // LBO of A in 16-byte units
+    const uint32_t np16 = (uint32_t)g.Np;               // LBO of B in 16-byte units
+    // layout 0: LBO = rows*16 B (next K core matrix), SBO = 128 B (next 8-row group), no swizzle.
+    // layout 1: SWIZZLE_32B (layout_type 6): LBO field 1 (unused), SBO = 256 B; K step = next [c16] chunk.
+    uint64_t hiA, hiB;
+    uint32_t lboA_f, lboB_f, kstepA, kstepB, rowunit;
+    if (g.layout == 0) {
+      hiA = g.swap_lbo_sbo ? ((uint64_t)(rows16 | (1u << 14)) << 32) : ((uint64_t)(8u | (1u << 14)) << 32);
+      hiB = g.swap_lbo_sbo ? ((uint64_t)(np16 | (1u << 14)) << 32) : ((uint64_t)(8u | (1u << 14)) << 32);
+      lboA_f = (g.swap_lbo_sbo ? 8u : rows16) << 16;
+      lboB_f = (g.swap_lbo_sbo ? 8u : np16) << 16;
+      kstepA = 2u * rows16;   // two 8-channel units per K=16 step
+      kstepB = 2u * np16;
+      rowunit = 1u;           // 16 B per row
+    } else {
+      hiA = hiB = ((uint64_t)(16u | (1u << 14)) << 32) | (6ull << 61);
+      lboA_f = lboB_f = 1u << 16;
+      kstepA = 2u * rows16;   // one [c16] chunk = rows * 32 B
+      kstepB = 2u * np16;
+      rowunit = 2u;           // 32 B per row
+    }
+    const uint32_t a16 = sA >> 4, w16 = sW >> 4, stage16 = g.stage_bytes >> 4;
     int it = 0;
     for (int conv = 0; conv < p.nconv; ++conv) {
       mbar_wait(bar_aready, (uint32_t)conv & 1u, 30);
@@ -328,24 +305,28 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(TcConvParams p, 
           const uint32_t ph = (uint32_t)(it / g.nstages) & 1u;
           mbar_wait(bar_full(s), ph, 31);
           tc_fence_after();
-          if (lane == 0) {
-            const int nks = min(2, nks_total - kc * 2);
-            const uint32_t wbase = sW + (uint32_t)s * g.stage_bytes;
-            for (int i = 0; i < g.m; ++i) {
-              for (int ks = 0; ks < nks; ++ks) {
-                const uint32_t aaddr = sA + (uint32_t)(kc * 4 + ks * 2) * lboA + (uint32_t)(i * 128 + j * dil) * 16u;
-                const uint32_t baddr = wbase + (uint32_t)(ks * 2) * lboB;
-                const uint64_t ad = g.swap_lbo_sbo ? make_desc(aaddr, 128u, lboA) : make_desc(aaddr, lboA, 128u);
-                const uint64_t bd = g.swap_lbo_sbo ? make_desc(baddr, 128u, lboB) : make_desc(baddr, lboB, 128u);
-                tc_mma_f16(tmem + (uint32_t)(i * g.Np), ad, bd, g.idesc, (j | kc | ks) != 0 ? 1u : 0u);
-              }
+          const bool two = nks_total - kc * 2 >= 2;
+          const uint32_t astart = a16 + (uint32_t)(kc * 2) * kstepA + (uint32_t)(j * dil) * rowunit;
+          uint32_t alo = astart | lboA_f;
+          const uint32_t blo = (w16 + (uint32_t)s * stage16) | lboB_f;
+          const uint32_t acc0 = (j | kc) != 0 ? 1u : 0u;
+          uint32_t td = tmem;
+          for (int i = 0; i < g.m; ++i) {
+            if (elected) {
+              // base_offset (bits 49-51) = (start address >> 7) & 7 when the debug knob asks for it
+              const uint64_t bo0 = g.base_off ? ((uint64_t)((alo >> 3) & 7u) << 49) : 0ull;
+              const uint64_t bo1 = g.base_off ? ((uint64_t)(((alo + kstepA) >> 3) & 7u) << 49) : 0ull;
+              tc_mma_f16(td, hiA | bo0 | alo, hiB | blo, g.idesc, acc0);
+              if (two) tc_mma_f16(td, hiA | bo1 | (alo + kstepA), hiB | (blo + kstepB), g.idesc, 1u);
             }
-            tc_commit(bar_empty(s));
+            alo += 128u * rowunit;
+            td += (uint32_t)g.Np;
           }
+          if (elected) tc_commit(bar_empty(s));
           __syncwarp();
         }
       }
-      if (lane == 0) tc_commit(bar_accfull);
+      if (elected) tc_commit(bar_accfull);
       __syncwarp();
     }
     tc_fence_before();
@@ -362,7 +343,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(TcConvParams p, 
 // weight image:  [tap j][kc][c8l 0..3][co 0..Np)[8]  16-bit, zero padded
 // ---------------------------------------------------------------------------
 __global__ void tc_pack_weight_kernel(const float* __restrict__ w_t, uint16_t* __restrict__ img, int cin,
-                                      int cout, int k, int Np, int nkc, int bf16) {
+                                      int cout, int k, int Np, int nkc, int bf16, int layout) {
+  // one thread per 16-bit element of the image; stage (j, kc) holds channels [32*kc, 32*kc+32)
   const int64_t total = (int64_t)k * nkc * 4 * Np * 8;
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (int64_t)gridDim.x * blockDim.x) {
@@ -386,7 +368,15 @@ __global__ void tc_pack_weight_kernel(const float* __restrict__ w_t, uint16_t* _
       __half h = __float2half_rn(v);
       bits = *reinterpret_cast<uint16_t*>(&h);
     }
-    img[idx] = bits;
+    const int64_t stage = (int64_t)j * nkc + kc;
+    int64_t off;   // in 16-bit elements within the image
+    if (layout == 0) {
+      off = stage * (4 * Np * 8) + ((int64_t)c8l * Np + co) * 8 + e;
+    } else {
+      const int unit = (c8l & 1) ^ ((co >> 2) & 1);
+      off = stage * (4 * Np * 8) + (int64_t)(c8l >> 1) * Np * 16 + (int64_t)co * 16 + unit * 8 + e;
+    }
+    img[off] = bits;
   }
 }
 
@@ -414,12 +404,12 @@ int make_geom(const TcConvParams& p, TcGeom& g) {
     if (m * 128 - lost < 8) continue;
     g.rowsA = round_up(m * 128 + halo, 8);
     const uint32_t abytes = (uint32_t)g.rowsA * (uint32_t)g.Np * 2u;
-    if (abytes + 2u * g.stage_bytes + misc + 256u > TC_SMEM_LIMIT) continue;
+    if (abytes + 2u * g.stage_bytes + misc + 1280u > TC_SMEM_LIMIT) continue;
     g.m = m;
-    int ns = (int)((TC_SMEM_LIMIT - abytes - misc - 256u) / g.stage_bytes);
+    int ns = (int)((TC_SMEM_LIMIT - abytes - misc - 1280u) / g.stage_bytes);
     if (ns > TC_MAX_STAGES) ns = TC_MAX_STAGES;
     g.nstages = ns;
-    g.off_w = (abytes + 127u) & ~127u;
+    g.off_w = (abytes + 1023u) & ~1023u;
     g.off_bias = g.off_w + (uint32_t)ns * g.stage_bytes;
     g.off_bar = (g.off_bias + 2u * g.Np * 4u + 15u) & ~15u;
     g.smem_bytes = g.off_bar + 8u * (2 * TC_MAX_STAGES + 2) + 16u;
@@ -433,6 +423,15 @@ int make_geom(const TcConvParams& p, TcGeom& g) {
   g.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(g.Np >> 3) << 17) | ((128u >> 4) << 24);
   const char* sw = getenv("AB_TC_SWAP_LBO_SBO");
   g.swap_lbo_sbo = (sw && sw[0] == '1') ? 1 : 0;
+  g.layout = tc_layout();
+  const char* bo = getenv("AB_TC_BASE_OFFSET");
+  g.base_off = (bo && bo[0] == '1') ? 1 : 0;
+  g.dbg = nullptr;
+  static const int stag = [] { const char* e = getenv("AB_TC_STAGGER"); return e ? atoi(e) : 0; }();
+  g.stagger_groups = stag;
+  const double mma = (double)p.nconv * p.k * g.nkc * g.m * 2.0 * (64.0 + g.Np / 2.0);
+  const double mem = (double)g.m * 128.0 * g.Np * 12.0 / 11.0;
+  g.stagger_cycles = stag > 1 ? (long long)((mma + mem + 15000.0) / stag) : 0;
   return AB_OK;
 }
 
@@ -456,7 +455,7 @@ int launch_tc_pack_weight(const float* w_t, void* image, int cin, int cout, int 
   const int64_t total = (int64_t)bytes / 2;
   const int blocks = (int)std::min<int64_t>((total + 255) / 256, 148 * 8);
   tc_pack_weight_kernel<<<blocks, 256, 0, s>>>(w_t, static_cast<uint16_t*>(image), cin, cout, k, Np, nkc,
-                                               precision == AB_PREC_TC_BF16 ? 1 : 0);
+                                               precision == AB_PREC_TC_BF16 ? 1 : 0, tc_layout());
   AB_LAUNCH_CHECK("tc_pack_weight_kernel");
   return AB_OK;
 }
@@ -477,8 +476,45 @@ int launch_tc_conv(const TcConvParams& p, cudaStream_t s) {
   if (grid > 0x7fffffffll) return fail(AB_ERR_UNSUPPORTED, "tc_conv: grid too large");
   // request > half of the SM's shared memory so exactly one CTA (512 TMEM columns) is resident
   const uint32_t smem = std::max<uint32_t>(g.smem_bytes, 120u * 1024u);
+  static const bool dbg_on = [] { const char* e = getenv("AB_TC_DEBUG_TIMING"); return e && e[0] == '1'; }();
+  static long long* dbg_buf = nullptr;
+  if (dbg_on) {  // debug only: the one place the library allocates, never on the product path
+    if (!dbg_buf) AB_CUDA_TRY(cudaMalloc(&dbg_buf, sizeof(long long) * DBG_BLOCKS * DBG_SLOTS));
+    AB_CUDA_TRY(cudaMemsetAsync(dbg_buf, 0, sizeof(long long) * DBG_BLOCKS * DBG_SLOTS, s));
+    g.dbg = dbg_buf;
+  }
   tc_conv_kernel<<<(unsigned)grid, TC_THREADS, smem, s>>>(p, g);
   AB_LAUNCH_CHECK("tc_conv_kernel");
+  if (dbg_on) {
+    AB_CUDA_TRY(cudaStreamSynchronize(s));
+    static std::vector<long long> h(DBG_BLOCKS * DBG_SLOTS);
+    AB_CUDA_TRY(cudaMemcpy(h.data(), dbg_buf, sizeof(long long) * h.size(), cudaMemcpyDeviceToHost));
+    const int nb = (int)std::min<int64_t>(grid, DBG_BLOCKS);
+    double ph[5] = {0, 0, 0, 0, 0};
+    int cnt = 0;
+    for (int i = 0; i < nb; ++i) {
+      const long long* r = &h[(size_t)i * DBG_SLOTS];
+      if (r[5] == 0) continue;
+      ++cnt;
+      ph[0] += (double)(r[1] - r[0]);                       // prologue
+      if (p.nconv == 2) {
+        ph[1] += (double)(r[2] - r[1]);                     // conv1 MMA (wait)
+        ph[2] += (double)(r[3] - r[2]);                     // epilogue 1
+        ph[3] += (double)(r[4] - r[3]);                     // conv2 MMA (wait)
+      } else {
+        ph[1] += (double)(r[4] - r[1]);
+      }
+      ph[4] += (double)(r[5] - r[4]);                       // epilogue 2
+    }
+    if (cnt) {
+      const double ideal = (double)g.m * (g.Np / 2.0) * (g.Np / 16.0) * p.k;   // cycles per conv at 8192 flop/clk/SM
+      fprintf(stderr,
+              "[tc_timing] C=%d k=%d d=%d nconv=%d m=%d V=%d tiles=%lld stages=%d | cycles: prologue %.0f conv1 %.0f epi1 %.0f "
+              "conv2 %.0f epi2 %.0f | ideal MMA/conv %.0f\n",
+              p.C, p.k, p.d1, p.nconv, g.m, g.V, (long long)grid, g.nstages, ph[0] / cnt, ph[1] / cnt, ph[2] / cnt,
+              ph[3] / cnt, ph[4] / cnt, ideal);
+    }
+  }
   return AB_OK;
 }
 

@@ -24,6 +24,26 @@ struct TcConvParams {
   int precision;          // AB_PREC_TC_F16 | AB_PREC_TC_BF16
 };
 
+// N-blocked implicit GEMM (ab_kernels_gemmconv.cu): ConvTranspose1d (mode 1) and wide Conv1d (mode 0)
+struct GcParams {
+  const float* x;         // contiguous [B, Cin, Tin] fp32
+  float* y;               // conv: [B, Cout, Tin]; conv-transpose: [B, Cout, Tin*u]
+  const void* w;          // operand image built by launch_gc_pack_weight
+  const float* bias;      // nullable
+  const float* residual;  // conv only, nullable
+  int B, Cin, Cout, Tin;
+  int mode;               // 0 conv, 1 conv-transpose
+  int k, d, u;
+  float pre_slope;
+  int post_tanh;          // conv only
+  int precision;
+};
+size_t gc_weight_image_bytes(int mode, int cin, int cout, int k, int d_or_u);
+int launch_gc_pack_weight(const float* w_t, void* image, int mode, int cin, int cout, int k, int d_or_u,
+                          int precision, cudaStream_t s);
+int launch_gemmconv(const GcParams& p, cudaStream_t s);
+
+int tc_layout();
 int tc_max_channels();
 bool tc_conv_supported(int C, int k);
 size_t tc_weight_image_bytes(int cin, int cout, int k);

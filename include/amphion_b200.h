@@ -121,7 +121,7 @@ int ab_generator_last_launches(const ab_generator* g);
  * ab_generator_get_profile synchronises on the recorded events, accumulates
  * (launches, milliseconds, algorithmic FLOPs, algorithmic HBM bytes) per class
  * since the last call, and resets.  Classes: "tc_conv", "conv1d_fp32",
- * "conv_transpose1d_fp32", "activation1d". */
+ * "conv_transpose1d_fp32", "activation1d", "tc_gemmconv" (max_entries >= 5). */
 typedef struct ab_profile_entry {
   char name[32];
   int32_t launches;
@@ -157,10 +157,13 @@ int ab_conv1d_forward(const float* dev_x, const float* dev_w, const float* dev_b
                       float pre_slope, int32_t post_tanh, int32_t precision,
                       void* dev_workspace, size_t workspace_bytes, void* stream);
 size_t ab_conv1d_workspace_bytes(int64_t cin, int64_t cout, int32_t ksize, int32_t precision);
+size_t ab_conv_transpose1d_workspace_bytes(int64_t cin, int64_t cout, int32_t ksize, int32_t stride,
+                                          int32_t precision);
 int ab_conv_transpose1d_forward(const float* dev_x, const float* dev_w, const float* dev_bias,
                                 float* dev_y, int64_t batch, int64_t cin, int64_t cout,
                                 int64_t length_in, int32_t ksize, int32_t stride, float pre_slope,
-                                void* dev_workspace, size_t workspace_bytes, void* stream);
+                                int32_t precision, void* dev_workspace, size_t workspace_bytes,
+                                void* stream);
 
 /* ------------------------------------------------------------------------
  * Mel front end:
