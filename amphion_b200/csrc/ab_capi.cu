@@ -361,7 +361,18 @@ int ab_generator_finalize(ab_generator* g, int32_t precision, void* stream) {
 // forward
 // ---------------------------------------------------------------------------
 namespace {
-constexpr int NBUF = 7;  // R0 R1 U P0 P1 TMP ACT
+constexpr int NBUF = 7;  // fp32: R0 R1 U P0 P1 TMP ACT
+constexpr int NIMG = 3;  // 16-bit operand images: U P0 P1
+
+size_t stage_max_image_bytes(const ab_generator* g, int64_t B, int64_t T) {
+  size_t mx = 0;
+  int64_t t = T;
+  for (auto& st : g->stages) {
+    t *= st.u;
+    mx = std::max(mx, tc_act_image_bytes(B, st.ch, t));
+  }
+  return mx;
+}
 
 size_t stage_max_elems(const ab_generator* g, int64_t B, int64_t T) {
   size_t mx = (size_t)B * g->cfg.upsample_initial_channel * T;
@@ -376,7 +387,8 @@ size_t stage_max_elems(const ab_generator* g, int64_t B, int64_t T) {
 
 size_t ab_generator_workspace_bytes(const ab_generator* g, int64_t B, int64_t T) {
   if (!g || B <= 0 || T <= 0) return 0;
-  return NBUF * align_up(stage_max_elems(g, B, T) * sizeof(float), 256);
+  return NBUF * align_up(stage_max_elems(g, B, T) * sizeof(float), 256) +
+         NIMG * align_up(stage_max_image_bytes(g, B, T), 256);
 }
 
 int ab_generator_last_launches(const ab_generator* g) { return g ? g->launches : 0; }
@@ -423,9 +435,14 @@ int ab_generator_forward(ab_generator* g, const float* dev_mel, int64_t B, int64
   if (!dev_workspace || workspace_bytes < need) return fail(AB_ERR_WORKSPACE, "forward: workspace %zu B < required %zu B", workspace_bytes, need);
   if (reinterpret_cast<uintptr_t>(dev_workspace) & 255) return fail(AB_ERR_ARG, "forward: workspace must be 256-byte aligned");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const size_t bufsz = need / NBUF;
+  const size_t bufsz = align_up(stage_max_elems(g, B, T) * sizeof(float), 256);
+  const size_t imgsz = align_up(stage_max_image_bytes(g, B, T), 256);
   float* buf[NBUF];
   for (int i = 0; i < NBUF; ++i) buf[i] = reinterpret_cast<float*>(static_cast<char*>(dev_workspace) + i * bufsz);
+  uint16_t* img[NIMG];
+  for (int i = 0; i < NIMG; ++i)
+    img[i] = reinterpret_cast<uint16_t*>(static_cast<char*>(dev_workspace) + NBUF * bufsz + i * imgsz);
+  uint16_t *U16 = img[0], *P16[2] = {img[1], img[2]};
   float *R[2] = {buf[0], buf[1]}, *U = buf[2], *P[2] = {buf[3], buf[4]}, *TMP = buf[5], *ACT = buf[6];
   const bool big = g->cfg.kind == AB_GEN_BIGVGAN;
   const bool tc = g->precision != AB_PREC_FP32;
@@ -477,8 +494,9 @@ int ab_generator_forward(ab_generator* g, const float* dev_mel, int64_t B, int64
   // one (conv1 -> conv2 -> + x) pair or a single (conv -> + x) on the tensor cores
   auto tc_convs = [&](const ConvRef& c1, const ConvRef* c2, const float* x, float* y, int C, int Tn,
                       float pre_slope, float mid_slope, const float* residual, const float* acc_prev,
-                      float out_div) -> int {
+                      float out_div, const uint16_t* ximg, uint16_t* yimg) -> int {
     TcConvParams p;
+    p.ximg = ximg; p.yimg = yimg; p.img_slope = 0.1f;
     p.x = x; p.y = y; p.residual = residual; p.acc_prev = acc_prev;
     p.w1 = g->tcptr(c1.w); p.b1 = g->fptr(c1.b);
     p.w2 = c2 ? g->tcptr(c2->w) : nullptr; p.b2 = c2 ? g->fptr(c2->b) : nullptr;
@@ -511,6 +529,7 @@ int ab_generator_forward(ab_generator* g, const float* dev_mel, int64_t B, int64
     tp.B = (int)B; tp.Cin = cin; tp.Cout = sg.ch; tp.Tin = Tn; tp.k = sg.up.k; tp.u = sg.u;
     tp.pre_slope = big ? 1.0f : 0.1f;
     ++launches;
+    uint16_t* u_img = nullptr;
     {
       const double eo = (double)B * sg.ch * Tn * sg.u;
       prof_begin(2, 2.0 * eo * cin * ((double)sg.up.k / sg.u),
@@ -521,6 +540,9 @@ int ab_generator_forward(ab_generator* g, const float* dev_mel, int64_t B, int64
       gp.x = R[cur_r]; gp.y = U; gp.w = g->tcptr(sg.up.w); gp.bias = g->fptr(sg.up.b); gp.residual = nullptr;
       gp.B = (int)B; gp.Cin = cin; gp.Cout = sg.ch; gp.Tin = Tn; gp.mode = 1; gp.k = sg.up.k; gp.d = 1; gp.u = sg.u;
       gp.pre_slope = tp.pre_slope; gp.post_tanh = 0; gp.precision = g->precision;
+      // HiFi-GAN: every consumer of U applies lrelu(., 0.1) first (hifigan.py:95) -> emit that operand image
+      u_img = (!big && gc_can_emit_image(sg.ch, sg.up.k, sg.u)) ? U16 : nullptr;
+      gp.yimg = u_img; gp.img_slope = 0.1f;
       if (g->profiling) g->prof_recs.back().cls = 4;
       rc = launch_gemmconv(gp, st);
     } else {
@@ -536,11 +558,13 @@ int ab_generator_forward(ab_generator* g, const float* dev_mel, int64_t B, int64
     for (int j = 0; j < nk; ++j) {
       const BlockRef& blk = sg.blocks[j];
       const float* cur = U;
+      const uint16_t* cur_img = u_img;
       int pp = 0;
       const int nd = (int)blk.dil.size();
       for (int p = 0; p < nd; ++p) {
         const bool last = p == nd - 1;
         float* dst = last ? Rout : P[pp];
+        uint16_t* dst_img = (last || big) ? nullptr : P16[pp];
         if (!last) pp ^= 1;
         // xs = rb_0(x) ; xs += rb_j(x) ; x = xs / num_kernels  (hifigan.py:208-214)
         const float* accp = (last && j > 0) ? Rout : nullptr;
@@ -549,16 +573,20 @@ int ab_generator_forward(ab_generator* g, const float* dev_mel, int64_t B, int64
         const bool blk_tc = use_tc && tc_conv_supported(C, blk.k);
         if (!big) {
           if (blk_tc) {
-            rc = tc_convs(blk.c1[p], pair ? &blk.c2[p] : nullptr, cur, dst, C, Tn, 0.1f, 0.1f, cur, accp, div);
+            rc = tc_convs(blk.c1[p], pair ? &blk.c2[p] : nullptr, cur, dst, C, Tn, 0.1f, 0.1f, cur, accp, div,
+                          cur_img, dst_img);
             if (rc != AB_OK) return rc;
+            cur_img = dst_img;
           } else if (pair) {
             rc = conv(blk.c1[p], cur, sb, sc, 1, TMP, Tn, 0.1f, nullptr, nullptr, 1.0f, 0);
             if (rc != AB_OK) return rc;
             rc = conv(blk.c2[p], TMP, sb, sc, 1, dst, Tn, 0.1f, cur, accp, div, 0);
             if (rc != AB_OK) return rc;
+            cur_img = nullptr;
           } else {
             rc = conv(blk.c1[p], cur, sb, sc, 1, dst, Tn, 0.1f, cur, accp, div, 0);
             if (rc != AB_OK) return rc;
+            cur_img = nullptr;
           }
         } else {
           // AMPBlock: anti-aliased snake in front of every conv (bigvgan.py:137-146, :222-228)
@@ -566,16 +594,16 @@ int ab_generator_forward(ab_generator* g, const float* dev_mel, int64_t B, int64
           rc = snake(a1, cur, ACT, C, Tn);
           if (rc != AB_OK) return rc;
           if (pair) {
-            if (blk_tc) rc = tc_convs(blk.c1[p], nullptr, ACT, TMP, C, Tn, 1.0f, 1.0f, nullptr, nullptr, 1.0f);
+            if (blk_tc) rc = tc_convs(blk.c1[p], nullptr, ACT, TMP, C, Tn, 1.0f, 1.0f, nullptr, nullptr, 1.0f, nullptr, nullptr);
             else rc = conv(blk.c1[p], ACT, sb, sc, 1, TMP, Tn, 1.0f, nullptr, nullptr, 1.0f, 0);
             if (rc != AB_OK) return rc;
             rc = snake(blk.acts[2 * p + 1], TMP, ACT, C, Tn);
             if (rc != AB_OK) return rc;
-            if (blk_tc) rc = tc_convs(blk.c2[p], nullptr, ACT, dst, C, Tn, 1.0f, 1.0f, cur, accp, div);
+            if (blk_tc) rc = tc_convs(blk.c2[p], nullptr, ACT, dst, C, Tn, 1.0f, 1.0f, cur, accp, div, nullptr, nullptr);
             else rc = conv(blk.c2[p], ACT, sb, sc, 1, dst, Tn, 1.0f, cur, accp, div, 0);
             if (rc != AB_OK) return rc;
           } else {
-            if (blk_tc) rc = tc_convs(blk.c1[p], nullptr, ACT, dst, C, Tn, 1.0f, 1.0f, cur, accp, div);
+            if (blk_tc) rc = tc_convs(blk.c1[p], nullptr, ACT, dst, C, Tn, 1.0f, 1.0f, cur, accp, div, nullptr, nullptr);
             else rc = conv(blk.c1[p], ACT, sb, sc, 1, dst, Tn, 1.0f, cur, accp, div, 0);
             if (rc != AB_OK) return rc;
           }
@@ -651,6 +679,7 @@ int ab_conv1d_forward(const float* dev_x, const float* dev_w, const float* dev_b
   p.w1 = img; p.b1 = dev_bias; p.w2 = nullptr; p.b2 = nullptr;
   p.B = (int)B; p.C = (int)cin; p.T = (int)T; p.k = k; p.d1 = d; p.nconv = 1;
   p.pre_slope = pre_slope; p.mid_slope = 1.0f; p.out_div = 1.0f; p.precision = precision;
+  p.ximg = nullptr; p.yimg = nullptr; p.img_slope = 1.0f;
   return launch_tc_conv(p, st);
 }
 
@@ -680,6 +709,7 @@ int ab_conv_transpose1d_forward(const float* dev_x, const float* dev_w, const fl
     gp.x = dev_x; gp.y = dev_y; gp.w = img; gp.bias = dev_bias; gp.residual = nullptr;
     gp.B = (int)B; gp.Cin = (int)cin; gp.Cout = (int)cout; gp.Tin = (int)Tin; gp.mode = 1; gp.k = k; gp.d = 1; gp.u = u;
     gp.pre_slope = pre_slope; gp.post_tanh = 0; gp.precision = precision;
+    gp.yimg = nullptr; gp.img_slope = 1.0f;
     return launch_gemmconv(gp, st);
   }
   ConvTParams p;

@@ -47,9 +47,63 @@ struct GcGeom {
   int row0_time;   // time of A row 0 is tile_origin - row0_time
   int Tout;        // output length
   int pad;         // convT: (k-u)/2
+  int grouped;     // convT: 8-channel-group epilogue (u in {2,4,8}, cc % 8 == 0)
   uint32_t idesc;
-  int layout;
 };
+
+// ConvTranspose epilogue for one group of 8 output channels (8*U accumulator columns of one TMEM row):
+// the row is input time s, column (c*U + phi) holds y[co0 + c, s*U - pad + phi].  Stores the fp32 samples
+// (U consecutive floats per channel) and, optionally, the fp16 operand image row of each output time.
+template <int U>
+__device__ __forceinline__ void convT_group_store(const GcParams& p, const GcGeom& g, uint32_t taddr, int b, int co0,
+                                                  int s, const float* bias_s, int bf16) {
+  uint32_t r[8 * U];
+#pragma unroll
+  for (int q = 0; q < (8 * U) / 16; ++q) {
+    uint32_t tmp[16];
+    tc_ld16(taddr + (uint32_t)(q * 16), tmp);
+#pragma unroll
+    for (int e = 0; e < 16; ++e) r[q * 16 + e] = tmp[e];
+  }
+  tc_wait_ld();
+  const int tb = s * U - g.pad;
+  float o[8][U];
+#pragma unroll
+  for (int c = 0; c < 8; ++c)
+#pragma unroll
+    for (int f = 0; f < U; ++f) o[c][f] = __uint_as_float(r[c * U + f]) + bias_s[co0 + c];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    if (co0 + c < p.Cout) {
+      float* yr = p.y + ((int64_t)b * p.Cout + co0 + c) * g.Tout;
+      if (U >= 4 && tb >= 0 && tb + U <= g.Tout && ((tb & 3) == 0)) {
+#pragma unroll
+        for (int f = 0; f < U; f += 4)
+          *reinterpret_cast<float4*>(yr + tb + f) = make_float4(o[c][f], o[c][f + 1], o[c][f + 2], o[c][f + 3]);
+      } else {
+#pragma unroll
+        for (int f = 0; f < U; ++f)
+          if (tb + f >= 0 && tb + f < g.Tout) yr[tb + f] = o[c][f];
+      }
+    }
+  }
+  if (p.yimg != nullptr) {
+    const int c8n = (p.Cout + 15) >> 4 << 1;
+    uint16_t* yi = p.yimg + ((size_t)b * c8n + (size_t)(co0 >> 3)) * (size_t)g.Tout * 8;
+#pragma unroll
+    for (int f = 0; f < U; ++f) {
+      const int t = tb + f;
+      if (t >= 0 && t < g.Tout) {
+        uint4 q;
+        q.x = pack2(lrelu(o[0][f], p.img_slope), lrelu(o[1][f], p.img_slope), bf16);
+        q.y = pack2(lrelu(o[2][f], p.img_slope), lrelu(o[3][f], p.img_slope), bf16);
+        q.z = pack2(lrelu(o[4][f], p.img_slope), lrelu(o[5][f], p.img_slope), bf16);
+        q.w = pack2(lrelu(o[6][f], p.img_slope), lrelu(o[7][f], p.img_slope), bf16);
+        *reinterpret_cast<uint4*>(yi + (size_t)t * 8) = q;
+      }
+    }
+  }
+}
 
 __global__ void __launch_bounds__(GC_THREADS, 1) gemmconv_kernel(GcParams p, GcGeom g) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -128,7 +182,7 @@ __global__ void __launch_bounds__(GC_THREADS, 1) gemmconv_kernel(GcParams p, GcG
             q.y = pack2(lrelu(v[r][2], p.pre_slope), lrelu(v[r][3], p.pre_slope), bf16);
             q.z = pack2(lrelu(v[r][4], p.pre_slope), lrelu(v[r][5], p.pre_slope), bf16);
             q.w = pack2(lrelu(v[r][6], p.pre_slope), lrelu(v[r][7], p.pre_slope), bf16);
-            *reinterpret_cast<uint4*>(smem + unit_offset(g.layout, g.rowsA, c8, row)) = q;
+            *reinterpret_cast<uint4*>(smem + unit_offset(g.rowsA, c8, row)) = q;
           }
         }
       }
@@ -145,6 +199,18 @@ __global__ void __launch_bounds__(GC_THREADS, 1) gemmconv_kernel(GcParams p, GcG
       for (int i = 0; i < g.m; ++i) {
         const int row = i * 128 + q4 * 32 + lane;
         const uint32_t tbase = tmem + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(buf * ncols_buf + i * g.Nb);
+        if (g.mode == 1 && g.grouped) {
+          // 8-channel groups (8*u columns each); this warp takes groups hsel, hsel+2, ...
+          const int ngroups = g.cc >> 3;
+          for (int grp = hsel; grp < ngroups; grp += 2) {
+            const uint32_t ta = tbase + (uint32_t)(grp * 8 * p.u);
+            const int co0 = nb * g.cc + grp * 8;
+            if (p.u == 8) convT_group_store<8>(p, g, ta, b, co0, R0 + row, bias_s, bf16);
+            else if (p.u == 4) convT_group_store<4>(p, g, ta, b, co0, R0 + row, bias_s, bf16);
+            else convT_group_store<2>(p, g, ta, b, co0, R0 + row, bias_s, bf16);
+          }
+          continue;
+        }
         for (int ch = hsel; ch < nch; ch += 2) {
           uint32_t r[16];
           tc_ld16(tbase + (uint32_t)(ch * 16), r);
@@ -165,39 +231,16 @@ __global__ void __launch_bounds__(GC_THREADS, 1) gemmconv_kernel(GcParams p, GcG
               }
             }
           } else {
-            // row = input time s; columns n = co_local*u + phi hold y[co, s*u - pad + phi]
-            const int s = R0 + row;
-            const int tb = s * p.u - g.pad;
-            if (p.u == 8) {
+            // generic stride: row = input time s; column n = co_local*u + phi holds y[co, s*u - pad + phi]
+            const int tb = (R0 + row) * p.u - g.pad;
 #pragma unroll
-              for (int half = 0; half < 2; ++half) {
-                const int col = nb * g.cc + ((ch * 16 + half * 8) >> 3);
-                if (col < p.Cout && col < (nb + 1) * g.cc) {
-                  float* yr = p.y + ((int64_t)b * p.Cout + col) * g.Tout;
-                  const float bv = bias_s[col];
-                  float o[8];
-#pragma unroll
-                  for (int e = 0; e < 8; ++e) o[e] = __uint_as_float(r[half * 8 + e]) + bv;
-                  if (tb >= 0 && tb + 8 <= g.Tout && ((tb & 3) == 0)) {
-                    *reinterpret_cast<float4*>(yr + tb) = make_float4(o[0], o[1], o[2], o[3]);
-                    *reinterpret_cast<float4*>(yr + tb + 4) = make_float4(o[4], o[5], o[6], o[7]);
-                  } else {
-#pragma unroll
-                    for (int e = 0; e < 8; ++e)
-                      if (tb + e >= 0 && tb + e < g.Tout) yr[tb + e] = o[e];
-                  }
-                }
-              }
-            } else {
-#pragma unroll
-              for (int e = 0; e < 16; ++e) {
-                const int n = ch * 16 + e;
-                const int col = n / p.u, phi = n - col * p.u;
-                const int co = nb * g.cc + col;
-                const int t = tb + phi;
-                if (col < g.cc && co < p.Cout && t >= 0 && t < g.Tout)
-                  p.y[((int64_t)b * p.Cout + co) * g.Tout + t] = __uint_as_float(r[e]) + bias_s[co];
-              }
+            for (int e = 0; e < 16; ++e) {
+              const int n = ch * 16 + e;
+              const int col = n / p.u, phi = n - col * p.u;
+              const int co = nb * g.cc + col;
+              const int t = tb + phi;
+              if (col < g.cc && co < p.Cout && t >= 0 && t < g.Tout)
+                p.y[((int64_t)b * p.Cout + co) * g.Tout + t] = __uint_as_float(r[e]) + bias_s[co];
             }
           }
         }
@@ -222,20 +265,8 @@ __global__ void __launch_bounds__(GC_THREADS, 1) gemmconv_kernel(GcParams p, GcG
     // ===================== MMA issuer =====================
     const uint32_t elected = elect_one_sync();
     const int nks_total = g.Kp >> 4;
-    const uint32_t rows16 = (uint32_t)g.rowsA, nb16 = (uint32_t)g.Nb;
-    uint64_t hiA, hiB;
-    uint32_t lboA_f, lboB_f, rowunit;
-    const uint32_t kstepA = 2u * rows16, kstepB = 2u * nb16;
-    if (g.layout == 0) {
-      hiA = hiB = (uint64_t)(8u | (1u << 14)) << 32;
-      lboA_f = rows16 << 16;
-      lboB_f = nb16 << 16;
-      rowunit = 1u;
-    } else {
-      hiA = hiB = ((uint64_t)(16u | (1u << 14)) << 32) | (6ull << 61);
-      lboA_f = lboB_f = 1u << 16;
-      rowunit = 2u;
-    }
+    const uint64_t hi = desc_hi_sw32();
+    const uint32_t kstepA = 2u * (uint32_t)g.rowsA, kstepB = 2u * (uint32_t)g.Nb;
     const uint32_t a16 = sA >> 4, w16 = sW >> 4, stage16 = g.stage_bytes >> 4;
     mbar_wait(bar_aready, 0, 30);
     tc_fence_after();
@@ -252,16 +283,16 @@ __global__ void __launch_bounds__(GC_THREADS, 1) gemmconv_kernel(GcParams p, GcG
           mbar_wait(bar_full(s), ph, 31);
           tc_fence_after();
           const bool two = nks_total - kc * 2 >= 2;
-          uint32_t alo = (a16 + (uint32_t)(kc * 2) * kstepA + (uint32_t)shift * rowunit) | lboA_f;
-          const uint32_t blo = (w16 + (uint32_t)s * stage16) | lboB_f;
+          uint32_t alo = desc_lo_sw32(a16 + (uint32_t)(kc * 2) * kstepA + (uint32_t)shift * 2u);
+          const uint32_t blo = desc_lo_sw32(w16 + (uint32_t)s * stage16);
           const uint32_t acc0 = (tap | kc) != 0 ? 1u : 0u;
           uint32_t td = tmem + (uint32_t)(buf * ncols_buf);
           for (int i = 0; i < g.m; ++i) {
             if (elected) {
-              tc_mma_f16(td, hiA | alo, hiB | blo, g.idesc, acc0);
-              if (two) tc_mma_f16(td, hiA | (alo + kstepA), hiB | (blo + kstepB), g.idesc, 1u);
+              tc_mma_f16(td, hi | alo, hi | blo, g.idesc, acc0);
+              if (two) tc_mma_f16(td, hi | (alo + kstepA), hi | (blo + kstepB), g.idesc, 1u);
             }
-            alo += 128u * rowunit;
+            alo += 256u;   // 128 rows x 32 B
             td += (uint32_t)g.Nb;
           }
           if (elected) tc_commit(bar_empty(s));
@@ -319,14 +350,8 @@ __global__ void gc_pack_weight_kernel(const float* __restrict__ w_t, uint16_t* _
       bits = *reinterpret_cast<uint16_t*>(&h);
     }
     const int64_t stage = ((int64_t)nb * g.ntaps + tap) * g.nkc + kc;
-    int64_t off;
-    if (g.layout == 0) {
-      off = stage * per_stage + ((int64_t)c8l * g.Nb + n) * 8 + e;
-    } else {
-      const int unit = (c8l & 1) ^ ((n >> 2) & 1);
-      off = stage * per_stage + (int64_t)(c8l >> 1) * g.Nb * 16 + (int64_t)n * 16 + unit * 8 + e;
-    }
-    img[off] = bits;
+    const int unit = (c8l & 1) ^ ((n >> 2) & 1);
+    img[stage * per_stage + (int64_t)(c8l >> 1) * g.Nb * 16 + (int64_t)n * 16 + unit * 8 + e] = bits;
   }
 }
 
@@ -338,7 +363,6 @@ int gc_layer_geom(int mode, int cin, int cout, int k, int d_or_u, GcGeom& g) {
   g.mode = mode;
   g.Kp = rup(cin, 16);
   g.nkc = (g.Kp + 31) / 32;
-  g.layout = tc_layout();
   if (mode == 0) {
     if (!(k & 1)) return fail(AB_ERR_UNSUPPORTED, "gemmconv: conv kernel size must be odd");
     const int Np = rup(cout, 16);
@@ -347,6 +371,7 @@ int gc_layer_geom(int mode, int cin, int cout, int k, int d_or_u, GcGeom& g) {
     g.cc = g.Nb;
     g.ntaps = k;
     g.pad = 0;
+    g.grouped = 0;
   } else {
     const int u = d_or_u;
     if (k < u || ((k - u) & 1)) return fail(AB_ERR_UNSUPPORTED, "gemmconv: conv-transpose needs k >= stride, k-stride even");
@@ -358,6 +383,7 @@ int gc_layer_geom(int mode, int cin, int cout, int k, int d_or_u, GcGeom& g) {
     g.NB = (cout + cc - 1) / cc;
     g.ntaps = (k + u - 1) / u;
     g.pad = (k - u) / 2;
+    g.grouped = ((u == 2 || u == 4 || u == 8) && (cc % 8) == 0 && (cout % 8) == 0) ? 1 : 0;
   }
   g.stage_bytes = (uint32_t)g.Nb * 64u;
   return AB_OK;
@@ -400,6 +426,12 @@ int gc_full_geom(const GcParams& p, GcGeom& g) {
 
 }  // namespace
 
+bool gc_can_emit_image(int cout, int k, int u) {
+  GcGeom g;
+  if (gc_layer_geom(1, 16, cout, k, u, g) != AB_OK) return false;
+  return g.grouped && (cout % 16) == 0;
+}
+
 size_t gc_weight_image_bytes(int mode, int cin, int cout, int k, int d_or_u) {
   GcGeom g;
   if (gc_layer_geom(mode, cin, cout, k, d_or_u, g) != AB_OK) return 0;
@@ -426,6 +458,8 @@ int launch_gemmconv(const GcParams& p, cudaStream_t s) {
   GcGeom g;
   int rc = gc_full_geom(p, g);
   if (rc != AB_OK) return rc;
+  if (p.yimg != nullptr && !(p.mode == 1 && g.grouped && (p.Cout % 16) == 0))
+    return fail(AB_ERR_UNSUPPORTED, "gemmconv: cannot emit an operand image for this layer");
   static bool configured = false;
   if (!configured) {
     AB_CUDA_TRY(cudaFuncSetAttribute(gemmconv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GC_SMEM_LIMIT));

@@ -22,6 +22,12 @@ struct TcConvParams {
   int k, d1, nconv;
   float pre_slope, mid_slope, out_div;
   int precision;          // AB_PREC_TC_F16 | AB_PREC_TC_BF16
+  // fp16/bf16 operand images [B][Np/8][T][8] (Np = C rounded up to 16): when ximg is given the prologue is
+  // a cp.async burst of already activated operands (pre_slope is ignored); when yimg is given the epilogue
+  // also stores cvt(lrelu(y, img_slope)) for the next kernel
+  const uint16_t* ximg;
+  uint16_t* yimg;
+  float img_slope;
 };
 
 // N-blocked implicit GEMM (ab_kernels_gemmconv.cu): ConvTranspose1d (mode 1) and wide Conv1d (mode 0)
@@ -37,16 +43,19 @@ struct GcParams {
   float pre_slope;
   int post_tanh;          // conv only
   int precision;
+  uint16_t* yimg;         // conv-transpose only, nullable: operand image of lrelu(y, img_slope)
+  float img_slope;
 };
+bool gc_can_emit_image(int cout, int k, int u);
 size_t gc_weight_image_bytes(int mode, int cin, int cout, int k, int d_or_u);
 int launch_gc_pack_weight(const float* w_t, void* image, int mode, int cin, int cout, int k, int d_or_u,
                           int precision, cudaStream_t s);
 int launch_gemmconv(const GcParams& p, cudaStream_t s);
 
-int tc_layout();
 int tc_max_channels();
 bool tc_conv_supported(int C, int k);
 size_t tc_weight_image_bytes(int cin, int cout, int k);
+size_t tc_act_image_bytes(int64_t B, int C, int64_t T);
 // w_t: fp32 [Cin][k][Cout] (the repacked fp32 image) -> 16-bit operand image
 int launch_tc_pack_weight(const float* w_t, void* image, int cin, int cout, int k, int precision,
                           cudaStream_t s);

@@ -71,6 +71,18 @@ __device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t adesc, uint
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Ampere-style async copies (LDGSTS): register-free, so the bytes in flight are not bounded by the
+// register file.  src_bytes = 0 zero-fills the 16-byte destination (used for out-of-range rows).
+__device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait_group() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
                : "memory");
@@ -86,14 +98,6 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&r)[16]) {
 }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// no-swizzle K-major shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
-//   [0,14) start>>4 | [16,30) LBO>>4 (next core matrix along K) | [32,46) SBO>>4
-//   (next 8-row group along M/N) | [46,48) version=1 | [61,64) layout=0 (none)
-__device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t lbo, uint32_t sbo) {
-  return (uint64_t)((addr >> 4) & 0x3FFFu) | ((uint64_t)((lbo >> 4) & 0x3FFFu) << 16) |
-         ((uint64_t)((sbo >> 4) & 0x3FFFu) << 32) | (1ull << 46);
-}
-
 __device__ __forceinline__ uint32_t pack2(float a, float b, int bf16) {
   if (bf16) {
     __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
@@ -108,15 +112,19 @@ __device__ __forceinline__ uint32_t pack2(float a, float b, int bf16) {
 
 __device__ __forceinline__ float lrelu(float v, float slope) { return v >= 0.f ? v : v * slope; }
 
-// Operand tile addressing.  `rows` = rows of the tile (A: rowsA, B: Np).
-//   layout 0 (no swizzle):   [c8][row][16 B]                     -> K-adjacent 16-B units are rows*16 B apart
-//   layout 1 (SWIZZLE_32B):  [c16][row][32 B], 16-B halves XOR-ed with address bit 7 (= (row>>2)&1 for a
-//                            256-B aligned chunk): each row's K=16 slice is 32 contiguous bytes
-__device__ __forceinline__ uint32_t unit_offset(int layout, int rows, int c8, int row) {
-  if (layout == 0) return (uint32_t)c8 * (uint32_t)rows * 16u + (uint32_t)row * 16u;
+// Operand tile addressing: SWIZZLE_32B K-major rows.  `rows` = rows of the tile (A: rowsA, B: N block).
+//   [c16][row][32 B]; within a row the two 16-byte halves (8 channels each) are XOR-ed with address
+//   bit 7 (= (row>>2)&1 for a 256-byte aligned chunk), so each row's K=16 slice is 32 contiguous bytes
+//   and 8 consecutive rows hit 32 distinct banks.  (A no-swizzle interleaved variant was measured to
+//   give identical MMA rates: the operand path is 64 B/clk either way — DESIGN.md §6.)
+__device__ __forceinline__ uint32_t unit_offset(int rows, int c8, int row) {
   return (uint32_t)(c8 >> 1) * (uint32_t)rows * 32u + (uint32_t)row * 32u +
          ((uint32_t)((c8 & 1) ^ ((row >> 2) & 1)) << 4);
 }
+// descriptor constants for that layout (cute::UMMA::SmemDescriptor): SBO = 256 B (next 8-row group),
+// version 1, layout_type 6 (SWIZZLE_32B); LBO field 1 (unused for swizzled K-major)
+__device__ __forceinline__ uint64_t desc_hi_sw32() { return ((uint64_t)(16u | (1u << 14)) << 32) | (6ull << 61); }
+__device__ __forceinline__ uint32_t desc_lo_sw32(uint32_t addr16) { return addr16 | (1u << 16); }
 
 // one lane of a converged warp (the canonical way to issue tcgen05.mma / commit)
 __device__ __forceinline__ uint32_t elect_one_sync() {
