@@ -58,12 +58,16 @@ struct TcGeom {
   int tmem_cols;   // TMEM columns to allocate (power of two >= m*Np)
   int dual;        // 1: half-size tile, 4 worker warps, two CTAs per SM
   int staged;      // 1: epilogue 2 streams residual / branch sum through the cp.async ring (needs T % 4 == 0)
+  int stagger_groups, first_wave;   // first-wave CTAs start (blockIdx % groups) * stagger_cycles late so that the
+  long long stagger_cycles;         // HBM-bound phases of identical tiles do not run in lock-step chip-wide
+  float out_scale; // 1 / out_div (the reference divides, hifigan.py:214; <= 1 ulp apart)
+  int skip;        // debug timing experiments (AB_TC_DEBUG_SKIP bitmask): 1 no fp32 y store, 2 no image store, 4 no residual loads
   long long* dbg;  // debug: per-CTA phase timestamps (AB_TC_DEBUG_TIMING=1), else nullptr
 };
 
 constexpr int DBG_BLOCKS = 2048, DBG_SLOTS = 8;
 
-template <int WW, int MINB>
+template <int WW, int MINB, int BF16>
 __global__ void __launch_bounds__(WW * 32 + 64, MINB) tc_conv_kernel(TcConvParams p, TcGeom g) {
   constexpr int WORKERS = WW * 32;
   constexpr int NWG = WW / 4;   // worker warps per TMEM lane quarter
@@ -71,7 +75,7 @@ __global__ void __launch_bounds__(WW * 32 + 64, MINB) tc_conv_kernel(TcConvParam
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.x / g.tiles, tile = blockIdx.x - b * g.tiles;
   const int T0 = tile * g.V;
-  const int bf16 = p.precision == AB_PREC_TC_BF16;
+  constexpr int bf16 = BF16;
 
   const uint32_t sA = smem_u32(smem);
   const uint32_t sW = sA + g.off_w;
@@ -108,6 +112,11 @@ __global__ void __launch_bounds__(WW * 32 + 64, MINB) tc_conv_kernel(TcConvParam
     if (g.dbg != nullptr && threadIdx.x == 0 && blockIdx.x < DBG_BLOCKS)
       g.dbg[blockIdx.x * DBG_SLOTS + slot] = clock64();
   };
+  if (g.stagger_groups > 1 && (int)blockIdx.x < g.first_wave) {
+    const long long wait = (long long)(blockIdx.x % (unsigned)g.stagger_groups) * g.stagger_cycles;
+    const long long t0 = clock64();
+    while (clock64() - t0 < wait) __nanosleep(500);
+  }
   stamp(0);
 
   if (warp < WW) {
@@ -156,10 +165,10 @@ __global__ void __launch_bounds__(WW * 32 + 64, MINB) tc_conv_kernel(TcConvParam
           const int row = row0 + 32 * r;
           if (row < g.rowsA) {
             uint4 q;
-            q.x = pack2(lrelu(v[r][0], p.pre_slope), lrelu(v[r][1], p.pre_slope), bf16);
-            q.y = pack2(lrelu(v[r][2], p.pre_slope), lrelu(v[r][3], p.pre_slope), bf16);
-            q.z = pack2(lrelu(v[r][4], p.pre_slope), lrelu(v[r][5], p.pre_slope), bf16);
-            q.w = pack2(lrelu(v[r][6], p.pre_slope), lrelu(v[r][7], p.pre_slope), bf16);
+            q.x = pack2t<BF16>(lrelu(v[r][0], p.pre_slope), lrelu(v[r][1], p.pre_slope));
+            q.y = pack2t<BF16>(lrelu(v[r][2], p.pre_slope), lrelu(v[r][3], p.pre_slope));
+            q.z = pack2t<BF16>(lrelu(v[r][4], p.pre_slope), lrelu(v[r][5], p.pre_slope));
+            q.w = pack2t<BF16>(lrelu(v[r][6], p.pre_slope), lrelu(v[r][7], p.pre_slope));
             *reinterpret_cast<uint4*>(smem + unit_offset(g.rowsA, c8, row)) = q;
           }
         }
@@ -193,10 +202,10 @@ __global__ void __launch_bounds__(WW * 32 + 64, MINB) tc_conv_kernel(TcConvParam
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             uint4 q;
-            q.x = pack2(v[8 * h + 0], v[8 * h + 1], bf16);
-            q.y = pack2(v[8 * h + 2], v[8 * h + 3], bf16);
-            q.z = pack2(v[8 * h + 4], v[8 * h + 5], bf16);
-            q.w = pack2(v[8 * h + 6], v[8 * h + 7], bf16);
+            q.x = pack2t<BF16>(v[8 * h + 0], v[8 * h + 1]);
+            q.y = pack2t<BF16>(v[8 * h + 2], v[8 * h + 3]);
+            q.z = pack2t<BF16>(v[8 * h + 4], v[8 * h + 5]);
+            q.w = pack2t<BF16>(v[8 * h + 6], v[8 * h + 7]);
             *reinterpret_cast<uint4*>(smem + unit_offset(g.rowsA, ch * 2 + h, row)) = q;
           }
         }
@@ -215,6 +224,7 @@ __global__ void __launch_bounds__(WW * 32 + 64, MINB) tc_conv_kernel(TcConvParam
     if (g.staged) {
       // All MMAs have completed, so the A region is free: each warp streams the residual / branch-sum
       // values of its own (32 rows x 16 channels) items through a private cp.async ring there.
+      const bool has_res = p.residual != nullptr && !(g.skip & 4), has_acc = p.acc_prev != nullptr && !(g.skip & 4);
       const int nchw = (nch - hsel + NWG - 1) / NWG;     // column chunks owned by this warp
       const int nitems = g.m * nchw;
       uint8_t* ring = smem + (size_t)warp * (RING_DEPTH * RING_SLOT_BYTES);
@@ -228,8 +238,8 @@ __global__ void __launch_bounds__(WW * 32 + 64, MINB) tc_conv_kernel(TcConvParam
           const int co = ch * 16 + c, t = tb + 4 * r4;
           const bool ok = co < p.C && t < p.T;
           const int64_t off = bCT + (int64_t)co * p.T + t;
-          if (p.residual) cp_async16(slot + (uint32_t)(c * 128 + r4 * 16), ok ? p.residual + off : p.residual, ok ? 16u : 0u);
-          if (p.acc_prev) cp_async16(slot + 2048u + (uint32_t)(c * 128 + r4 * 16), ok ? p.acc_prev + off : p.acc_prev, ok ? 16u : 0u);
+          if (p.residual && !(g.skip & 4)) cp_async16(slot + (uint32_t)(c * 128 + r4 * 16), ok ? p.residual + off : p.residual, ok ? 16u : 0u);
+          if (p.acc_prev && !(g.skip & 4)) cp_async16(slot + 2048u + (uint32_t)(c * 128 + r4 * 16), ok ? p.acc_prev + off : p.acc_prev, ok ? 16u : 0u);
         }
         cp_async_commit();
       };
@@ -248,26 +258,34 @@ __global__ void __launch_bounds__(WW * 32 + 64, MINB) tc_conv_kernel(TcConvParam
         const int row = i * 128 + q4 * 32 + lane;
         const int t = T0 + row;
         const bool ok = row < g.V && t < p.T;
+        const bool full = ch * 16 + 16 <= p.C;
+        float bv[16];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float4 b4 = *reinterpret_cast<const float4*>(bias2 + ch * 16 + 4 * q);
+          bv[4 * q] = b4.x; bv[4 * q + 1] = b4.y; bv[4 * q + 2] = b4.z; bv[4 * q + 3] = b4.w;
+        }
+        float* yp = p.y + bCT + (int64_t)(ch * 16) * p.T + t;
         float v[16];
 #pragma unroll
         for (int e = 0; e < 16; ++e) {
-          const int co = ch * 16 + e;
-          float a = __uint_as_float(r[e]) + bias2[co];
-          if (p.residual) a += rs[e * 32 + lane];
-          if (p.acc_prev) a += rs[512 + e * 32 + lane];
-          if (p.out_div != 1.0f) a = a / p.out_div;
+          float a = __uint_as_float(r[e]) + bv[e];
+          if (has_res) a += rs[e * 32 + lane];
+          if (has_acc) a += rs[512 + e * 32 + lane];
+          a *= g.out_scale;
           v[e] = a;
-          if (ok && co < p.C) p.y[bCT + (int64_t)co * p.T + t] = a;
+          if (ok && (full || ch * 16 + e < p.C) && !(g.skip & 1)) *yp = a;
+          yp += p.T;
         }
-        if (p.yimg != nullptr && ok) {
+        if (p.yimg != nullptr && ok && !(g.skip & 2)) {
           uint16_t* yi = p.yimg + (((size_t)b * c8n + (size_t)ch * 2) * p.T + (size_t)t) * 8;
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             uint4 q;
-            q.x = pack2(lrelu(v[8 * h + 0], p.img_slope), lrelu(v[8 * h + 1], p.img_slope), bf16);
-            q.y = pack2(lrelu(v[8 * h + 2], p.img_slope), lrelu(v[8 * h + 3], p.img_slope), bf16);
-            q.z = pack2(lrelu(v[8 * h + 4], p.img_slope), lrelu(v[8 * h + 5], p.img_slope), bf16);
-            q.w = pack2(lrelu(v[8 * h + 6], p.img_slope), lrelu(v[8 * h + 7], p.img_slope), bf16);
+            q.x = pack2t<BF16>(lrelu(v[8 * h + 0], p.img_slope), lrelu(v[8 * h + 1], p.img_slope));
+            q.y = pack2t<BF16>(lrelu(v[8 * h + 2], p.img_slope), lrelu(v[8 * h + 3], p.img_slope));
+            q.z = pack2t<BF16>(lrelu(v[8 * h + 4], p.img_slope), lrelu(v[8 * h + 5], p.img_slope));
+            q.w = pack2t<BF16>(lrelu(v[8 * h + 6], p.img_slope), lrelu(v[8 * h + 7], p.img_slope));
             *reinterpret_cast<uint4*>(yi + (size_t)h * p.T * 8) = q;
           }
         }
@@ -299,7 +317,7 @@ __global__ void __launch_bounds__(WW * 32 + 64, MINB) tc_conv_kernel(TcConvParam
             float a = __uint_as_float(r[e]) + bias2[co];
             a += res[e];
             a += acp[e];
-            if (p.out_div != 1.0f) a = a / p.out_div;
+            a *= g.out_scale;
             v[e] = a;
             if (ok && co < p.C) p.y[bCT + (int64_t)co * p.T + t] = a;
           }
@@ -308,10 +326,10 @@ __global__ void __launch_bounds__(WW * 32 + 64, MINB) tc_conv_kernel(TcConvParam
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
               uint4 q;
-              q.x = pack2(lrelu(v[8 * h + 0], p.img_slope), lrelu(v[8 * h + 1], p.img_slope), bf16);
-              q.y = pack2(lrelu(v[8 * h + 2], p.img_slope), lrelu(v[8 * h + 3], p.img_slope), bf16);
-              q.z = pack2(lrelu(v[8 * h + 4], p.img_slope), lrelu(v[8 * h + 5], p.img_slope), bf16);
-              q.w = pack2(lrelu(v[8 * h + 6], p.img_slope), lrelu(v[8 * h + 7], p.img_slope), bf16);
+              q.x = pack2t<BF16>(lrelu(v[8 * h + 0], p.img_slope), lrelu(v[8 * h + 1], p.img_slope));
+              q.y = pack2t<BF16>(lrelu(v[8 * h + 2], p.img_slope), lrelu(v[8 * h + 3], p.img_slope));
+              q.z = pack2t<BF16>(lrelu(v[8 * h + 4], p.img_slope), lrelu(v[8 * h + 5], p.img_slope));
+              q.w = pack2t<BF16>(lrelu(v[8 * h + 6], p.img_slope), lrelu(v[8 * h + 7], p.img_slope));
               *reinterpret_cast<uint4*>(yi + (size_t)h * p.T * 8) = q;
             }
           }
@@ -477,6 +495,16 @@ int make_geom(const TcConvParams& p, TcGeom& g) {
   // N>>3 @17, M>>4 @24
   g.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(g.Np >> 3) << 17) | ((128u >> 4) << 24);
   g.dbg = nullptr;
+  g.out_scale = 1.0f / p.out_div;
+  static const int skip = [] { const char* e = getenv("AB_TC_DEBUG_SKIP"); return e ? atoi(e) : 0; }();
+  g.skip = skip;
+  // stagger: period model = MMA issue time + HBM time of the tile at ~4.5 TB/s chip-wide
+  static const int stag = [] { const char* e = getenv("AB_TC_STAGGER"); return e ? atoi(e) : 0; }();
+  g.stagger_groups = stag;
+  g.first_wave = 148 * (g.dual ? 2 : 1);
+  const double mma = (double)p.nconv * p.k * g.nkc * g.m * 2.0 * (64.0 + g.Np / 2.0) * (g.dual ? 2.0 : 1.0);
+  const double mem = (double)g.m * 128.0 * g.Np * 12.0 / (g.dual ? 7.7 : 15.4);
+  g.stagger_cycles = stag > 1 ? (long long)((mma + mem + 8000.0) / stag) : 0;
   return AB_OK;
 }
 
@@ -516,8 +544,10 @@ int launch_tc_conv(const TcConvParams& p, cudaStream_t s) {
   if (rc != AB_OK) return rc;
   static bool configured = false;
   if (!configured) {
-    AB_CUDA_TRY(cudaFuncSetAttribute(tc_conv_kernel<8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_LIMIT));
-    AB_CUDA_TRY(cudaFuncSetAttribute(tc_conv_kernel<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
+    AB_CUDA_TRY(cudaFuncSetAttribute(tc_conv_kernel<8, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_LIMIT));
+    AB_CUDA_TRY(cudaFuncSetAttribute(tc_conv_kernel<8, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_LIMIT));
+    AB_CUDA_TRY(cudaFuncSetAttribute(tc_conv_kernel<4, 2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
+    AB_CUDA_TRY(cudaFuncSetAttribute(tc_conv_kernel<4, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
     configured = true;
   }
   const int64_t grid = (int64_t)p.B * g.tiles;
@@ -531,10 +561,14 @@ int launch_tc_conv(const TcConvParams& p, cudaStream_t s) {
     AB_CUDA_TRY(cudaMemsetAsync(dbg_buf, 0, sizeof(long long) * DBG_BLOCKS * DBG_SLOTS, s));
     g.dbg = dbg_buf;
   }
-  if (g.dual)
-    tc_conv_kernel<4, 2><<<(unsigned)grid, 4 * 32 + 64, smem, s>>>(p, g);
-  else
-    tc_conv_kernel<8, 1><<<(unsigned)grid, 8 * 32 + 64, smem, s>>>(p, g);
+  const bool bf = p.precision == AB_PREC_TC_BF16;
+  if (g.dual) {
+    if (bf) tc_conv_kernel<4, 2, 1><<<(unsigned)grid, 4 * 32 + 64, smem, s>>>(p, g);
+    else tc_conv_kernel<4, 2, 0><<<(unsigned)grid, 4 * 32 + 64, smem, s>>>(p, g);
+  } else {
+    if (bf) tc_conv_kernel<8, 1, 1><<<(unsigned)grid, 8 * 32 + 64, smem, s>>>(p, g);
+    else tc_conv_kernel<8, 1, 0><<<(unsigned)grid, 8 * 32 + 64, smem, s>>>(p, g);
+  }
   AB_LAUNCH_CHECK("tc_conv_kernel");
   if (dbg_on) {
     AB_CUDA_TRY(cudaStreamSynchronize(s));

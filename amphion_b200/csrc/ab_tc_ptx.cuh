@@ -98,19 +98,21 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&r)[16]) {
 }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-__device__ __forceinline__ uint32_t pack2(float a, float b, int bf16) {
-  if (bf16) {
-    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-    return *reinterpret_cast<uint32_t*>(&h);
-  }
-  // saturating: fp16 operands must never become inf
-  a = fminf(fmaxf(a, -65504.f), 65504.f);
-  b = fminf(fmaxf(b, -65504.f), 65504.f);
-  __half2 h = __floats2half2_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&h);
+// two fp32 -> packed 16-bit pair (first argument in the low half = lower address), round to nearest,
+// saturating to the largest finite value: operands must never become inf.  One F2FP.
+template <int BF16>
+__device__ __forceinline__ uint32_t pack2t(float lo, float hi) {
+  uint32_t r;
+  if (BF16) asm("cvt.rn.satfinite.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  else asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ uint32_t pack2(float lo, float hi, int bf16) {
+  return bf16 ? pack2t<1>(lo, hi) : pack2t<0>(lo, hi);
 }
 
-__device__ __forceinline__ float lrelu(float v, float slope) { return v >= 0.f ? v : v * slope; }
+// leaky_relu for 0 <= slope <= 1 (slope 1 = identity): max(v, slope*v)
+__device__ __forceinline__ float lrelu(float v, float slope) { return fmaxf(v, v * slope); }
 
 // Operand tile addressing: SWIZZLE_32B K-major rows.  `rows` = rows of the tile (A: rowsA, B: N block).
 //   [c16][row][32 B]; within a row the two 16-byte halves (8 channels each) are XOR-ed with address
