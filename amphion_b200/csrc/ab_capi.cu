@@ -480,13 +480,14 @@ int ab_generator_forward(ab_generator* g, const float* dev_mel, int64_t B, int64
     prof_end();
     return r;
   };
-  auto snake = [&](const ActRef& a, const float* x, float* y, int C, int Tn) -> int {
+  auto snake = [&](const ActRef& a, const float* x, float* y, int C, int Tn, uint16_t* yimg = nullptr) -> int {
     SnakeParams p;
+    p.yimg = yimg; p.bf16 = g->precision == AB_PREC_TC_BF16;
     p.x = x; p.y = y; p.alpha = g->fptr(a.alpha); p.beta = g->fptr(a.beta);
     p.f_up = g->fptr(a.fup); p.f_down = g->fptr(a.fdown);
     p.B = (int)B; p.C = C; p.T = Tn; p.logscale = g->cfg.snake_logscale;
     ++launches;
-    prof_begin(3, 0.0, 8.0 * (double)B * C * Tn);
+    prof_begin(3, 0.0, (double)B * C * Tn * (4.0 + (y ? 4.0 : 0.0) + (yimg ? 2.0 : 0.0)));
     const int r = launch_activation1d(p, st);
     prof_end();
     return r;
@@ -590,20 +591,22 @@ int ab_generator_forward(ab_generator* g, const float* dev_mel, int64_t B, int64
           }
         } else {
           // AMPBlock: anti-aliased snake in front of every conv (bigvgan.py:137-146, :222-228)
+          // tensor-core path: the activation kernel writes the 16-bit operand image only (no fp32 copy)
           const ActRef& a1 = pair ? blk.acts[2 * p] : blk.acts[p];
-          rc = snake(a1, cur, ACT, C, Tn);
+          uint16_t* A16 = P16[0];
+          rc = blk_tc ? snake(a1, cur, nullptr, C, Tn, A16) : snake(a1, cur, ACT, C, Tn);
           if (rc != AB_OK) return rc;
           if (pair) {
-            if (blk_tc) rc = tc_convs(blk.c1[p], nullptr, ACT, TMP, C, Tn, 1.0f, 1.0f, nullptr, nullptr, 1.0f, nullptr, nullptr);
+            if (blk_tc) rc = tc_convs(blk.c1[p], nullptr, cur, TMP, C, Tn, 1.0f, 1.0f, nullptr, nullptr, 1.0f, A16, nullptr);
             else rc = conv(blk.c1[p], ACT, sb, sc, 1, TMP, Tn, 1.0f, nullptr, nullptr, 1.0f, 0);
             if (rc != AB_OK) return rc;
-            rc = snake(blk.acts[2 * p + 1], TMP, ACT, C, Tn);
+            rc = blk_tc ? snake(blk.acts[2 * p + 1], TMP, nullptr, C, Tn, A16) : snake(blk.acts[2 * p + 1], TMP, ACT, C, Tn);
             if (rc != AB_OK) return rc;
-            if (blk_tc) rc = tc_convs(blk.c2[p], nullptr, ACT, dst, C, Tn, 1.0f, 1.0f, cur, accp, div, nullptr, nullptr);
+            if (blk_tc) rc = tc_convs(blk.c2[p], nullptr, TMP, dst, C, Tn, 1.0f, 1.0f, cur, accp, div, A16, nullptr);
             else rc = conv(blk.c2[p], ACT, sb, sc, 1, dst, Tn, 1.0f, cur, accp, div, 0);
             if (rc != AB_OK) return rc;
           } else {
-            if (blk_tc) rc = tc_convs(blk.c1[p], nullptr, ACT, dst, C, Tn, 1.0f, 1.0f, cur, accp, div, nullptr, nullptr);
+            if (blk_tc) rc = tc_convs(blk.c1[p], nullptr, cur, dst, C, Tn, 1.0f, 1.0f, cur, accp, div, A16, nullptr);
             else rc = conv(blk.c1[p], ACT, sb, sc, 1, dst, Tn, 1.0f, cur, accp, div, 0);
             if (rc != AB_OK) return rc;
           }
@@ -641,6 +644,7 @@ int ab_activation1d_forward(const float* dev_x, float* dev_y, int64_t B, int64_t
   SnakeParams p;
   p.x = dev_x; p.y = dev_y; p.alpha = dev_alpha; p.beta = dev_beta; p.f_up = f_up; p.f_down = f_down;
   p.B = (int)B; p.C = (int)C; p.T = (int)T; p.logscale = logscale;
+  p.yimg = nullptr; p.bf16 = 0;
   return launch_activation1d(p, static_cast<cudaStream_t>(stream));
 }
 

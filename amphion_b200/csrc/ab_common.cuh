@@ -67,6 +67,8 @@ struct SnakeParams {
   const float* f_down;  // [12]
   int B, C, T;
   int logscale;
+  uint16_t* yimg;       // optional 16-bit operand image [B][ceil16(C)/8][T][8] of y (y itself may then be null)
+  int bf16;
 };
 
 // launchers (ab_kernels_fp32.cu)

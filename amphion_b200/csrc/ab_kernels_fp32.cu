@@ -344,66 +344,104 @@ __device__ __forceinline__ float snake_eval(float u, float a, float invb) {
   return fmaf(invb, sv * sv, u);
 }
 
+// One CTA = (batch, group of 8 channels, 1024-sample tile); the 8 channels are processed one after the
+// other through the same shared-memory buffers so that the fp16 operand image (8 channels = 16 B per time
+// step, the unit the tensor-core kernels stage) can be written with coalesced 16-byte stores.
 __global__ void __launch_bounds__(NT) activation1d_kernel(SnakeParams p) {
   __shared__ float xs[AT + 13];
   __shared__ float ve[AT + 6];
   __shared__ float vo[AT + 6];
   __shared__ float fu[12], fd[12];
-  const int t0 = blockIdx.x * AT, c = blockIdx.y, b = blockIdx.z;
+  const int t0 = blockIdx.x * AT, c8 = blockIdx.y, b = blockIdx.z;
   const int T = p.T;
-  const float* xr = p.x + ((int64_t)b * p.C + c) * T;
-  float* yr = p.y + ((int64_t)b * p.C + c) * T;
   if (threadIdx.x < 12) {
     fu[threadIdx.x] = __ldg(p.f_up + threadIdx.x);
     fd[threadIdx.x] = __ldg(p.f_down + threadIdx.x);
   }
-  float a = __ldg(p.alpha + c), bb = __ldg(p.beta + c);
-  if (p.logscale) {
-    a = expf(a);
-    bb = expf(bb);
-  }
-  const float invb = 1.0f / (bb + 1e-9f);
-  for (int n = threadIdx.x; n < AT + 13; n += NT) {
-    int t = t0 - 6 + n;
-    t = min(max(t, 0), T - 1);
-    xs[n] = __ldg(xr + t);
-  }
-  __syncthreads();
+  float out[AT / NT][8];
+#pragma unroll
+  for (int r = 0; r < AT / NT; ++r)
+#pragma unroll
+    for (int cg = 0; cg < 8; ++cg) out[r][cg] = 0.f;
   const int i0 = 2 * t0 - 5;
   const int imax = 2 * T - 1;
-  for (int n = threadIdx.x; n < 2 * AT + 12; n += NT) {
-    const int ic = min(max(i0 + n, 0), imax);
-    const int q = ic >> 1, odd = ic & 1;
-    const float* xp = xs + (q + 3 + odd - t0);
-    const float* fp = fu + (11 - odd);
-    float u = 0.f;
 #pragma unroll
-    for (int m = 0; m < 6; ++m) u = fmaf(fp[-2 * m], xp[m], u);
-    u *= 2.0f;
-    const float v = snake_eval(u, a, invb);
-    if (n & 1) vo[n >> 1] = v; else ve[n >> 1] = v;
-  }
-  __syncthreads();
-#pragma unroll
-  for (int r = 0; r < AT / NT; ++r) {
-    const int tl = threadIdx.x + NT * r;
-    const int t = t0 + tl;
-    if (t >= T) continue;
-    float y = 0.f;
-#pragma unroll
-    for (int j = 0; j < 6; ++j) {
-      y = fmaf(fd[2 * j], ve[tl + j], y);
-      y = fmaf(fd[2 * j + 1], vo[tl + j], y);
+  for (int cg = 0; cg < 8; ++cg) {
+    const int c = c8 * 8 + cg;
+    if (c >= p.C) break;                       // block-uniform
+    const float* xr = p.x + ((int64_t)b * p.C + c) * T;
+    float a = __ldg(p.alpha + c), bb = __ldg(p.beta + c);
+    if (p.logscale) {
+      a = expf(a);
+      bb = expf(bb);
     }
-    yr[t] = y;
+    const float invb = 1.0f / (bb + 1e-9f);
+    __syncthreads();                           // previous channel's reads of xs/ve/vo are done
+    for (int n = threadIdx.x; n < AT + 13; n += NT) {
+      int t = t0 - 6 + n;
+      t = min(max(t, 0), T - 1);
+      xs[n] = __ldg(xr + t);
+    }
+    __syncthreads();
+    for (int n = threadIdx.x; n < 2 * AT + 12; n += NT) {
+      const int ic = min(max(i0 + n, 0), imax);
+      const int q = ic >> 1, odd = ic & 1;
+      const float* xp = xs + (q + 3 + odd - t0);
+      const float* fp = fu + (11 - odd);
+      float u = 0.f;
+#pragma unroll
+      for (int m = 0; m < 6; ++m) u = fmaf(fp[-2 * m], xp[m], u);
+      u *= 2.0f;
+      const float v = snake_eval(u, a, invb);
+      if (n & 1) vo[n >> 1] = v; else ve[n >> 1] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < AT / NT; ++r) {
+      const int tl = threadIdx.x + NT * r;
+      float y = 0.f;
+#pragma unroll
+      for (int j = 0; j < 6; ++j) {
+        y = fmaf(fd[2 * j], ve[tl + j], y);
+        y = fmaf(fd[2 * j + 1], vo[tl + j], y);
+      }
+      out[r][cg] = y;
+      if (p.y != nullptr && t0 + tl < T) p.y[((int64_t)b * p.C + c) * T + t0 + tl] = y;
+    }
+  }
+  if (p.yimg != nullptr) {
+    const int c8n = (int)gridDim.y;
+    uint16_t* yi = p.yimg + ((size_t)b * c8n + c8) * (size_t)T * 8;
+#pragma unroll
+    for (int r = 0; r < AT / NT; ++r) {
+      const int t = t0 + threadIdx.x + NT * r;
+      if (t < T) {
+        uint4 q;
+        if (p.bf16) {
+          asm("cvt.rn.satfinite.bf16x2.f32 %0, %1, %2;" : "=r"(q.x) : "f"(out[r][1]), "f"(out[r][0]));
+          asm("cvt.rn.satfinite.bf16x2.f32 %0, %1, %2;" : "=r"(q.y) : "f"(out[r][3]), "f"(out[r][2]));
+          asm("cvt.rn.satfinite.bf16x2.f32 %0, %1, %2;" : "=r"(q.z) : "f"(out[r][5]), "f"(out[r][4]));
+          asm("cvt.rn.satfinite.bf16x2.f32 %0, %1, %2;" : "=r"(q.w) : "f"(out[r][7]), "f"(out[r][6]));
+        } else {
+          asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(q.x) : "f"(out[r][1]), "f"(out[r][0]));
+          asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(q.y) : "f"(out[r][3]), "f"(out[r][2]));
+          asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(q.z) : "f"(out[r][5]), "f"(out[r][4]));
+          asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(q.w) : "f"(out[r][7]), "f"(out[r][6]));
+        }
+        *reinterpret_cast<uint4*>(yi + (size_t)t * 8) = q;
+      }
+    }
   }
 }
 }  // namespace
 
 int launch_activation1d(const SnakeParams& p, cudaStream_t s) {
   if (p.B <= 0 || p.C <= 0 || p.T <= 0) return fail(AB_ERR_ARG, "activation1d: bad shape");
-  if (p.C > 65535 || p.B > 65535) return fail(AB_ERR_UNSUPPORTED, "activation1d: B or C > 65535");
-  dim3 grid((unsigned)ceil_div(p.T, AT), (unsigned)p.C, (unsigned)p.B);
+  if (p.C > 65535 * 8 || p.B > 65535) return fail(AB_ERR_UNSUPPORTED, "activation1d: B or C too large");
+  if (p.y == nullptr && p.yimg == nullptr) return fail(AB_ERR_ARG, "activation1d: no output requested");
+  // channel groups: the operand image covers ceil16(C) channels (padding groups are written as zeros)
+  const int c8n = p.yimg ? (int)(ceil_div(p.C, 16) * 2) : (int)ceil_div(p.C, 8);
+  dim3 grid((unsigned)ceil_div(p.T, AT), (unsigned)c8n, (unsigned)p.B);
   activation1d_kernel<<<grid, NT, 0, s>>>(p);
   AB_LAUNCH_CHECK("activation1d_kernel");
   return AB_OK;

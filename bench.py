@@ -46,11 +46,18 @@ def parse():
     ap.add_argument("--frames", type=int, default=1024)
     ap.add_argument("--precision", default=os.environ.get("AMPHION_B200_PRECISION", "tc_f16"))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="hifigan_v1", choices=["hifigan_v1", "bigvgan_base"],
+                    help="hifigan_v1 = BASELINE config 2 (the headline, default); bigvgan_base = config 3 "
+                         "(batch 32, 100x1024 mel, 24 kHz) for the results table")
     return ap.parse_args()
 
 
-def make_cfg():
+def make_cfg(workload="hifigan_v1"):
     from types import SimpleNamespace as NS
+    if workload == "bigvgan_base":
+        pre = NS(n_mel=100, hop_size=HOP, extract_amplitude_phase=False)
+        hp = dict(HP_V1, activation="snakebeta", snake_logscale=True)
+        return NS(preprocess=pre, model=NS(generator="bigvgan", bigvgan=NS(**hp)))
     pre = NS(n_mel=N_MEL, hop_size=HOP, extract_amplitude_phase=False)
     return NS(preprocess=pre, model=NS(generator="hifigan", hifigan=NS(**HP_V1)))
 
@@ -185,12 +192,24 @@ def run_native(args, rank, local_rank, world):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    cfg = make_cfg()
+    cfg = make_cfg(args.workload)
     torch.manual_seed(1234)
-    model = HiFiGAN(cfg).to(dev).eval()
+    if args.workload == "bigvgan_base":
+        from amphion_b200.vocoders.bigvgan import BigVGAN
+        model = BigVGAN(cfg).to(dev).eval()
+        gsn = torch.Generator().manual_seed(1)
+        with torch.no_grad():       # alpha/beta ~ N(0, 0.3): the default 0 is too benign
+            for n, prm in model.named_parameters():
+                if n.endswith(".alpha") or n.endswith(".beta"):
+                    prm.copy_((torch.randn(prm.shape, generator=gsn) * 0.3).to(dev))
+        if args.batch == 64:
+            args.batch = 32
+    else:
+        model = HiFiGAN(cfg).to(dev).eval()
     model.precision = args.precision
     B, T = args.batch, args.frames
-    mel = torch.randn(B, N_MEL, T, generator=torch.Generator().manual_seed(rank)).to(dev)
+    n_mel = cfg.preprocess.n_mel
+    mel = torch.randn(B, n_mel, T, generator=torch.Generator().manual_seed(rank)).to(dev)
     samples_step = world * B * T * HOP
     gathered = torch.empty(world * B, 1, T * HOP, device=dev) if world > 1 else None
 
@@ -252,21 +271,26 @@ def run_native(args, rank, local_rank, world):
 
     if rank == 0:
         pk = peaks()
-        dom = "tc_conv" if prof["tc_conv"]["launches"] else "conv1d_fp32"
+        dom = max(prof, key=lambda k: prof[k]["ms"])
         d = prof[dom]
         tf = d["flops"] / (d["ms"] / 1e3) / 1e12 if d["ms"] > 0 else 0.0
         gbs = d["bytes"] / (d["ms"] / 1e3) / 1e9 if d["ms"] > 0 else 0.0
-        roofline = dict(bound="tensor", kernel=dom + "_kernel", achieved=tf, peak=pk["tensor"], unit="TFLOP/s",
-                        frac=tf / pk["tensor"], traffic=None, peak_source=pk["source"] + ", bf16 sustained",
+        hbm_bound = dom == "activation1d"     # the anti-aliased Snake is an 8 B/element streaming kernel
+        roofline = dict(bound="hbm" if hbm_bound else "tensor", kernel=dom + "_kernel",
+                        achieved=gbs if hbm_bound else tf, peak=pk["hbm"] if hbm_bound else pk["tensor"],
+                        unit="GB/s" if hbm_bound else "TFLOP/s",
+                        frac=(gbs / pk["hbm"]) if hbm_bound else (tf / pk["tensor"]), traffic=None,
+                        peak_source=pk["source"] + (", copy" if hbm_bound else ", bf16 sustained"),
                         launches=d["launches"], avg_launch_ms=d["ms"] / max(d["launches"], 1),
                         share_of_step=d["ms"] / ms_total,
+                        tensor=dict(achieved=tf, peak=pk["tensor"], unit="TFLOP/s", frac=tf / pk["tensor"]),
                         hbm=dict(achieved=gbs, peak=pk["hbm"], unit="GB/s", frac=gbs / pk["hbm"],
-                                 note="algorithmic bytes of the fused pair (x read + y write + weights once)"),
+                                 note="algorithmic bytes: fp32 x read + y write (+ branch sum) + weights once"),
                         whole_step=dict(tflops=samples_step / world * FLOP_PER_SAMPLE / (ms_step / 1e3) / 1e12,
                                         frac_of_tensor_peak=samples_step / world * FLOP_PER_SAMPLE / (ms_step / 1e3) / 1e12 / pk["tensor"]),
                         classes={k: dict(launches=v["launches"], ms=round(v["ms"], 3)) for k, v in prof.items()})
         cpu = None
-        if world == 1 and not args.no_cpu_baseline:
+        if world == 1 and not args.no_cpu_baseline and args.workload == "hifigan_v1":
             v, cores, dt, sample = cpu_oracle_samples_per_sec(T, batch=2, repeats=2)
             cpu = dict(value=v, unit=UNIT, cores=cores, kind="port", sample=sample, seconds=dt)
         dt = {"fp32": "f32", "tc_f16": "f16 operands, f32 accumulate (tcgen05); f32 elsewhere",
@@ -274,11 +298,12 @@ def run_native(args, rank, local_rank, world):
         line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
                     ms_per_step=ms_step, higher_is_better=True, scaling="weak", vs_baseline=None, dtype=dt,
                     data="synthetic",
-                    config=dict(workload="HiFi-GAN V1 22.05kHz generator forward, batch=%d per GPU, 80x%d synthetic mel"
-                                         % (B, T), global_batch=world * B, frames=T, hop=HOP, precision=args.precision,
+                    config=dict(workload=("HiFi-GAN V1 22.05kHz" if args.workload == "hifigan_v1" else "BigVGAN-base 24kHz")
+                                + " generator forward, batch=%d per GPU, %dx%d synthetic mel" % (B, n_mel, T),
+                                global_batch=world * B, frames=T, hop=HOP, precision=args.precision,
                                 parallelism="utterance-batch sharding dp%d, NCCL all-gather of wav" % world,
                                 l2="no explicit flush: each step streams >8 GB of stage tensors (>> 126 MB L2)"),
-                    e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=world * B * N_MEL * T * 4,
+                    e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=world * B * n_mel * T * 4,
                              d2h_bytes_per_step=world * B * T * HOP * 4, ms_per_step=e2e_ms_total / args.steps),
                     gpu_launches=launches, clocks=clocks, roofline=roofline, cpu_baseline=cpu, impl="native")
         print(json.dumps(line))
