@@ -52,6 +52,8 @@ struct Slot {
   size_t tc_offset;
   size_t tc_bytes;
   int stride;         // ConvTranspose1d stride (SLOT_CONVT_W)
+  int dilation;       // Conv1d dilation (SLOT_CONV_W)
+  int tc_kind;        // 0 none, 1 tc_conv image (square, C <= 256), 2 gemmconv image
 };
 
 struct ConvRef {   // one weight-normed conv of the model
@@ -129,6 +131,8 @@ struct ab_generator {
     s.tc_offset = 0;
     s.tc_bytes = 0;
     s.stride = 1;
+    s.dilation = 1;
+    s.tc_kind = 0;
     fp32_bytes += align_up(s.bytes, 256);
     slots.push_back(s);
     index[name] = (int)slots.size() - 1;
@@ -150,6 +154,7 @@ ConvRef make_conv(ab_generator* g, const std::string& name, int cin, int cout, i
     c.w = g->add_slot(name + ".weight", SLOT_CONVT_W, {cin, cout, k});
   else
     c.w = g->add_slot(name + ".weight", SLOT_CONV_W, {cout, cin, k});
+  g->slots[c.w].dilation = d;
   c.b = g->add_slot(name + ".bias", SLOT_VEC, {cout});
   return c;
 }
@@ -254,10 +259,16 @@ int ab_generator_create(const ab_generator_config* cfg, ab_generator** out) {
   for (auto& s : g->slots) {
     if (s.kind == SLOT_CONV_W) {
       s.tc_bytes = tc_weight_image_bytes((int)s.shape[1], (int)s.shape[0], (int)s.shape[2]);
+      s.tc_kind = s.tc_bytes ? 1 : 0;
+      if (!s.tc_bytes && s.shape[1] <= 512) {   // non-square / wide convs (conv_pre, conv_post): N-blocked kernel
+        s.tc_bytes = gc_weight_image_bytes(0, (int)s.shape[1], (int)s.shape[0], (int)s.shape[2], s.dilation);
+        s.tc_kind = s.tc_bytes ? 2 : 0;
+      }
       s.tc_offset = g->fp32_bytes + tc;
       tc += align_up(s.tc_bytes, 256);
     } else if (s.kind == SLOT_CONVT_W) {
       s.tc_bytes = gc_weight_image_bytes(1, (int)s.shape[0], (int)s.shape[1], (int)s.shape[2], s.stride);
+      s.tc_kind = s.tc_bytes ? 2 : 0;
       s.tc_offset = g->fp32_bytes + tc;
       tc += align_up(s.tc_bytes, 256);
     }
@@ -343,9 +354,12 @@ int ab_generator_finalize(ab_generator* g, int32_t precision, void* stream) {
     for (size_t i = 0; i < g->slots.size(); ++i) {
       Slot& s = g->slots[i];
       int rc = AB_OK;
-      if (s.kind == SLOT_CONV_W)
+      if (s.kind == SLOT_CONV_W && s.tc_kind == 1)
         rc = launch_tc_pack_weight(g->fptr((int)i), g->tcptr((int)i), (int)s.shape[1], (int)s.shape[0],
                                    (int)s.shape[2], precision, st);
+      else if (s.kind == SLOT_CONV_W && s.tc_kind == 2)
+        rc = launch_gc_pack_weight(g->fptr((int)i), g->tcptr((int)i), 0, (int)s.shape[1], (int)s.shape[0],
+                                   (int)s.shape[2], s.dilation, precision, st);
       else if (s.kind == SLOT_CONVT_W && s.tc_bytes)
         rc = launch_gc_pack_weight(g->fptr((int)i), g->tcptr((int)i), 1, (int)s.shape[0], (int)s.shape[1],
                                    (int)s.shape[2], s.stride, precision, st);
@@ -474,9 +488,21 @@ int ab_generator_forward(ab_generator* g, const float* dev_mel, int64_t B, int64
     p.pre_slope = pre_slope; p.out_div = out_div; p.post_tanh = post_tanh;
     ++launches;
     const double el = (double)B * Tn;
-    prof_begin(1, 2.0 * el * c.cout * c.cin * c.k,
+    // conv_post (C -> 1, then tanh) stays on the exact fp32 kernel: it is HBM-bound and the last layer
+    const bool gc = tc && g->slots[c.w].tc_kind == 2 && acc_prev == nullptr && out_div == 1.0f && c.cout > 4;
+    prof_begin(gc ? 4 : 1, 2.0 * el * c.cout * c.cin * c.k,
                4.0 * (el * c.cin + el * c.cout * (1 + (residual != nullptr) + (acc_prev != nullptr)) + (double)c.cin * c.cout * c.k));
-    const int r = launch_conv1d_fp32(p, st);
+    int r;
+    if (gc) {
+      GcParams gp;
+      gp.x = x; gp.xsb = xsb; gp.xsc = xsc; gp.xst = xst; gp.y = y; gp.w = g->tcptr(c.w); gp.bias = g->fptr(c.b);
+      gp.residual = residual; gp.B = (int)B; gp.Cin = c.cin; gp.Cout = c.cout; gp.Tin = Tn; gp.mode = 0;
+      gp.k = c.k; gp.d = c.d; gp.u = 1; gp.pre_slope = pre_slope; gp.post_tanh = post_tanh;
+      gp.precision = g->precision; gp.yimg = nullptr; gp.img_slope = 1.0f;
+      r = launch_gemmconv(gp, st);
+    } else {
+      r = launch_conv1d_fp32(p, st);
+    }
     prof_end();
     return r;
   };
@@ -538,7 +564,7 @@ int ab_generator_forward(ab_generator* g, const float* dev_mel, int64_t B, int64
     }
     if (tc && g->slots[sg.up.w].tc_bytes) {
       GcParams gp;
-      gp.x = R[cur_r]; gp.y = U; gp.w = g->tcptr(sg.up.w); gp.bias = g->fptr(sg.up.b); gp.residual = nullptr;
+      gp.x = R[cur_r]; gp.xsb = (int64_t)cin * Tn; gp.xsc = Tn; gp.xst = 1; gp.y = U; gp.w = g->tcptr(sg.up.w); gp.bias = g->fptr(sg.up.b); gp.residual = nullptr;
       gp.B = (int)B; gp.Cin = cin; gp.Cout = sg.ch; gp.Tin = Tn; gp.mode = 1; gp.k = sg.up.k; gp.d = 1; gp.u = sg.u;
       gp.pre_slope = tp.pre_slope; gp.post_tanh = 0; gp.precision = g->precision;
       // HiFi-GAN: every consumer of U applies lrelu(., 0.1) first (hifigan.py:95) -> emit that operand image
@@ -650,7 +676,8 @@ int ab_activation1d_forward(const float* dev_x, float* dev_y, int64_t B, int64_t
 
 size_t ab_conv1d_workspace_bytes(int64_t cin, int64_t cout, int32_t k, int32_t precision) {
   size_t n = align_up((size_t)cin * cout * k * sizeof(float), 256);
-  if (precision != AB_PREC_FP32) n += align_up(tc_weight_image_bytes((int)cin, (int)cout, k), 256);
+  if (precision != AB_PREC_FP32)
+    n += align_up(std::max(tc_weight_image_bytes((int)cin, (int)cout, k), gc_weight_image_bytes(0, (int)cin, (int)cout, k, 1)), 256);
   return n;
 }
 
@@ -673,8 +700,19 @@ int ab_conv1d_forward(const float* dev_x, const float* dev_w, const float* dev_b
     p.pre_slope = pre_slope; p.out_div = 1.0f; p.post_tanh = post_tanh;
     return launch_conv1d_fp32(p, st);
   }
-  if (cin != cout || post_tanh || !tc_conv_supported((int)cin, k))
-    return fail(AB_ERR_UNSUPPORTED, "conv1d: tensor-core path needs Cin == Cout <= %d and no tanh", tc_max_channels());
+  if (cin != cout || post_tanh || !tc_conv_supported((int)cin, k) || cin > tc_max_channels()) {
+    // non-square / wide / tanh: the N-blocked kernel
+    void* gimg = static_cast<char*>(ws) + align_up((size_t)cin * cout * k * sizeof(float), 256);
+    if (gc_weight_image_bytes(0, (int)cin, (int)cout, k, d) == 0) return fail(AB_ERR_UNSUPPORTED, "conv1d: %s", ab_last_error());
+    rc = launch_gc_pack_weight(w_t, gimg, 0, (int)cin, (int)cout, k, d, precision, st);
+    if (rc != AB_OK) return rc;
+    GcParams gp;
+    gp.x = dev_x; gp.xsb = cin * T; gp.xsc = T; gp.xst = 1; gp.y = dev_y; gp.w = gimg; gp.bias = dev_bias;
+    gp.residual = dev_residual; gp.B = (int)B; gp.Cin = (int)cin; gp.Cout = (int)cout; gp.Tin = (int)T; gp.mode = 0;
+    gp.k = k; gp.d = d; gp.u = 1; gp.pre_slope = pre_slope; gp.post_tanh = post_tanh; gp.precision = precision;
+    gp.yimg = nullptr; gp.img_slope = 1.0f;
+    return launch_gemmconv(gp, st);
+  }
   void* img = static_cast<char*>(ws) + align_up((size_t)cin * cout * k * sizeof(float), 256);
   rc = launch_tc_pack_weight(w_t, img, (int)cin, (int)cout, k, precision, st);
   if (rc != AB_OK) return rc;
@@ -710,7 +748,7 @@ int ab_conv_transpose1d_forward(const float* dev_x, const float* dev_w, const fl
     rc = launch_gc_pack_weight(w_t, img, 1, (int)cin, (int)cout, k, u, precision, st);
     if (rc != AB_OK) return rc;
     GcParams gp;
-    gp.x = dev_x; gp.y = dev_y; gp.w = img; gp.bias = dev_bias; gp.residual = nullptr;
+    gp.x = dev_x; gp.xsb = cin * Tin; gp.xsc = Tin; gp.xst = 1; gp.y = dev_y; gp.w = img; gp.bias = dev_bias; gp.residual = nullptr;
     gp.B = (int)B; gp.Cin = (int)cin; gp.Cout = (int)cout; gp.Tin = (int)Tin; gp.mode = 1; gp.k = k; gp.d = 1; gp.u = u;
     gp.pre_slope = pre_slope; gp.post_tanh = 0; gp.precision = precision;
     gp.yimg = nullptr; gp.img_slope = 1.0f;

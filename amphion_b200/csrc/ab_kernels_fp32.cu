@@ -347,86 +347,155 @@ __device__ __forceinline__ float snake_eval(float u, float a, float invb) {
 // One CTA = (batch, group of 8 channels, 1024-sample tile); the 8 channels are processed one after the
 // other through the same shared-memory buffers so that the fp16 operand image (8 channels = 16 B per time
 // step, the unit the tensor-core kernels stage) can be written with coalesced 16-byte stores.
-__global__ void __launch_bounds__(NT) activation1d_kernel(SnakeParams p) {
-  __shared__ float xs[AT + 13];
-  __shared__ float ve[AT + 6];
-  __shared__ float vo[AT + 6];
-  __shared__ float fu[12], fd[12];
+// Per channel: phase 1 computes the 2x-rate samples v = snake(up(x)) four at a time from one 7-sample
+// window of x (filters in registers, 4 x LDS.64 per 4 samples); phase 2 computes four consecutive outputs
+// per thread from an 18-sample window of v (5 x LDS.128).
+__global__ void __launch_bounds__(NT, 3) activation1d_kernel(SnakeParams p) {
+  __shared__ __align__(16) float xs[AT + 16];       // xs[n] = xhat[t0 - 5 + n]
+  __shared__ __align__(16) float vs[2 * AT + 24];   // vs[n] = v[clamp(2*t0 - 5 + n, 0, 2T-1)]
   const int t0 = blockIdx.x * AT, c8 = blockIdx.y, b = blockIdx.z;
   const int T = p.T;
-  if (threadIdx.x < 12) {
-    fu[threadIdx.x] = __ldg(p.f_up + threadIdx.x);
-    fd[threadIdx.x] = __ldg(p.f_down + threadIdx.x);
+  float fu[12], fd[12];
+#pragma unroll
+  for (int j = 0; j < 12; ++j) {
+    fu[j] = __ldg(p.f_up + j);
+    fd[j] = __ldg(p.f_down + j);
   }
-  float out[AT / NT][8];
+  float out[4][8];
 #pragma unroll
-  for (int r = 0; r < AT / NT; ++r)
+  for (int k = 0; k < 4; ++k)
 #pragma unroll
-    for (int cg = 0; cg < 8; ++cg) out[r][cg] = 0.f;
+    for (int cg = 0; cg < 8; ++cg) out[k][cg] = 0.f;
   const int i0 = 2 * t0 - 5;
   const int imax = 2 * T - 1;
+  const int tl = 4 * threadIdx.x;
+  // x rows are software-pipelined: the next channel's samples are fetched into registers while the
+  // current channel is being computed, so the global-load latency is off the critical path
+  constexpr int XL = (AT + 12 + NT - 1) / NT;   // x samples per thread
+  float xnext[XL];
+  auto fetch = [&](int c) {
+    const float* xr = p.x + ((int64_t)b * p.C + c) * T;
 #pragma unroll
+    for (int q = 0; q < XL; ++q) {
+      const int n = threadIdx.x + NT * q;
+      const int t = min(max(t0 - 5 + n, 0), T - 1);
+      xnext[q] = (n < AT + 12) ? __ldg(xr + t) : 0.f;
+    }
+  };
+  if (c8 * 8 < p.C) fetch(c8 * 8);
+#pragma unroll 1
   for (int cg = 0; cg < 8; ++cg) {
     const int c = c8 * 8 + cg;
     if (c >= p.C) break;                       // block-uniform
-    const float* xr = p.x + ((int64_t)b * p.C + c) * T;
     float a = __ldg(p.alpha + c), bb = __ldg(p.beta + c);
     if (p.logscale) {
       a = expf(a);
       bb = expf(bb);
     }
     const float invb = 1.0f / (bb + 1e-9f);
-    __syncthreads();                           // previous channel's reads of xs/ve/vo are done
-    for (int n = threadIdx.x; n < AT + 13; n += NT) {
-      int t = t0 - 6 + n;
-      t = min(max(t, 0), T - 1);
-      xs[n] = __ldg(xr + t);
+    __syncthreads();                           // previous channel's reads of xs / vs are done
+#pragma unroll
+    for (int q = 0; q < XL; ++q) {
+      const int n = threadIdx.x + NT * q;
+      if (n < AT + 12) xs[n] = xnext[q];
     }
     __syncthreads();
-    for (int n = threadIdx.x; n < 2 * AT + 12; n += NT) {
-      const int ic = min(max(i0 + n, 0), imax);
-      const int q = ic >> 1, odd = ic & 1;
-      const float* xp = xs + (q + 3 + odd - t0);
-      const float* fp = fu + (11 - odd);
-      float u = 0.f;
+    if (cg + 1 < 8 && c + 1 < p.C) fetch(c + 1);
+    // ---- phase 1: groups of 4 consecutive 2x-rate samples (2*AT + 12 of them)
+    for (int j = threadIdx.x; j < (2 * AT + 12) / 4; j += NT) {
+      const int n0 = 4 * j;
+      float v0, v1, v2, v3;
+      if (i0 + n0 >= 0 && i0 + n0 + 3 <= imax) {
+        // i0 + n0 is odd: samples (odd, even, odd, even); the first two read xhat[t0-5+2j+m], the last two +1
+        float w[8];
 #pragma unroll
-      for (int m = 0; m < 6; ++m) u = fmaf(fp[-2 * m], xp[m], u);
-      u *= 2.0f;
-      const float v = snake_eval(u, a, invb);
-      if (n & 1) vo[n >> 1] = v; else ve[n >> 1] = v;
-    }
-    __syncthreads();
+        for (int q = 0; q < 4; ++q) {
+          const float2 t2 = *reinterpret_cast<const float2*>(xs + 2 * j + 2 * q);
+          w[2 * q] = t2.x;
+          w[2 * q + 1] = t2.y;
+        }
+        float u0 = 0.f, u1 = 0.f, u2 = 0.f, u3 = 0.f;
 #pragma unroll
-    for (int r = 0; r < AT / NT; ++r) {
-      const int tl = threadIdx.x + NT * r;
-      float y = 0.f;
+        for (int m = 0; m < 6; ++m) {
+          u0 = fmaf(fu[10 - 2 * m], w[m], u0);
+          u1 = fmaf(fu[11 - 2 * m], w[m], u1);
+          u2 = fmaf(fu[10 - 2 * m], w[m + 1], u2);
+          u3 = fmaf(fu[11 - 2 * m], w[m + 1], u3);
+        }
+        v0 = snake_eval(2.0f * u0, a, invb);
+        v1 = snake_eval(2.0f * u1, a, invb);
+        v2 = snake_eval(2.0f * u2, a, invb);
+        v3 = snake_eval(2.0f * u3, a, invb);
+      } else {
+        float vv[4];
 #pragma unroll
-      for (int j = 0; j < 6; ++j) {
-        y = fmaf(fd[2 * j], ve[tl + j], y);
-        y = fmaf(fd[2 * j + 1], vo[tl + j], y);
+        for (int k = 0; k < 4; ++k) {      // sequence edges: replicate-clamped index, generic taps
+          const int ic = min(max(i0 + n0 + k, 0), imax);
+          const int q = ic >> 1, odd = ic & 1;
+          const float* xp = xs + (q - 3 + odd - (t0 - 5));
+          float u = 0.f;
+#pragma unroll
+          for (int m = 0; m < 6; ++m) u = fmaf(odd ? fu[10 - 2 * m] : fu[11 - 2 * m], xp[m], u);
+          vv[k] = snake_eval(2.0f * u, a, invb);
+        }
+        v0 = vv[0]; v1 = vv[1]; v2 = vv[2]; v3 = vv[3];
       }
-      out[r][cg] = y;
-      if (p.y != nullptr && t0 + tl < T) p.y[((int64_t)b * p.C + c) * T + t0 + tl] = y;
+      *reinterpret_cast<float4*>(vs + n0) = make_float4(v0, v1, v2, v3);
+    }
+    __syncthreads();
+    // ---- phase 2: four consecutive outputs per thread: y[t] = sum_j fd[j] * vs[2*(t - t0) + j]
+    {
+      float w[20];
+#pragma unroll
+      for (int q = 0; q < 5; ++q) {
+        const float4 t4 = *reinterpret_cast<const float4*>(vs + 2 * tl + 4 * q);
+        w[4 * q] = t4.x; w[4 * q + 1] = t4.y; w[4 * q + 2] = t4.z; w[4 * q + 3] = t4.w;
+      }
+      float y[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float acc = 0.f;
+#pragma unroll
+        for (int j = 0; j < 12; ++j) acc = fmaf(fd[j], w[2 * k + j], acc);
+        y[k] = acc;
+      }
+      // out[k][cg] with a compile-time cg: unrolled select keeps the accumulators in registers
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        if (q == cg) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) out[k][q] = y[k];
+        }
+      if (p.y != nullptr) {
+        float* yr = p.y + ((int64_t)b * p.C + c) * T + t0 + tl;
+        if (t0 + tl + 3 < T && (T & 3) == 0) {
+          *reinterpret_cast<float4*>(yr) = make_float4(y[0], y[1], y[2], y[3]);
+        } else {
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            if (t0 + tl + k < T) yr[k] = y[k];
+        }
+      }
     }
   }
   if (p.yimg != nullptr) {
     const int c8n = (int)gridDim.y;
     uint16_t* yi = p.yimg + ((size_t)b * c8n + c8) * (size_t)T * 8;
 #pragma unroll
-    for (int r = 0; r < AT / NT; ++r) {
-      const int t = t0 + threadIdx.x + NT * r;
+    for (int k = 0; k < 4; ++k) {
+      const int t = t0 + tl + k;
       if (t < T) {
         uint4 q;
         if (p.bf16) {
-          asm("cvt.rn.satfinite.bf16x2.f32 %0, %1, %2;" : "=r"(q.x) : "f"(out[r][1]), "f"(out[r][0]));
-          asm("cvt.rn.satfinite.bf16x2.f32 %0, %1, %2;" : "=r"(q.y) : "f"(out[r][3]), "f"(out[r][2]));
-          asm("cvt.rn.satfinite.bf16x2.f32 %0, %1, %2;" : "=r"(q.z) : "f"(out[r][5]), "f"(out[r][4]));
-          asm("cvt.rn.satfinite.bf16x2.f32 %0, %1, %2;" : "=r"(q.w) : "f"(out[r][7]), "f"(out[r][6]));
+          asm("cvt.rn.satfinite.bf16x2.f32 %0, %1, %2;" : "=r"(q.x) : "f"(out[k][1]), "f"(out[k][0]));
+          asm("cvt.rn.satfinite.bf16x2.f32 %0, %1, %2;" : "=r"(q.y) : "f"(out[k][3]), "f"(out[k][2]));
+          asm("cvt.rn.satfinite.bf16x2.f32 %0, %1, %2;" : "=r"(q.z) : "f"(out[k][5]), "f"(out[k][4]));
+          asm("cvt.rn.satfinite.bf16x2.f32 %0, %1, %2;" : "=r"(q.w) : "f"(out[k][7]), "f"(out[k][6]));
         } else {
-          asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(q.x) : "f"(out[r][1]), "f"(out[r][0]));
-          asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(q.y) : "f"(out[r][3]), "f"(out[r][2]));
-          asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(q.z) : "f"(out[r][5]), "f"(out[r][4]));
-          asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(q.w) : "f"(out[r][7]), "f"(out[r][6]));
+          asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(q.x) : "f"(out[k][1]), "f"(out[k][0]));
+          asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(q.y) : "f"(out[k][3]), "f"(out[k][2]));
+          asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(q.z) : "f"(out[k][5]), "f"(out[k][4]));
+          asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(q.w) : "f"(out[k][7]), "f"(out[k][6]));
         }
         *reinterpret_cast<uint4*>(yi + (size_t)t * 8) = q;
       }

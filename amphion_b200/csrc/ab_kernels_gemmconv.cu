@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(GC_THREADS, 1) gemmconv_kernel(GcParams p, GcG
     {
       const int ngrp = (g.rowsA + 127) >> 7;
       const int c8n = g.Kp >> 3;
-      const float* xb = p.x + (int64_t)b * p.Cin * p.Tin;
+      const float* xb = p.x + (int64_t)b * p.xsb;
       for (int item = warp; item < c8n * ngrp; item += GC_WORKER_WARPS) {
         const int c8 = item / ngrp, grp = item - c8 * ngrp;
         const int row0 = (grp << 7) + lane;
@@ -170,7 +170,7 @@ __global__ void __launch_bounds__(GC_THREADS, 1) gemmconv_kernel(GcParams p, GcG
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
             const int c = c8 * 8 + e;
-            v[r][e] = (ok && c < p.Cin) ? __ldg(xb + (int64_t)c * p.Tin + t) : 0.f;
+            v[r][e] = (ok && c < p.Cin) ? __ldg(xb + (int64_t)c * p.xsc + (int64_t)t * p.xst) : 0.f;
           }
         }
 #pragma unroll

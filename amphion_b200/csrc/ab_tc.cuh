@@ -32,7 +32,8 @@ struct TcConvParams {
 
 // N-blocked implicit GEMM (ab_kernels_gemmconv.cu): ConvTranspose1d (mode 1) and wide Conv1d (mode 0)
 struct GcParams {
-  const float* x;         // contiguous [B, Cin, Tin] fp32
+  const float* x;         // [B, Cin, Tin] fp32 with element strides xsb / xsc / xst
+  int64_t xsb, xsc, xst;
   float* y;               // conv: [B, Cout, Tin]; conv-transpose: [B, Cout, Tin*u]
   const void* w;          // operand image built by launch_gc_pack_weight
   const float* bias;      // nullable
