@@ -244,7 +244,7 @@ def run_native(args, rank, local_rank, world):
         prof = model.get_profile()
         model.set_profiling(False)
         clocks = sampler.stop() if rank == 0 else None
-        launches = model.last_launches * args.steps
+        launches = model.last_launches * args.steps * world      # whole job (every rank runs the same pipeline)
 
         # ---- end to end through the reference-facing call, host buffers ----
         mel_host = mel.cpu().pin_memory()
