@@ -53,7 +53,7 @@ struct Slot {
   size_t tc_bytes;
   int stride;         // ConvTranspose1d stride (SLOT_CONVT_W)
   int dilation;       // Conv1d dilation (SLOT_CONV_W)
-  int tc_kind;        // 0 none, 1 tc_conv image (square, C <= 256), 2 gemmconv image
+  int tc_kind;        // 0 none, 1 tc_conv image (square, C <= 256), 2 gemmconv image, 3 streaming gemmconv image
 };
 
 struct ConvRef {   // one weight-normed conv of the model
@@ -260,7 +260,11 @@ int ab_generator_create(const ab_generator_config* cfg, ab_generator** out) {
     if (s.kind == SLOT_CONV_W) {
       s.tc_bytes = tc_weight_image_bytes((int)s.shape[1], (int)s.shape[0], (int)s.shape[2]);
       s.tc_kind = s.tc_bytes ? 1 : 0;
-      if (!s.tc_bytes && s.shape[1] <= 512) {   // non-square / wide convs (conv_pre, conv_post): N-blocked kernel
+      if (!s.tc_bytes && s.shape[0] == s.shape[1] && s.shape[1] > 256) {
+        // wide square convs (BigVGAN-large stages 0/1): streaming N-blocked kernel fed from operand images
+        s.tc_bytes = gs_weight_image_bytes((int)s.shape[1], (int)s.shape[0], (int)s.shape[2], s.dilation);
+        s.tc_kind = s.tc_bytes ? 3 : 0;
+      } else if (!s.tc_bytes && s.shape[1] <= 512) {   // non-square convs (conv_pre, conv_post): N-blocked kernel
         s.tc_bytes = gc_weight_image_bytes(0, (int)s.shape[1], (int)s.shape[0], (int)s.shape[2], s.dilation);
         s.tc_kind = s.tc_bytes ? 2 : 0;
       }
@@ -357,6 +361,9 @@ int ab_generator_finalize(ab_generator* g, int32_t precision, void* stream) {
       if (s.kind == SLOT_CONV_W && s.tc_kind == 1)
         rc = launch_tc_pack_weight(g->fptr((int)i), g->tcptr((int)i), (int)s.shape[1], (int)s.shape[0],
                                    (int)s.shape[2], precision, st);
+      else if (s.kind == SLOT_CONV_W && s.tc_kind == 3)
+        rc = launch_gs_pack_weight(g->fptr((int)i), g->tcptr((int)i), (int)s.shape[1], (int)s.shape[0], (int)s.shape[2],
+                                   s.dilation, precision, st);
       else if (s.kind == SLOT_CONV_W && s.tc_kind == 2)
         rc = launch_gc_pack_weight(g->fptr((int)i), g->tcptr((int)i), 0, (int)s.shape[1], (int)s.shape[0],
                                    (int)s.shape[2], s.dilation, precision, st);
@@ -540,6 +547,22 @@ int ab_generator_forward(ab_generator* g, const float* dev_mel, int64_t B, int64
     return r;
   };
 
+  // wide single conv on the streaming tensor-core kernel (operand image in)
+  auto gs_conv = [&](const ConvRef& c, const uint16_t* ximg, float* y, int Tn, const float* residual,
+                     const float* acc_prev, float out_div) -> int {
+    GsParams p;
+    p.ximg = ximg; p.y = y; p.w = g->tcptr(c.w); p.bias = g->fptr(c.b); p.residual = residual; p.acc_prev = acc_prev;
+    p.B = (int)B; p.Cin = c.cin; p.Cout = c.cout; p.T = Tn; p.k = c.k; p.d = c.d; p.out_div = out_div;
+    p.precision = g->precision;
+    ++launches;
+    const double el = (double)B * Tn;
+    prof_begin(4, 2.0 * el * c.cout * c.cin * c.k,
+               4.0 * el * c.cout * (1 + (residual != nullptr) + (acc_prev != nullptr)) + 2.0 * el * c.cin + 4.0 * c.cin * c.cout * c.k);
+    const int r = launch_gemmconv_stream(p, st);
+    prof_end();
+    return r;
+  };
+
   // conv_pre (hifigan.py:204, bigvgan.py:314)
   const int C0 = g->cfg.upsample_initial_channel;
   rc = conv(g->conv_pre, dev_mel, mel_strides[0], mel_strides[1], mel_strides[2], R[0], (int)T, 1.0f,
@@ -598,6 +621,8 @@ int ab_generator_forward(ab_generator* g, const float* dev_mel, int64_t B, int64
         const float div = (last && j == nk - 1) ? (float)nk : 1.0f;
         const bool pair = !blk.c2.empty();
         const bool blk_tc = use_tc && tc_conv_supported(C, blk.k);
+        // wide layers (C > 256): streaming kernel, BigVGAN only (it needs the activation as an operand image)
+        const bool blk_gs = tc && big && !blk_tc && g->slots[blk.c1[0].w].tc_kind == 3;
         if (!big) {
           if (blk_tc) {
             rc = tc_convs(blk.c1[p], pair ? &blk.c2[p] : nullptr, cur, dst, C, Tn, 0.1f, 0.1f, cur, accp, div,
@@ -620,19 +645,23 @@ int ab_generator_forward(ab_generator* g, const float* dev_mel, int64_t B, int64
           // tensor-core path: the activation kernel writes the 16-bit operand image only (no fp32 copy)
           const ActRef& a1 = pair ? blk.acts[2 * p] : blk.acts[p];
           uint16_t* A16 = P16[0];
-          rc = blk_tc ? snake(a1, cur, nullptr, C, Tn, A16) : snake(a1, cur, ACT, C, Tn);
+          const bool img = blk_tc || blk_gs;
+          rc = img ? snake(a1, cur, nullptr, C, Tn, A16) : snake(a1, cur, ACT, C, Tn);
           if (rc != AB_OK) return rc;
           if (pair) {
             if (blk_tc) rc = tc_convs(blk.c1[p], nullptr, cur, TMP, C, Tn, 1.0f, 1.0f, nullptr, nullptr, 1.0f, A16, nullptr);
+            else if (blk_gs) rc = gs_conv(blk.c1[p], A16, TMP, Tn, nullptr, nullptr, 1.0f);
             else rc = conv(blk.c1[p], ACT, sb, sc, 1, TMP, Tn, 1.0f, nullptr, nullptr, 1.0f, 0);
             if (rc != AB_OK) return rc;
-            rc = blk_tc ? snake(blk.acts[2 * p + 1], TMP, nullptr, C, Tn, A16) : snake(blk.acts[2 * p + 1], TMP, ACT, C, Tn);
+            rc = img ? snake(blk.acts[2 * p + 1], TMP, nullptr, C, Tn, A16) : snake(blk.acts[2 * p + 1], TMP, ACT, C, Tn);
             if (rc != AB_OK) return rc;
             if (blk_tc) rc = tc_convs(blk.c2[p], nullptr, TMP, dst, C, Tn, 1.0f, 1.0f, cur, accp, div, A16, nullptr);
+            else if (blk_gs) rc = gs_conv(blk.c2[p], A16, dst, Tn, cur, accp, div);
             else rc = conv(blk.c2[p], ACT, sb, sc, 1, dst, Tn, 1.0f, cur, accp, div, 0);
             if (rc != AB_OK) return rc;
           } else {
             if (blk_tc) rc = tc_convs(blk.c1[p], nullptr, cur, dst, C, Tn, 1.0f, 1.0f, cur, accp, div, A16, nullptr);
+            else if (blk_gs) rc = gs_conv(blk.c1[p], A16, dst, Tn, cur, accp, div);
             else rc = conv(blk.c1[p], ACT, sb, sc, 1, dst, Tn, 1.0f, cur, accp, div, 0);
             if (rc != AB_OK) return rc;
           }

@@ -386,6 +386,11 @@ int gc_layer_geom(int mode, int cin, int cout, int k, int d_or_u, GcGeom& g) {
     g.grouped = ((u == 2 || u == 4 || u == 8) && (cc % 8) == 0 && (cout % 8) == 0) ? 1 : 0;
   }
   g.stage_bytes = (uint32_t)g.Nb * 64u;
+  // the activation tile is resident: even one M-tile (128 rows + tap reach) must fit next to two weight stages
+  const int maxshift = mode ? (g.ntaps - 1) : (k - 1) * d_or_u;
+  const uint32_t a1 = (uint32_t)rup(128 + maxshift, 8) * (uint32_t)g.Kp * 2u;
+  if (a1 + 2u * g.stage_bytes + 8192u > GC_SMEM_LIMIT)
+    return fail(AB_ERR_UNSUPPORTED, "gemmconv: C_in=%d needs the streaming variant (resident tile does not fit)", cin);
   return AB_OK;
 }
 
@@ -424,7 +429,296 @@ int gc_full_geom(const GcParams& p, GcGeom& g) {
   return AB_OK;
 }
 
+
+// ===========================================================================
+// Streaming variant for wide layers (C_in too large for a resident activation tile, e.g. BigVGAN-large
+// stage 0/1 with 768 / 384 channels): conv mode only, operand-image input only.
+//   for each N block (<= 256 output channels, TMEM double buffered):
+//     for each K chunk (<= 256 input channels): loader warps cp.async the chunk [rows x kchunk] of the
+//       image into one of two smem buffers; the MMA warp sweeps the k taps x kchunk/16 K-steps over it.
+// Warp roles: 0-3 epilogue, 4-7 activation loaders, 8 TMA weight producer, 9 MMA issuer.
+// ===========================================================================
+struct GsGeom {
+  int Kp, kchunk, KA, nkc_l;   // padded C_in, channels per chunk, chunks, 32-channel stages per chunk
+  int Nb, NB, nbuf;
+  int ntaps, rowsA, tiles, nstages, hh;
+  uint32_t chunk_bytes, stage_bytes, off_w, off_bias, off_bar, smem_bytes;
+  uint32_t idesc;
+  float out_scale;
+};
+
+__global__ void __launch_bounds__(320, 1) gemmconv_stream_kernel(GsParams p, GsGeom g) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x / g.tiles, tile = blockIdx.x - b * g.tiles;
+  const int R0 = tile * 128;
+  const uint32_t sA = smem_u32(smem);
+  const uint32_t sW = sA + g.off_w;
+  float* bias_s = reinterpret_cast<float*>(smem + g.off_bias);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + g.off_bar);
+  const uint32_t bar0 = smem_u32(bars);
+  auto bar_full = [&](int s) { return bar0 + 8u * s; };
+  auto bar_empty = [&](int s) { return bar0 + 8u * (GC_MAX_STAGES + s); };
+  auto bar_afull = [&](int q) { return bar0 + 8u * (2 * GC_MAX_STAGES + q); };
+  auto bar_aempty = [&](int q) { return bar0 + 8u * (2 * GC_MAX_STAGES + 2 + q); };
+  auto bar_accfull = [&](int q) { return bar0 + 8u * (2 * GC_MAX_STAGES + 4 + q); };
+  auto bar_accempty = [&](int q) { return bar0 + 8u * (2 * GC_MAX_STAGES + 6 + q); };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * GC_MAX_STAGES + 8);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < g.nstages; ++s) {
+      mbar_init(bar_full(s), 1);
+      mbar_init(bar_empty(s), 1);
+    }
+    for (int q = 0; q < 2; ++q) {
+      mbar_init(bar_afull(q), 128);
+      mbar_init(bar_aempty(q), 1);
+      mbar_init(bar_accfull(q), 1);
+      mbar_init(bar_accempty(q), 128);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    fence_proxy_async();
+  }
+  if (warp == 9) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  for (int i = threadIdx.x; i < g.NB * g.Nb; i += 320) bias_s[i] = (p.bias != nullptr && i < p.Cout) ? __ldg(p.bias + i) : 0.f;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp < 4) {
+    // ===================== epilogue =====================
+    const int q4 = warp;
+    const int nch = g.Nb >> 4;
+    const int row = q4 * 32 + lane;
+    const int t = R0 + row;
+    const bool ok = t < p.T;
+    for (int nb = 0; nb < g.NB; ++nb) {
+      const int buf = nb % g.nbuf;
+      mbar_wait(bar_accfull(buf), (uint32_t)(nb / g.nbuf) & 1u, 10);
+      tc_fence_after();
+      const uint32_t tbase = tmem + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(buf * g.Nb);
+      for (int ch = 0; ch < nch; ++ch) {
+        uint32_t r[16];
+        tc_ld16(tbase + (uint32_t)(ch * 16), r);
+        float res[16], acp[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          const int co = nb * g.Nb + ch * 16 + e;
+          const bool w = ok && co < p.Cout;
+          const int64_t off = ((int64_t)b * p.Cout + co) * p.T + t;
+          res[e] = (w && p.residual) ? __ldg(p.residual + off) : 0.f;
+          acp[e] = (w && p.acc_prev) ? __ldg(p.acc_prev + off) : 0.f;
+        }
+        tc_wait_ld();
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          const int co = nb * g.Nb + ch * 16 + e;
+          if (ok && co < p.Cout) {
+            float a = __uint_as_float(r[e]) + bias_s[co];
+            a += res[e];
+            a += acp[e];
+            a *= g.out_scale;
+            p.y[((int64_t)b * p.Cout + co) * p.T + t] = a;
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(bar_accempty(buf));
+    }
+  } else if (warp < 8) {
+    // ===================== activation loaders (cp.async from the operand image) =====================
+    const int lw = warp - 4;
+    const int c8_img = (p.Cin + 15) >> 4 << 1;           // 8-channel groups present in the image
+    const int c8_chunk = g.kchunk >> 3;
+    const uint16_t* xb = p.ximg + (size_t)b * c8_img * p.T * 8;
+    const int total = g.NB * g.KA;
+    for (int it = 0; it < total; ++it) {
+      const int ab = it & 1, kcA = it % g.KA;
+      mbar_wait(bar_aempty(ab), (((uint32_t)(it >> 1)) & 1u) ^ 1u, 40);
+      const uint32_t base = sA + (uint32_t)ab * g.chunk_bytes;
+      for (int c8 = lw; c8 < c8_chunk; c8 += 4) {
+        const int c8g = kcA * c8_chunk + c8;
+        const uint16_t* xc = xb + (size_t)c8g * p.T * 8;
+        for (int r = lane; r < g.rowsA; r += 32) {
+          const int tt = R0 - g.hh + r;
+          const bool okl = c8g < c8_img && tt >= 0 && tt < p.T;
+          cp_async16(base + unit_offset(g.rowsA, c8, r), okl ? (const void*)(xc + (size_t)tt * 8) : (const void*)xb,
+                     okl ? 16u : 0u);
+        }
+      }
+      cp_async_wait_all();
+      fence_proxy_async();
+      mbar_arrive(bar_afull(ab));
+    }
+  } else if (warp == 8) {
+    // ===================== TMA weight producer =====================
+    if (lane == 0) {
+      const int total = g.NB * g.KA * g.ntaps * g.nkc_l;
+      for (int it = 0; it < total; ++it) {
+        const int s = it % g.nstages;
+        const uint32_t ph = (uint32_t)(it / g.nstages) & 1u;
+        mbar_wait(bar_empty(s), ph ^ 1u, 20);
+        mbar_arrive_expect_tx(bar_full(s), g.stage_bytes);
+        bulk_g2s(sW + (uint32_t)s * g.stage_bytes, static_cast<const uint8_t*>(p.w) + (size_t)it * g.stage_bytes,
+                 g.stage_bytes, bar_full(s));
+      }
+    }
+  } else {
+    // ===================== MMA issuer =====================
+    const uint32_t elected = elect_one_sync();
+    const uint64_t hi = desc_hi_sw32();
+    const uint32_t kstepA = 2u * (uint32_t)g.rowsA, kstepB = 2u * (uint32_t)g.Nb;
+    const uint32_t w16 = sW >> 4, stage16 = g.stage_bytes >> 4;
+    int it = 0, ita = 0;
+    for (int nb = 0; nb < g.NB; ++nb) {
+      const int buf = nb % g.nbuf;
+      mbar_wait(bar_accempty(buf), ((uint32_t)(nb / g.nbuf) & 1u) ^ 1u, 32);
+      tc_fence_after();
+      const uint32_t td = tmem + (uint32_t)(buf * g.Nb);
+      for (int kcA = 0; kcA < g.KA; ++kcA, ++ita) {
+        const int ab = ita & 1;
+        mbar_wait(bar_afull(ab), ((uint32_t)(ita >> 1)) & 1u, 33);
+        tc_fence_after();
+        const uint32_t a16 = (sA + (uint32_t)ab * g.chunk_bytes) >> 4;
+        for (int tap = 0; tap < g.ntaps; ++tap) {
+          for (int kc = 0; kc < g.nkc_l; ++kc, ++it) {
+            const int s = it % g.nstages;
+            const uint32_t ph = (uint32_t)(it / g.nstages) & 1u;
+            mbar_wait(bar_full(s), ph, 31);
+            tc_fence_after();
+            const uint32_t alo = desc_lo_sw32(a16 + (uint32_t)(kc * 2) * kstepA + (uint32_t)(tap * p.d) * 2u);
+            const uint32_t blo = desc_lo_sw32(w16 + (uint32_t)s * stage16);
+            if (elected) {
+              tc_mma_f16(td, hi | alo, hi | blo, g.idesc, (kcA | tap | kc) != 0 ? 1u : 0u);
+              tc_mma_f16(td, hi | (alo + kstepA), hi | (blo + kstepB), g.idesc, 1u);
+              tc_commit(bar_empty(s));
+            }
+            __syncwarp();
+          }
+        }
+        if (elected) tc_commit(bar_aempty(ab));
+        __syncwarp();
+      }
+      if (elected) tc_commit(bar_accfull(buf));
+      __syncwarp();
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 9) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+  }
+}
+
+// image: [nb][kcA][tap][kc_l] stages, each [Nb rows x 32 channels] (SWIZZLE_32B rows)
+__global__ void gs_pack_weight_kernel(const float* __restrict__ w_t, uint16_t* __restrict__ img, GsGeom g, int cin,
+                                      int cout, int k, int bf16) {
+  const int64_t per_stage = (int64_t)g.Nb * 32;
+  const int64_t total = (int64_t)g.NB * g.KA * g.ntaps * g.nkc_l * per_stage;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int e = (int)(idx & 7);
+    int64_t r = idx >> 3;
+    const int n = (int)(r % g.Nb);
+    r /= g.Nb;
+    const int c8l = (int)(r & 3);
+    r >>= 2;
+    const int kc = (int)(r % g.nkc_l);
+    r /= g.nkc_l;
+    const int tap = (int)(r % g.ntaps);
+    r /= g.ntaps;
+    const int kcA = (int)(r % g.KA);
+    const int nb = (int)(r / g.KA);
+    const int ci = kcA * g.kchunk + kc * 32 + c8l * 8 + e;
+    const int co = nb * g.Nb + n;
+    float v = 0.f;
+    if (ci < cin && co < cout) v = w_t[((int64_t)ci * k + tap) * cout + co];
+    const int64_t stage = (((int64_t)nb * g.KA + kcA) * g.ntaps + tap) * g.nkc_l + kc;
+    const int unit = (c8l & 1) ^ ((n >> 2) & 1);
+    img[stage * per_stage + (int64_t)(c8l >> 1) * g.Nb * 16 + (int64_t)n * 16 + unit * 8 + e] =
+        (uint16_t)(pack2(v, 0.f, bf16) & 0xffffu);
+  }
+}
+
+int gs_layer_geom(int cin, int cout, int k, int d, GsGeom& g) {
+  if (cin <= 0 || cout <= 0 || k <= 0 || !(k & 1) || d <= 0) return fail(AB_ERR_UNSUPPORTED, "gemmconv(stream): bad layer");
+  g.Kp = rup(cin, 16);
+  const int Np = rup(cout, 16);
+  g.NB = (Np + 255) / 256;
+  g.Nb = rup((Np + g.NB - 1) / g.NB, 16);
+  g.nbuf = g.NB > 1 ? 2 : 1;
+  g.ntaps = k;
+  g.hh = (k - 1) * d / 2;
+  g.rowsA = rup(128 + (k - 1) * d, 8);
+  g.stage_bytes = (uint32_t)g.Nb * 64u;
+  const uint32_t misc = (uint32_t)(g.NB * g.Nb) * 4u + 8u * (2 * GC_MAX_STAGES + 8) + 16u;
+  for (int kchunk = 256; kchunk >= 32; kchunk -= 32) {
+    const uint32_t cb = ((uint32_t)g.rowsA * (uint32_t)kchunk * 2u + 1023u) & ~1023u;
+    if (2u * cb + 2u * g.stage_bytes + misc + 1280u > GC_SMEM_LIMIT) continue;
+    g.kchunk = kchunk;
+    g.chunk_bytes = cb;
+    g.KA = (g.Kp + kchunk - 1) / kchunk;
+    g.nkc_l = kchunk / 32;
+    g.nstages = std::min((int)((GC_SMEM_LIMIT - 2u * cb - misc - 1280u) / g.stage_bytes), GC_MAX_STAGES);
+    g.off_w = 2u * cb;
+    g.off_bias = g.off_w + (uint32_t)g.nstages * g.stage_bytes;
+    g.off_bar = (g.off_bias + (uint32_t)(g.NB * g.Nb) * 4u + 15u) & ~15u;
+    g.smem_bytes = g.off_bar + 8u * (2 * GC_MAX_STAGES + 8) + 16u;
+    return AB_OK;
+  }
+  return fail(AB_ERR_UNSUPPORTED, "gemmconv(stream): k=%d d=%d does not fit shared memory", k, d);
+}
+
 }  // namespace
+
+size_t gs_weight_image_bytes(int cin, int cout, int k, int d) {
+  GsGeom g;
+  if (gs_layer_geom(cin, cout, k, d, g) != AB_OK) return 0;
+  return (size_t)g.NB * g.KA * g.ntaps * g.nkc_l * g.stage_bytes;
+}
+
+int launch_gs_pack_weight(const float* w_t, void* image, int cin, int cout, int k, int d, int precision,
+                          cudaStream_t s) {
+  GsGeom g;
+  int rc = gs_layer_geom(cin, cout, k, d, g);
+  if (rc != AB_OK) return rc;
+  const int64_t total = (int64_t)g.NB * g.KA * g.ntaps * g.nkc_l * g.Nb * 32;
+  const int blocks = (int)std::min<int64_t>((total + 255) / 256, 148 * 8);
+  gs_pack_weight_kernel<<<blocks, 256, 0, s>>>(w_t, static_cast<uint16_t*>(image), g, cin, cout, k,
+                                               precision == AB_PREC_TC_BF16 ? 1 : 0);
+  AB_LAUNCH_CHECK("gs_pack_weight_kernel");
+  return AB_OK;
+}
+
+int launch_gemmconv_stream(const GsParams& p, cudaStream_t s) {
+  if (!p.ximg || !p.y || !p.w) return fail(AB_ERR_ARG, "gemmconv(stream): null argument");
+  if (p.B <= 0 || p.T <= 0) return fail(AB_ERR_ARG, "gemmconv(stream): bad shape");
+  GsGeom g;
+  int rc = gs_layer_geom(p.Cin, p.Cout, p.k, p.d, g);
+  if (rc != AB_OK) return rc;
+  g.tiles = (p.T + 127) / 128;
+  const uint32_t fmt = p.precision == AB_PREC_TC_BF16 ? 1u : 0u;
+  g.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(g.Nb >> 3) << 17) | ((128u >> 4) << 24);
+  g.out_scale = 1.0f / p.out_div;
+  static bool configured = false;
+  if (!configured) {
+    AB_CUDA_TRY(cudaFuncSetAttribute(gemmconv_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GC_SMEM_LIMIT));
+    configured = true;
+  }
+  const int64_t grid = (int64_t)p.B * g.tiles;
+  if (grid > 0x7fffffffll) return fail(AB_ERR_UNSUPPORTED, "gemmconv(stream): grid too large");
+  const uint32_t smem = std::max<uint32_t>(g.smem_bytes, 120u * 1024u);
+  gemmconv_stream_kernel<<<(unsigned)grid, 320, smem, s>>>(p, g);
+  AB_LAUNCH_CHECK("gemmconv_stream_kernel");
+  return AB_OK;
+}
 
 bool gc_can_emit_image(int cout, int k, int u) {
   GcGeom g;

@@ -38,7 +38,7 @@ namespace {
 constexpr int TC_MAX_STAGES = 8;
 constexpr int TC_MAX_C = 256;
 constexpr uint32_t TC_SMEM_LIMIT = 227 * 1024;
-constexpr int RING_DEPTH = 4;                 // per-warp residual ring: slots of (16 ch x 32 rows) x 2 tensors
+constexpr int RING_DEPTH_MAX = 4;             // per-warp residual ring: slots of (16 ch x 32 rows) x 2 tensors
 constexpr uint32_t RING_SLOT_BYTES = 4096;    // 2 KB residual + 2 KB branch sum
 
 struct TcGeom {
@@ -56,7 +56,8 @@ struct TcGeom {
   int h2;          // time of the intermediate row 0 is T0 - h2 (pair mode)
   uint32_t idesc;
   int tmem_cols;   // TMEM columns to allocate (power of two >= m*Np)
-  int dual;        // 1: half-size tile, 4 worker warps, two CTAs per SM
+  int dual;        // 0: full tile, 8 worker warps, 1 CTA/SM; n >= 2: 1/n tile, 4 worker warps, n CTAs per SM
+  int ring_depth;  // slots per worker warp in the epilogue-2 ring (2..4)
   int staged;      // 1: epilogue 2 streams residual / branch sum through the cp.async ring (needs T % 4 == 0)
   int stagger_groups, first_wave;   // first-wave CTAs start (blockIdx % groups) * stagger_cycles late so that the
   long long stagger_cycles;         // HBM-bound phases of identical tiles do not run in lock-step chip-wide
@@ -227,11 +228,12 @@ __global__ void __launch_bounds__(WW * 32 + 64, MINB) tc_conv_kernel(TcConvParam
       const bool has_res = p.residual != nullptr && !(g.skip & 4), has_acc = p.acc_prev != nullptr && !(g.skip & 4);
       const int nchw = (nch - hsel + NWG - 1) / NWG;     // column chunks owned by this warp
       const int nitems = g.m * nchw;
-      uint8_t* ring = smem + (size_t)warp * (RING_DEPTH * RING_SLOT_BYTES);
+      const int RD = g.ring_depth;
+      uint8_t* ring = smem + (size_t)warp * ((size_t)RD * RING_SLOT_BYTES);
       auto issue = [&](int it) {
         const int i = it / nchw, ch = hsel + (it - i * nchw) * NWG;
         const int tb = T0 + i * 128 + q4 * 32;
-        const uint32_t slot = smem_u32(ring + (size_t)(it % RING_DEPTH) * RING_SLOT_BYTES);
+        const uint32_t slot = smem_u32(ring + (size_t)(it % RD) * RING_SLOT_BYTES);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const int u = lane + 32 * k, c = u >> 3, r4 = u & 7;
@@ -243,18 +245,18 @@ __global__ void __launch_bounds__(WW * 32 + 64, MINB) tc_conv_kernel(TcConvParam
         }
         cp_async_commit();
       };
-      for (int it = 0; it < RING_DEPTH - 1; ++it) {
+      for (int it = 0; it < RD - 1; ++it) {
         if (it < nitems) issue(it); else cp_async_commit();
       }
       for (int it = 0; it < nitems; ++it) {
-        if (it + RING_DEPTH - 1 < nitems) issue(it + RING_DEPTH - 1); else cp_async_commit();
+        if (it + RD - 1 < nitems) issue(it + RD - 1); else cp_async_commit();
         const int i = it / nchw, ch = hsel + (it - i * nchw) * NWG;
         uint32_t r[16];
         tc_ld16(tmem + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(i * g.Np + ch * 16), r);
-        cp_async_wait_group<RING_DEPTH - 1>();
+        if (RD == 4) cp_async_wait_group<3>(); else if (RD == 3) cp_async_wait_group<2>(); else cp_async_wait_group<1>();
         __syncwarp();
         tc_wait_ld();
-        const float* rs = reinterpret_cast<const float*>(ring + (size_t)(it % RING_DEPTH) * RING_SLOT_BYTES);
+        const float* rs = reinterpret_cast<const float*>(ring + (size_t)(it % RD) * RING_SLOT_BYTES);
         const int row = i * 128 + q4 * 32 + lane;
         const int t = T0 + row;
         const bool ok = row < g.V && t < p.T;
@@ -457,10 +459,16 @@ int make_geom(const TcConvParams& p, TcGeom& g) {
   auto try_fit = [&](int m, int ww, uint32_t limit, int min_stages) -> bool {
     if (m < 1 || m * 128 - lost < 8) return false;
     g.rowsA = round_up(m * 128 + halo, 8);
-    // the A region also hosts the epilogue-2 residual ring (RING_DEPTH slots per worker warp)
-    const uint32_t abytes = std::max<uint32_t>((uint32_t)g.rowsA * (uint32_t)g.Np * 2u,
-                                               (uint32_t)ww * RING_DEPTH * RING_SLOT_BYTES);
-    if (abytes + (uint32_t)min_stages * g.stage_bytes + misc + 1280u > limit) return false;
+    // the A region also hosts the epilogue-2 residual ring (ring_depth slots per worker warp)
+    const uint32_t tile_bytes = (uint32_t)g.rowsA * (uint32_t)g.Np * 2u;
+    uint32_t abytes = 0;
+    int rd = RING_DEPTH_MAX;
+    for (; rd >= 2; --rd) {
+      abytes = std::max<uint32_t>(tile_bytes, (uint32_t)ww * rd * RING_SLOT_BYTES);
+      if (abytes + (uint32_t)min_stages * g.stage_bytes + misc + 1280u <= limit) break;
+    }
+    if (rd < 2) return false;
+    g.ring_depth = rd;
     g.m = m;
     int ns = (int)((limit - abytes - misc - 1280u) / g.stage_bytes);
     g.nstages = std::min(ns, TC_MAX_STAGES);
@@ -471,12 +479,21 @@ int make_geom(const TcConvParams& p, TcGeom& g) {
     return true;
   };
   g.dual = 0;
-  int m2 = std::min(256 / g.Np, 16);
-  while (m2 > 1 && (m2 - 1) * 128 - lost >= p.T) --m2;
-  if (dual_ok && m2 >= 1 && try_fit(m2, 4, 113u * 1024u, 3)) {
-    g.dual = 1;
-    g.tmem_cols = 32;
-    while (g.tmem_cols < g.m * g.Np) g.tmem_cols *= 2;
+  // preferred: 1/n-size tiles so that n CTAs share an SM and one CTA's global-memory phases overlap the
+  // others' MMA phases (n = 3 when the 108-register kernel, 512 TMEM columns and 227 KB smem allow it)
+  static const int ncta_pref = [] { const char* e = getenv("AB_TC_NCTA"); return e ? atoi(e) : 2; }();
+  for (int n = std::min(std::max(ncta_pref, 2), 3); n >= 2 && dual_ok && !g.dual; --n) {
+    const int cols = n == 2 ? 256 : 128;
+    int m2 = std::min(cols / g.Np, 16);
+    while (m2 > 1 && (m2 - 1) * 128 - lost >= p.T) --m2;
+    const uint32_t limit = n == 2 ? 113u * 1024u : 74u * 1024u;
+    if (m2 >= 1 && try_fit(m2, 4, limit, 3)) {
+      g.dual = n;
+      g.tmem_cols = 32;
+      while (g.tmem_cols < g.m * g.Np) g.tmem_cols *= 2;
+    }
+  }
+  if (g.dual) {
   } else {
     int m = std::min(512 / g.Np, 16);
     while (m > 1 && (m - 1) * 128 - lost >= p.T) --m;
@@ -501,7 +518,7 @@ int make_geom(const TcConvParams& p, TcGeom& g) {
   // stagger: period model = MMA issue time + HBM time of the tile at ~4.5 TB/s chip-wide
   static const int stag = [] { const char* e = getenv("AB_TC_STAGGER"); return e ? atoi(e) : 0; }();
   g.stagger_groups = stag;
-  g.first_wave = 148 * (g.dual ? 2 : 1);
+  g.first_wave = 148 * (g.dual ? g.dual : 1);
   const double mma = (double)p.nconv * p.k * g.nkc * g.m * 2.0 * (64.0 + g.Np / 2.0) * (g.dual ? 2.0 : 1.0);
   const double mem = (double)g.m * 128.0 * g.Np * 12.0 / (g.dual ? 7.7 : 15.4);
   g.stagger_cycles = stag > 1 ? (long long)((mma + mem + 8000.0) / stag) : 0;
@@ -548,6 +565,8 @@ int launch_tc_conv(const TcConvParams& p, cudaStream_t s) {
     AB_CUDA_TRY(cudaFuncSetAttribute(tc_conv_kernel<8, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_LIMIT));
     AB_CUDA_TRY(cudaFuncSetAttribute(tc_conv_kernel<4, 2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
     AB_CUDA_TRY(cudaFuncSetAttribute(tc_conv_kernel<4, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
+    AB_CUDA_TRY(cudaFuncSetAttribute(tc_conv_kernel<4, 3, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 74 * 1024));
+    AB_CUDA_TRY(cudaFuncSetAttribute(tc_conv_kernel<4, 3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 74 * 1024));
     configured = true;
   }
   const int64_t grid = (int64_t)p.B * g.tiles;
@@ -562,7 +581,10 @@ int launch_tc_conv(const TcConvParams& p, cudaStream_t s) {
     g.dbg = dbg_buf;
   }
   const bool bf = p.precision == AB_PREC_TC_BF16;
-  if (g.dual) {
+  if (g.dual == 3) {
+    if (bf) tc_conv_kernel<4, 3, 1><<<(unsigned)grid, 4 * 32 + 64, smem, s>>>(p, g);
+    else tc_conv_kernel<4, 3, 0><<<(unsigned)grid, 4 * 32 + 64, smem, s>>>(p, g);
+  } else if (g.dual == 2) {
     if (bf) tc_conv_kernel<4, 2, 1><<<(unsigned)grid, 4 * 32 + 64, smem, s>>>(p, g);
     else tc_conv_kernel<4, 2, 0><<<(unsigned)grid, 4 * 32 + 64, smem, s>>>(p, g);
   } else {

@@ -33,7 +33,8 @@ HP_V1 = dict(resblock="1", upsample_rates=[8, 8, 2, 2], upsample_kernel_sizes=[1
              upsample_initial_channel=512, resblock_kernel_sizes=[3, 7, 11],
              resblock_dilation_sizes=[[1, 3, 5]] * 3)
 N_MEL, HOP = 80, 256
-FLOP_PER_SAMPLE = 2398848          # conv FLOPs per output sample, HiFi-GAN V1
+FLOP_PER_SAMPLE = 2398848          # conv FLOPs per output sample, HiFi-GAN V1 / BigVGAN-base
+FLOP_PER_SAMPLE_LARGE = 7047456    # BigVGAN-large
 
 
 def parse():
@@ -46,7 +47,7 @@ def parse():
     ap.add_argument("--frames", type=int, default=1024)
     ap.add_argument("--precision", default=os.environ.get("AMPHION_B200_PRECISION", "tc_f16"))
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="hifigan_v1", choices=["hifigan_v1", "bigvgan_base"],
+    ap.add_argument("--workload", default="hifigan_v1", choices=["hifigan_v1", "bigvgan_base", "bigvgan_large"],
                     help="hifigan_v1 = BASELINE config 2 (the headline, default); bigvgan_base = config 3 "
                          "(batch 32, 100x1024 mel, 24 kHz) for the results table")
     return ap.parse_args()
@@ -57,6 +58,12 @@ def make_cfg(workload="hifigan_v1"):
     if workload == "bigvgan_base":
         pre = NS(n_mel=100, hop_size=HOP, extract_amplitude_phase=False)
         hp = dict(HP_V1, activation="snakebeta", snake_logscale=True)
+        return NS(preprocess=pre, model=NS(generator="bigvgan", bigvgan=NS(**hp)))
+    if workload == "bigvgan_large":   # egs/vocoder/gan/bigvgan_large/exp_config.json:14-57
+        pre = NS(n_mel=100, hop_size=HOP, extract_amplitude_phase=False)
+        hp = dict(resblock="1", upsample_rates=[4, 4, 2, 2, 2, 2], upsample_kernel_sizes=[8, 8, 4, 4, 4, 4],
+                  upsample_initial_channel=1536, resblock_kernel_sizes=[3, 7, 11],
+                  resblock_dilation_sizes=[[1, 3, 5]] * 3, activation="snakebeta", snake_logscale=True)
         return NS(preprocess=pre, model=NS(generator="bigvgan", bigvgan=NS(**hp)))
     pre = NS(n_mel=N_MEL, hop_size=HOP, extract_amplitude_phase=False)
     return NS(preprocess=pre, model=NS(generator="hifigan", hifigan=NS(**HP_V1)))
@@ -194,7 +201,7 @@ def run_native(args, rank, local_rank, world):
         dist.init_process_group("nccl", device_id=dev)
     cfg = make_cfg(args.workload)
     torch.manual_seed(1234)
-    if args.workload == "bigvgan_base":
+    if args.workload.startswith("bigvgan"):
         from amphion_b200.vocoders.bigvgan import BigVGAN
         model = BigVGAN(cfg).to(dev).eval()
         gsn = torch.Generator().manual_seed(1)
@@ -204,6 +211,8 @@ def run_native(args, rank, local_rank, world):
                     prm.copy_((torch.randn(prm.shape, generator=gsn) * 0.3).to(dev))
         if args.batch == 64:
             args.batch = 32
+        if args.workload == "bigvgan_large" and args.frames == 1024:
+            args.frames = 2048
     else:
         model = HiFiGAN(cfg).to(dev).eval()
     model.precision = args.precision
@@ -275,6 +284,7 @@ def run_native(args, rank, local_rank, world):
         d = prof[dom]
         tf = d["flops"] / (d["ms"] / 1e3) / 1e12 if d["ms"] > 0 else 0.0
         gbs = d["bytes"] / (d["ms"] / 1e3) / 1e9 if d["ms"] > 0 else 0.0
+        fps = FLOP_PER_SAMPLE_LARGE if args.workload == "bigvgan_large" else FLOP_PER_SAMPLE
         hbm_bound = dom == "activation1d"     # the anti-aliased Snake is an 8 B/element streaming kernel
         roofline = dict(bound="hbm" if hbm_bound else "tensor", kernel=dom + "_kernel",
                         achieved=gbs if hbm_bound else tf, peak=pk["hbm"] if hbm_bound else pk["tensor"],
@@ -286,8 +296,8 @@ def run_native(args, rank, local_rank, world):
                         tensor=dict(achieved=tf, peak=pk["tensor"], unit="TFLOP/s", frac=tf / pk["tensor"]),
                         hbm=dict(achieved=gbs, peak=pk["hbm"], unit="GB/s", frac=gbs / pk["hbm"],
                                  note="algorithmic bytes: fp32 x read + y write (+ branch sum) + weights once"),
-                        whole_step=dict(tflops=samples_step / world * FLOP_PER_SAMPLE / (ms_step / 1e3) / 1e12,
-                                        frac_of_tensor_peak=samples_step / world * FLOP_PER_SAMPLE / (ms_step / 1e3) / 1e12 / pk["tensor"]),
+                        whole_step=dict(tflops=samples_step / world * fps / (ms_step / 1e3) / 1e12,
+                                        frac_of_tensor_peak=samples_step / world * fps / (ms_step / 1e3) / 1e12 / pk["tensor"]),
                         classes={k: dict(launches=v["launches"], ms=round(v["ms"], 3)) for k, v in prof.items()})
         cpu = None
         if world == 1 and not args.no_cpu_baseline and args.workload == "hifigan_v1":
@@ -298,7 +308,7 @@ def run_native(args, rank, local_rank, world):
         line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
                     ms_per_step=ms_step, higher_is_better=True, scaling="weak", vs_baseline=None, dtype=dt,
                     data="synthetic",
-                    config=dict(workload=("HiFi-GAN V1 22.05kHz" if args.workload == "hifigan_v1" else "BigVGAN-base 24kHz")
+                    config=dict(workload={"hifigan_v1": "HiFi-GAN V1 22.05kHz", "bigvgan_base": "BigVGAN-base 24kHz", "bigvgan_large": "BigVGAN-large 24kHz"}[args.workload]
                                 + " generator forward, batch=%d per GPU, %dx%d synthetic mel" % (B, n_mel, T),
                                 global_batch=world * B, frames=T, hop=HOP, precision=args.precision,
                                 parallelism="utterance-batch sharding dp%d, NCCL all-gather of wav" % world,

@@ -286,6 +286,20 @@ def test_bigvgan_base_full_width_matches_oracle(prec, tol):
     assert np.abs(got - want).max() <= tol, np.abs(got - want).max()
 
 
+def test_bigvgan_wide_layers_match_oracle():
+    """BigVGAN-large style widths: stage 0 has 384 channels (> 256: streaming N-blocked tensor-core kernel),
+    stage 1 has 192 (pair kernel); CPU-checkable length."""
+    hp = dict(resblock="1", upsample_rates=[4, 2], upsample_kernel_sizes=[8, 4], upsample_initial_channel=768,
+              resblock_kernel_sizes=[3, 11], resblock_dilation_sizes=[[1, 3, 5]] * 2, activation="snakebeta",
+              snake_logscale=True)
+    model, mel, want = _full_size_case("bigvgan", hp, 20, 2, 37, seed=5)
+    for prec, tol in (("fp32", 1e-4), ("tc_f16", 1e-3)):
+        model.precision = prec
+        got = model(mel.to(DEV)).cpu().numpy()
+        assert np.isfinite(got).all()
+        assert np.abs(got - want).max() <= tol, (prec, np.abs(got - want).max())
+
+
 @pytest.mark.parametrize("prec", ["fp32", "tc_f16"])
 def test_generator_properties_at_scale(prec):
     """Size-independent properties on a batch the CPU oracle cannot afford:
