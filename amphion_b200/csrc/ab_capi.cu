@@ -262,7 +262,7 @@ int ab_generator_create(const ab_generator_config* cfg, ab_generator** out) {
       s.tc_kind = s.tc_bytes ? 1 : 0;
       if (!s.tc_bytes && s.shape[0] == s.shape[1] && s.shape[1] > 256) {
         // wide square convs (BigVGAN-large stages 0/1): streaming N-blocked kernel fed from operand images
-        s.tc_bytes = gs_weight_image_bytes((int)s.shape[1], (int)s.shape[0], (int)s.shape[2], s.dilation);
+        s.tc_bytes = gs_weight_image_bytes(0, (int)s.shape[1], (int)s.shape[0], (int)s.shape[2], s.dilation);
         s.tc_kind = s.tc_bytes ? 3 : 0;
       } else if (!s.tc_bytes && s.shape[1] <= 512) {   // non-square convs (conv_pre, conv_post): N-blocked kernel
         s.tc_bytes = gc_weight_image_bytes(0, (int)s.shape[1], (int)s.shape[0], (int)s.shape[2], s.dilation);
@@ -273,6 +273,10 @@ int ab_generator_create(const ab_generator_config* cfg, ab_generator** out) {
     } else if (s.kind == SLOT_CONVT_W) {
       s.tc_bytes = gc_weight_image_bytes(1, (int)s.shape[0], (int)s.shape[1], (int)s.shape[2], s.stride);
       s.tc_kind = s.tc_bytes ? 2 : 0;
+      if (!s.tc_bytes) {   // C_in too wide for a resident tile: streaming kernel
+        s.tc_bytes = gs_weight_image_bytes(1, (int)s.shape[0], (int)s.shape[1], (int)s.shape[2], s.stride);
+        s.tc_kind = s.tc_bytes ? 3 : 0;
+      }
       s.tc_offset = g->fp32_bytes + tc;
       tc += align_up(s.tc_bytes, 256);
     }
@@ -362,13 +366,16 @@ int ab_generator_finalize(ab_generator* g, int32_t precision, void* stream) {
         rc = launch_tc_pack_weight(g->fptr((int)i), g->tcptr((int)i), (int)s.shape[1], (int)s.shape[0],
                                    (int)s.shape[2], precision, st);
       else if (s.kind == SLOT_CONV_W && s.tc_kind == 3)
-        rc = launch_gs_pack_weight(g->fptr((int)i), g->tcptr((int)i), (int)s.shape[1], (int)s.shape[0], (int)s.shape[2],
+        rc = launch_gs_pack_weight(g->fptr((int)i), g->tcptr((int)i), 0, (int)s.shape[1], (int)s.shape[0], (int)s.shape[2],
                                    s.dilation, precision, st);
       else if (s.kind == SLOT_CONV_W && s.tc_kind == 2)
         rc = launch_gc_pack_weight(g->fptr((int)i), g->tcptr((int)i), 0, (int)s.shape[1], (int)s.shape[0],
                                    (int)s.shape[2], s.dilation, precision, st);
-      else if (s.kind == SLOT_CONVT_W && s.tc_bytes)
+      else if (s.kind == SLOT_CONVT_W && s.tc_kind == 2)
         rc = launch_gc_pack_weight(g->fptr((int)i), g->tcptr((int)i), 1, (int)s.shape[0], (int)s.shape[1],
+                                   (int)s.shape[2], s.stride, precision, st);
+      else if (s.kind == SLOT_CONVT_W && s.tc_kind == 3)
+        rc = launch_gs_pack_weight(g->fptr((int)i), g->tcptr((int)i), 1, (int)s.shape[0], (int)s.shape[1],
                                    (int)s.shape[2], s.stride, precision, st);
       if (rc != AB_OK) return rc;
     }
@@ -551,6 +558,7 @@ int ab_generator_forward(ab_generator* g, const float* dev_mel, int64_t B, int64
   auto gs_conv = [&](const ConvRef& c, const uint16_t* ximg, float* y, int Tn, const float* residual,
                      const float* acc_prev, float out_div) -> int {
     GsParams p;
+    p.x = nullptr; p.pre_slope = 1.0f; p.mode = 0; p.u = 1; p.yimg = nullptr; p.img_slope = 1.0f;
     p.ximg = ximg; p.y = y; p.w = g->tcptr(c.w); p.bias = g->fptr(c.b); p.residual = residual; p.acc_prev = acc_prev;
     p.B = (int)B; p.Cin = c.cin; p.Cout = c.cout; p.T = Tn; p.k = c.k; p.d = c.d; p.out_div = out_div;
     p.precision = g->precision;
@@ -585,7 +593,16 @@ int ab_generator_forward(ab_generator* g, const float* dev_mel, int64_t B, int64
       prof_begin(2, 2.0 * eo * cin * ((double)sg.up.k / sg.u),
                  4.0 * ((double)B * cin * Tn + eo + (double)cin * sg.ch * sg.up.k));
     }
-    if (tc && g->slots[sg.up.w].tc_bytes) {
+    if (tc && g->slots[sg.up.w].tc_kind == 3) {
+      GsParams sp;
+      sp.ximg = nullptr; sp.x = R[cur_r]; sp.pre_slope = tp.pre_slope; sp.mode = 1; sp.u = sg.u;
+      u_img = (!big && gs_can_emit_image(sg.ch, sg.up.k, sg.u)) ? U16 : nullptr;
+      sp.yimg = u_img; sp.img_slope = 0.1f; sp.y = U; sp.w = g->tcptr(sg.up.w); sp.bias = g->fptr(sg.up.b);
+      sp.residual = nullptr; sp.acc_prev = nullptr; sp.B = (int)B; sp.Cin = cin; sp.Cout = sg.ch; sp.T = Tn;
+      sp.k = sg.up.k; sp.d = 1; sp.out_div = 1.0f; sp.precision = g->precision;
+      if (g->profiling) g->prof_recs.back().cls = 4;
+      rc = launch_gemmconv_stream(sp, st);
+    } else if (tc && g->slots[sg.up.w].tc_kind == 2) {
       GcParams gp;
       gp.x = R[cur_r]; gp.xsb = (int64_t)cin * Tn; gp.xsc = Tn; gp.xst = 1; gp.y = U; gp.w = g->tcptr(sg.up.w); gp.bias = g->fptr(sg.up.b); gp.residual = nullptr;
       gp.B = (int)B; gp.Cin = cin; gp.Cout = sg.ch; gp.Tin = Tn; gp.mode = 1; gp.k = sg.up.k; gp.d = 1; gp.u = sg.u;

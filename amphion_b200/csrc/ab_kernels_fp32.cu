@@ -167,6 +167,70 @@ __global__ void __launch_bounds__(NT) conv1d_fewout_fp32_kernel(ConvParams p) {
     }
   }
 }
+// conv_post specialisation: one output channel, k = K taps, dilation 1 (hifigan.py:199,215-217).  Four
+// consecutive outputs per thread from a (4 + K - 1)-sample register window (3 x LDS.128 per input channel),
+// weights of the current 8-channel chunk in registers.  HBM-bound: reads C x T fp32 once.
+template <int K>
+__global__ void __launch_bounds__(NT) conv_post_fp32_kernel(ConvParams p) {
+  constexpr int XWP = PT + 8;                   // padded row: 1024 outputs + K - 1 (<= 8) halo, 16-byte rows
+  __shared__ __align__(16) float xs[PCI][XWP];
+  __shared__ float ws[PCI * K];
+  const int t0 = blockIdx.x * PT, b = blockIdx.z;
+  constexpr int pad = (K - 1) / 2;
+  const float slope = p.pre_slope;
+  const float* xb = p.x + (int64_t)b * p.xsb;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  const int tl = 4 * threadIdx.x;
+  for (int ci0 = 0; ci0 < p.Cin; ci0 += PCI) {
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < PCI * XWP; idx += NT) {
+      const int ci = idx / XWP, n = idx - ci * XWP;
+      const int t = t0 - pad + n, c = ci0 + ci;
+      float v = 0.f;
+      if (c < p.Cin && t >= 0 && t < p.T && n < PT + K - 1) {
+        v = __ldg(xb + (int64_t)c * p.xsc + (int64_t)t * p.xst);
+        v = v >= 0.f ? v : v * slope;
+      }
+      xs[ci][n] = v;
+    }
+    if (threadIdx.x < PCI * K) {
+      const int ci = threadIdx.x / K, j = threadIdx.x - ci * K;
+      ws[threadIdx.x] = (ci0 + ci < p.Cin) ? __ldg(p.w_t + (int64_t)(ci0 + ci) * K + j) : 0.f;   // [Cin][K][1]
+    }
+    __syncthreads();
+#pragma unroll
+    for (int ci = 0; ci < PCI; ++ci) {
+      float w[12];
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
+        const float4 t4 = *reinterpret_cast<const float4*>(&xs[ci][tl + 4 * q]);
+        w[4 * q] = t4.x; w[4 * q + 1] = t4.y; w[4 * q + 2] = t4.z; w[4 * q + 3] = t4.w;
+      }
+#pragma unroll
+      for (int j = 0; j < K; ++j) {
+        const float wj = ws[ci * K + j];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) acc[r] = fmaf(wj, w[r + j], acc[r]);
+      }
+    }
+  }
+  const float bv = p.bias ? __ldg(p.bias) : 0.f;
+  float* yr = p.y + (int64_t)b * p.T + t0 + tl;
+  float o[4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    float v = acc[r] + bv;
+    if (p.post_tanh) v = tanhf(v);
+    o[r] = v;
+  }
+  if (t0 + tl + 3 < p.T && (p.T & 3) == 0) {
+    *reinterpret_cast<float4*>(yr) = make_float4(o[0], o[1], o[2], o[3]);
+  } else {
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+      if (t0 + tl + r < p.T) yr[r] = o[r];
+  }
+}
 }  // namespace
 
 int launch_conv1d_fp32(const ConvParams& p, cudaStream_t s) {
@@ -178,6 +242,12 @@ int launch_conv1d_fp32(const ConvParams& p, cudaStream_t s) {
                 p.k, p.d);
   if (p.B > 65535) return fail(AB_ERR_UNSUPPORTED, "conv1d: batch %d > 65535", p.B);
   const int halo = (p.k - 1) * p.d;
+  if (p.Cout == 1 && p.k == 7 && p.d == 1 && !p.residual && !p.acc_prev && p.out_div == 1.0f) {
+    dim3 grid((unsigned)ceil_div(p.T, PT), 1, (unsigned)p.B);
+    conv_post_fp32_kernel<7><<<grid, NT, 0, s>>>(p);
+    AB_LAUNCH_CHECK("conv_post_fp32_kernel");
+    return AB_OK;
+  }
   if (p.Cout <= 4) {
     const size_t smem = sizeof(float) * ((size_t)PCI * (PT + halo) + (size_t)p.Cin * p.k * p.Cout);
     if (smem > 200 * 1024) return fail(AB_ERR_UNSUPPORTED, "conv1d(few-out): filter too large for smem");

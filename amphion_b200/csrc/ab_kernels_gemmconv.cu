@@ -54,8 +54,8 @@ struct GcGeom {
 // ConvTranspose epilogue for one group of 8 output channels (8*U accumulator columns of one TMEM row):
 // the row is input time s, column (c*U + phi) holds y[co0 + c, s*U - pad + phi].  Stores the fp32 samples
 // (U consecutive floats per channel) and, optionally, the fp16 operand image row of each output time.
-template <int U>
-__device__ __forceinline__ void convT_group_store(const GcParams& p, const GcGeom& g, uint32_t taddr, int b, int co0,
+template <int U, class P, class G>
+__device__ __forceinline__ void convT_group_store(const P& p, const G& g, uint32_t taddr, int b, int co0,
                                                   int s, const float* bias_s, int bf16) {
   uint32_t r[8 * U];
 #pragma unroll
@@ -445,6 +445,7 @@ struct GsGeom {
   uint32_t chunk_bytes, stage_bytes, off_w, off_bias, off_bar, smem_bytes;
   uint32_t idesc;
   float out_scale;
+  int mode, cc, pad, grouped, Tout;   // conv-transpose: channels per N block, (k-u)/2, 8-channel-group epilogue
 };
 
 __global__ void __launch_bounds__(320, 1) gemmconv_stream_kernel(GsParams p, GsGeom g) {
@@ -486,6 +487,7 @@ __global__ void __launch_bounds__(320, 1) gemmconv_stream_kernel(GsParams p, GsG
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   for (int i = threadIdx.x; i < g.NB * g.Nb; i += 320) bias_s[i] = (p.bias != nullptr && i < p.Cout) ? __ldg(p.bias + i) : 0.f;
+  const int bf16 = p.precision == AB_PREC_TC_BF16;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -503,6 +505,17 @@ __global__ void __launch_bounds__(320, 1) gemmconv_stream_kernel(GsParams p, GsG
       mbar_wait(bar_accfull(buf), (uint32_t)(nb / g.nbuf) & 1u, 10);
       tc_fence_after();
       const uint32_t tbase = tmem + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(buf * g.Nb);
+      if (g.mode == 1) {
+        // polyphase conv-transpose: row = input time, 8-channel groups of 8*u columns
+        const int ngroups = g.cc >> 3;
+        for (int grp = 0; grp < ngroups; ++grp) {
+          const uint32_t ta = tbase + (uint32_t)(grp * 8 * p.u);
+          const int co0 = nb * g.cc + grp * 8;
+          if (p.u == 8) convT_group_store<8>(p, g, ta, b, co0, R0 + row, bias_s, bf16);
+          else if (p.u == 4) convT_group_store<4>(p, g, ta, b, co0, R0 + row, bias_s, bf16);
+          else convT_group_store<2>(p, g, ta, b, co0, R0 + row, bias_s, bf16);
+        }
+      } else {
       for (int ch = 0; ch < nch; ++ch) {
         uint32_t r[16];
         tc_ld16(tbase + (uint32_t)(ch * 16), r);
@@ -528,6 +541,7 @@ __global__ void __launch_bounds__(320, 1) gemmconv_stream_kernel(GsParams p, GsG
           }
         }
       }
+      }
       tc_fence_before();
       mbar_arrive(bar_accempty(buf));
     }
@@ -536,23 +550,57 @@ __global__ void __launch_bounds__(320, 1) gemmconv_stream_kernel(GsParams p, GsG
     const int lw = warp - 4;
     const int c8_img = (p.Cin + 15) >> 4 << 1;           // 8-channel groups present in the image
     const int c8_chunk = g.kchunk >> 3;
-    const uint16_t* xb = p.ximg + (size_t)b * c8_img * p.T * 8;
+    const uint16_t* xb = p.ximg ? p.ximg + (size_t)b * c8_img * p.T * 8 : nullptr;
     const int total = g.NB * g.KA;
     for (int it = 0; it < total; ++it) {
       const int ab = it & 1, kcA = it % g.KA;
       mbar_wait(bar_aempty(ab), (((uint32_t)(it >> 1)) & 1u) ^ 1u, 40);
       const uint32_t base = sA + (uint32_t)ab * g.chunk_bytes;
-      for (int c8 = lw; c8 < c8_chunk; c8 += 4) {
-        const int c8g = kcA * c8_chunk + c8;
-        const uint16_t* xc = xb + (size_t)c8g * p.T * 8;
-        for (int r = lane; r < g.rowsA; r += 32) {
-          const int tt = R0 - g.hh + r;
-          const bool okl = c8g < c8_img && tt >= 0 && tt < p.T;
-          cp_async16(base + unit_offset(g.rowsA, c8, r), okl ? (const void*)(xc + (size_t)tt * 8) : (const void*)xb,
-                     okl ? 16u : 0u);
+      if (p.ximg != nullptr) {
+        for (int c8 = lw; c8 < c8_chunk; c8 += 4) {
+          const int c8g = kcA * c8_chunk + c8;
+          const uint16_t* xc = xb + (size_t)c8g * p.T * 8;
+          for (int r = lane; r < g.rowsA; r += 32) {
+            const int tt = R0 - g.hh + r;
+            const bool okl = c8g < c8_img && tt >= 0 && tt < p.T;
+            cp_async16(base + unit_offset(g.rowsA, c8, r), okl ? (const void*)(xc + (size_t)tt * 8) : (const void*)xb,
+                       okl ? 16u : 0u);
+          }
+        }
+        cp_async_wait_all();
+      } else {
+        // fp32 input: load, activate, convert (32 independent loads in flight per lane)
+        const float* xf = p.x + (int64_t)b * p.Cin * p.T;
+        const int ngrp = (g.rowsA + 127) >> 7;
+        for (int item = lw; item < c8_chunk * ngrp; item += 4) {
+          const int c8 = item / ngrp, grp = item - c8 * ngrp;
+          const int row0 = (grp << 7) + lane;
+          float v[4][8];
+#pragma unroll
+          for (int r = 0; r < 4; ++r) {
+            const int rr = row0 + 32 * r;
+            const int tt = R0 - g.hh + rr;
+            const bool okl = rr < g.rowsA && tt >= 0 && tt < p.T;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const int c = kcA * g.kchunk + c8 * 8 + e;
+              v[r][e] = (okl && c < p.Cin) ? __ldg(xf + (int64_t)c * p.T + tt) : 0.f;
+            }
+          }
+#pragma unroll
+          for (int r = 0; r < 4; ++r) {
+            const int rr = row0 + 32 * r;
+            if (rr < g.rowsA) {
+              uint4 q;
+              q.x = pack2(lrelu(v[r][0], p.pre_slope), lrelu(v[r][1], p.pre_slope), bf16);
+              q.y = pack2(lrelu(v[r][2], p.pre_slope), lrelu(v[r][3], p.pre_slope), bf16);
+              q.z = pack2(lrelu(v[r][4], p.pre_slope), lrelu(v[r][5], p.pre_slope), bf16);
+              q.w = pack2(lrelu(v[r][6], p.pre_slope), lrelu(v[r][7], p.pre_slope), bf16);
+              *reinterpret_cast<uint4*>(smem + (size_t)ab * g.chunk_bytes + unit_offset(g.rowsA, c8, rr)) = q;
+            }
+          }
         }
       }
-      cp_async_wait_all();
       fence_proxy_async();
       mbar_arrive(bar_afull(ab));
     }
@@ -592,7 +640,8 @@ __global__ void __launch_bounds__(320, 1) gemmconv_stream_kernel(GsParams p, GsG
             const uint32_t ph = (uint32_t)(it / g.nstages) & 1u;
             mbar_wait(bar_full(s), ph, 31);
             tc_fence_after();
-            const uint32_t alo = desc_lo_sw32(a16 + (uint32_t)(kc * 2) * kstepA + (uint32_t)(tap * p.d) * 2u);
+            const int shift = g.mode ? (g.ntaps - 1 - tap) : tap * p.d;
+            const uint32_t alo = desc_lo_sw32(a16 + (uint32_t)(kc * 2) * kstepA + (uint32_t)shift * 2u);
             const uint32_t blo = desc_lo_sw32(w16 + (uint32_t)s * stage16);
             if (elected) {
               tc_mma_f16(td, hi | alo, hi | blo, g.idesc, (kcA | tap | kc) != 0 ? 1u : 0u);
@@ -619,7 +668,7 @@ __global__ void __launch_bounds__(320, 1) gemmconv_stream_kernel(GsParams p, GsG
 
 // image: [nb][kcA][tap][kc_l] stages, each [Nb rows x 32 channels] (SWIZZLE_32B rows)
 __global__ void gs_pack_weight_kernel(const float* __restrict__ w_t, uint16_t* __restrict__ img, GsGeom g, int cin,
-                                      int cout, int k, int bf16) {
+                                      int cout, int k, int u, int bf16) {
   const int64_t per_stage = (int64_t)g.Nb * 32;
   const int64_t total = (int64_t)g.NB * g.KA * g.ntaps * g.nkc_l * per_stage;
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
@@ -637,9 +686,16 @@ __global__ void gs_pack_weight_kernel(const float* __restrict__ w_t, uint16_t* _
     const int kcA = (int)(r % g.KA);
     const int nb = (int)(r / g.KA);
     const int ci = kcA * g.kchunk + kc * 32 + c8l * 8 + e;
-    const int co = nb * g.Nb + n;
     float v = 0.f;
-    if (ci < cin && co < cout) v = w_t[((int64_t)ci * k + tap) * cout + co];
+    if (g.mode == 0) {
+      const int co = nb * g.Nb + n;
+      if (ci < cin && co < cout) v = w_t[((int64_t)ci * k + tap) * cout + co];
+    } else {
+      const int col = n / u, phi = n - col * u;
+      const int co = nb * g.cc + col;
+      const int j = phi + u * tap;
+      if (ci < cin && col < g.cc && co < cout && j < k) v = w_t[((int64_t)ci * k + j) * cout + co];
+    }
     const int64_t stage = (((int64_t)nb * g.KA + kcA) * g.ntaps + tap) * g.nkc_l + kc;
     const int unit = (c8l & 1) ^ ((n >> 2) & 1);
     img[stage * per_stage + (int64_t)(c8l >> 1) * g.Nb * 16 + (int64_t)n * 16 + unit * 8 + e] =
@@ -647,16 +703,40 @@ __global__ void gs_pack_weight_kernel(const float* __restrict__ w_t, uint16_t* _
   }
 }
 
-int gs_layer_geom(int cin, int cout, int k, int d, GsGeom& g) {
-  if (cin <= 0 || cout <= 0 || k <= 0 || !(k & 1) || d <= 0) return fail(AB_ERR_UNSUPPORTED, "gemmconv(stream): bad layer");
+int gs_layer_geom(int mode, int cin, int cout, int k, int d_or_u, GsGeom& g) {
+  if (cin <= 0 || cout <= 0 || k <= 0 || d_or_u <= 0) return fail(AB_ERR_UNSUPPORTED, "gemmconv(stream): bad layer");
+  g.mode = mode;
   g.Kp = rup(cin, 16);
-  const int Np = rup(cout, 16);
-  g.NB = (Np + 255) / 256;
-  g.Nb = rup((Np + g.NB - 1) / g.NB, 16);
+  int maxshift;
+  if (mode == 0) {
+    if (!(k & 1)) return fail(AB_ERR_UNSUPPORTED, "gemmconv(stream): conv kernel size must be odd");
+    const int Np = rup(cout, 16);
+    g.NB = (Np + 255) / 256;
+    g.Nb = rup((Np + g.NB - 1) / g.NB, 16);
+    g.cc = g.Nb;
+    g.ntaps = k;
+    g.pad = 0;
+    g.grouped = 0;
+    maxshift = (k - 1) * d_or_u;
+    if (maxshift & 1) return fail(AB_ERR_UNSUPPORTED, "gemmconv(stream): (k-1)*dilation must be even");
+    g.hh = maxshift / 2;
+  } else {
+    const int u = d_or_u;
+    if (k < u || ((k - u) & 1)) return fail(AB_ERR_UNSUPPORTED, "gemmconv(stream): conv-transpose needs k >= stride, k-stride even");
+    if (!(u == 2 || u == 4 || u == 8)) return fail(AB_ERR_UNSUPPORTED, "gemmconv(stream): stride must be 2, 4 or 8");
+    int cc = std::min(256 / u, cout);
+    if ((cc % 8) || (cout % 8)) return fail(AB_ERR_UNSUPPORTED, "gemmconv(stream): channels must be a multiple of 8");
+    g.cc = cc;
+    g.Nb = rup(cc * u, 16);
+    g.NB = (cout + cc - 1) / cc;
+    g.ntaps = (k + u - 1) / u;
+    g.pad = (k - u) / 2;
+    g.grouped = 1;
+    maxshift = g.ntaps - 1;
+    g.hh = g.ntaps - 1;
+  }
   g.nbuf = g.NB > 1 ? 2 : 1;
-  g.ntaps = k;
-  g.hh = (k - 1) * d / 2;
-  g.rowsA = rup(128 + (k - 1) * d, 8);
+  g.rowsA = rup(128 + maxshift, 8);
   g.stage_bytes = (uint32_t)g.Nb * 64u;
   const uint32_t misc = (uint32_t)(g.NB * g.Nb) * 4u + 8u * (2 * GC_MAX_STAGES + 8) + 16u;
   for (int kchunk = 256; kchunk >= 32; kchunk -= 32) {
@@ -673,37 +753,45 @@ int gs_layer_geom(int cin, int cout, int k, int d, GsGeom& g) {
     g.smem_bytes = g.off_bar + 8u * (2 * GC_MAX_STAGES + 8) + 16u;
     return AB_OK;
   }
-  return fail(AB_ERR_UNSUPPORTED, "gemmconv(stream): k=%d d=%d does not fit shared memory", k, d);
+  return fail(AB_ERR_UNSUPPORTED, "gemmconv(stream): k=%d d|u=%d does not fit shared memory", k, d_or_u);
 }
 
 }  // namespace
 
-size_t gs_weight_image_bytes(int cin, int cout, int k, int d) {
+bool gs_can_emit_image(int cout, int k, int u) {
   GsGeom g;
-  if (gs_layer_geom(cin, cout, k, d, g) != AB_OK) return 0;
+  return gs_layer_geom(1, 16, cout, k, u, g) == AB_OK && (cout % 16) == 0;
+}
+
+size_t gs_weight_image_bytes(int mode, int cin, int cout, int k, int d_or_u) {
+  GsGeom g;
+  if (gs_layer_geom(mode, cin, cout, k, d_or_u, g) != AB_OK) return 0;
   return (size_t)g.NB * g.KA * g.ntaps * g.nkc_l * g.stage_bytes;
 }
 
-int launch_gs_pack_weight(const float* w_t, void* image, int cin, int cout, int k, int d, int precision,
-                          cudaStream_t s) {
+int launch_gs_pack_weight(const float* w_t, void* image, int mode, int cin, int cout, int k, int d_or_u,
+                          int precision, cudaStream_t s) {
   GsGeom g;
-  int rc = gs_layer_geom(cin, cout, k, d, g);
+  int rc = gs_layer_geom(mode, cin, cout, k, d_or_u, g);
   if (rc != AB_OK) return rc;
   const int64_t total = (int64_t)g.NB * g.KA * g.ntaps * g.nkc_l * g.Nb * 32;
   const int blocks = (int)std::min<int64_t>((total + 255) / 256, 148 * 8);
-  gs_pack_weight_kernel<<<blocks, 256, 0, s>>>(w_t, static_cast<uint16_t*>(image), g, cin, cout, k,
+  gs_pack_weight_kernel<<<blocks, 256, 0, s>>>(w_t, static_cast<uint16_t*>(image), g, cin, cout, k, d_or_u,
                                                precision == AB_PREC_TC_BF16 ? 1 : 0);
   AB_LAUNCH_CHECK("gs_pack_weight_kernel");
   return AB_OK;
 }
 
 int launch_gemmconv_stream(const GsParams& p, cudaStream_t s) {
-  if (!p.ximg || !p.y || !p.w) return fail(AB_ERR_ARG, "gemmconv(stream): null argument");
+  if ((!p.ximg && !p.x) || !p.y || !p.w) return fail(AB_ERR_ARG, "gemmconv(stream): null argument");
   if (p.B <= 0 || p.T <= 0) return fail(AB_ERR_ARG, "gemmconv(stream): bad shape");
   GsGeom g;
-  int rc = gs_layer_geom(p.Cin, p.Cout, p.k, p.d, g);
+  int rc = gs_layer_geom(p.mode, p.Cin, p.Cout, p.k, p.mode ? p.u : p.d, g);
   if (rc != AB_OK) return rc;
-  g.tiles = (p.T + 127) / 128;
+  if (p.yimg != nullptr && !(p.mode == 1 && (p.Cout % 16) == 0))
+    return fail(AB_ERR_UNSUPPORTED, "gemmconv(stream): cannot emit an operand image for this layer");
+  g.Tout = p.mode ? p.T * p.u : p.T;
+  g.tiles = ((p.mode ? p.T + 1 : p.T) + 127) / 128;
   const uint32_t fmt = p.precision == AB_PREC_TC_BF16 ? 1u : 0u;
   g.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(g.Nb >> 3) << 17) | ((128u >> 4) << 24);
   g.out_scale = 1.0f / p.out_div;

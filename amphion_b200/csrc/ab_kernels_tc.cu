@@ -17,10 +17,11 @@
 //   epilogue 2 TMEM -> +bias +residual (+branch sum, /nk) -> fp32 y and the fp16 operand image of
 //              lrelu(y) for the next kernel.  The residual / branch-sum tiles are streamed through a
 //              per-warp cp.async ring placed in the (now free) A region.
-// Warp roles: WW worker warps, 1 TMA producer warp, 1 MMA-issue warp.  Two configurations:
-//   <8,1>: full tile (m*Np = 512 TMEM columns), one CTA per SM;
-//   <4,2>: half tile (<= 256 columns, <= 113 KB smem), two CTAs per SM so one CTA's global-memory
-//          phases overlap the other's MMA phases.
+// Warp roles: WW worker warps, 1 TMA producer warp, 1 MMA-issue warp.  Configurations:
+//   <8,1>: full tile (m*Np = 512 TMEM columns), one CTA per SM (C = 256: the tile does not fit twice);
+//   <8,2>: half tile (<= 256 columns, <= 113 KB smem, 96 registers), two CTAs per SM so one CTA's
+//          global-memory phases overlap the other's MMA phases (default whenever it fits);
+//   <4,2>, <4,3>: the same with 4 worker warps / third-size tiles (measured slower or equal; knobs only).
 #include <stdlib.h>
 
 #include <algorithm>
@@ -57,6 +58,7 @@ struct TcGeom {
   uint32_t idesc;
   int tmem_cols;   // TMEM columns to allocate (power of two >= m*Np)
   int dual;        // 0: full tile, 8 worker warps, 1 CTA/SM; n >= 2: 1/n tile, 4 worker warps, n CTAs per SM
+  int ww;          // worker warps of the chosen configuration (4 or 8)
   int ring_depth;  // slots per worker warp in the epilogue-2 ring (2..4)
   int staged;      // 1: epilogue 2 streams residual / branch sum through the cp.async ring (needs T % 4 == 0)
   int stagger_groups, first_wave;   // first-wave CTAs start (blockIdx % groups) * stagger_cycles late so that the
@@ -487,8 +489,11 @@ int make_geom(const TcConvParams& p, TcGeom& g) {
     int m2 = std::min(cols / g.Np, 16);
     while (m2 > 1 && (m2 - 1) * 128 - lost >= p.T) --m2;
     const uint32_t limit = n == 2 ? 113u * 1024u : 74u * 1024u;
-    if (m2 >= 1 && try_fit(m2, 4, limit, 3)) {
+    static const int ww_pref = [] { const char* e = getenv("AB_TC_WW"); return e ? atoi(e) : 8; }();
+    const int ww = (n == 2 && ww_pref == 8) ? 8 : 4;
+    if (m2 >= 1 && try_fit(m2, ww, limit, 3)) {
       g.dual = n;
+      g.ww = ww;
       g.tmem_cols = 32;
       while (g.tmem_cols < g.m * g.Np) g.tmem_cols *= 2;
     }
@@ -501,6 +506,7 @@ int make_geom(const TcConvParams& p, TcGeom& g) {
       if (m < 1) return fail(AB_ERR_UNSUPPORTED, "tc_conv: C=%d k=%d d=%d does not fit shared memory", p.C, p.k, p.d1);
       if (try_fit(m, 8, TC_SMEM_LIMIT, 2)) break;
     }
+    g.ww = 8;
     g.tmem_cols = 512;
   }
   g.V = ((g.m * 128 - lost) / 8) * 8;
@@ -565,6 +571,8 @@ int launch_tc_conv(const TcConvParams& p, cudaStream_t s) {
     AB_CUDA_TRY(cudaFuncSetAttribute(tc_conv_kernel<8, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_LIMIT));
     AB_CUDA_TRY(cudaFuncSetAttribute(tc_conv_kernel<4, 2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
     AB_CUDA_TRY(cudaFuncSetAttribute(tc_conv_kernel<4, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
+    AB_CUDA_TRY(cudaFuncSetAttribute(tc_conv_kernel<8, 2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
+    AB_CUDA_TRY(cudaFuncSetAttribute(tc_conv_kernel<8, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
     AB_CUDA_TRY(cudaFuncSetAttribute(tc_conv_kernel<4, 3, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 74 * 1024));
     AB_CUDA_TRY(cudaFuncSetAttribute(tc_conv_kernel<4, 3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 74 * 1024));
     configured = true;
@@ -584,6 +592,9 @@ int launch_tc_conv(const TcConvParams& p, cudaStream_t s) {
   if (g.dual == 3) {
     if (bf) tc_conv_kernel<4, 3, 1><<<(unsigned)grid, 4 * 32 + 64, smem, s>>>(p, g);
     else tc_conv_kernel<4, 3, 0><<<(unsigned)grid, 4 * 32 + 64, smem, s>>>(p, g);
+  } else if (g.dual == 2 && g.ww == 8) {
+    if (bf) tc_conv_kernel<8, 2, 1><<<(unsigned)grid, 8 * 32 + 64, smem, s>>>(p, g);
+    else tc_conv_kernel<8, 2, 0><<<(unsigned)grid, 8 * 32 + 64, smem, s>>>(p, g);
   } else if (g.dual == 2) {
     if (bf) tc_conv_kernel<4, 2, 1><<<(unsigned)grid, 4 * 32 + 64, smem, s>>>(p, g);
     else tc_conv_kernel<4, 2, 0><<<(unsigned)grid, 4 * 32 + 64, smem, s>>>(p, g);

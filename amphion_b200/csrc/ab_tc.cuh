@@ -52,8 +52,14 @@ bool gc_can_emit_image(int cout, int k, int u);
 // Streaming N-blocked conv for wide layers (C_in beyond a resident tile): operand-image input only.
 //   y = ((conv(ximg, d) + bias) + residual + acc_prev) / out_div
 struct GsParams {
-  const uint16_t* ximg;   // [B][ceil16(Cin)/8][T][8] already activated operands
-  float* y;               // [B, Cout, T] fp32
+  const uint16_t* ximg;   // [B][ceil16(Cin)/8][T][8] already activated operands, or nullptr ->
+  const float* x;         //   fp32 [B, Cin, T] contiguous, activated with lrelu(., pre_slope) by the loader warps
+  float pre_slope;
+  int mode;               // 0 conv ("same", dilation d); 1 conv-transpose (stride u, padding (k-u)/2)
+  int u;
+  uint16_t* yimg;         // conv-transpose only, nullable
+  float img_slope;
+  float* y;               // conv: [B, Cout, T]; conv-transpose: [B, Cout, T*u]
   const void* w;          // image built by launch_gs_pack_weight
   const float* bias;
   const float* residual;  // nullable
@@ -63,9 +69,10 @@ struct GsParams {
   float out_div;
   int precision;
 };
-size_t gs_weight_image_bytes(int cin, int cout, int k, int d);
-int launch_gs_pack_weight(const float* w_t, void* image, int cin, int cout, int k, int d, int precision,
-                          cudaStream_t s);
+size_t gs_weight_image_bytes(int mode, int cin, int cout, int k, int d_or_u);
+int launch_gs_pack_weight(const float* w_t, void* image, int mode, int cin, int cout, int k, int d_or_u,
+                          int precision, cudaStream_t s);
+bool gs_can_emit_image(int cout, int k, int u);
 int launch_gemmconv_stream(const GsParams& p, cudaStream_t s);
 size_t gc_weight_image_bytes(int mode, int cin, int cout, int k, int d_or_u);
 int launch_gc_pack_weight(const float* w_t, void* image, int mode, int cin, int cout, int k, int d_or_u,

@@ -298,6 +298,14 @@ def test_bigvgan_wide_layers_match_oracle():
         got = model(mel.to(DEV)).cpu().numpy()
         assert np.isfinite(got).all()
         assert np.abs(got - want).max() <= tol, (prec, np.abs(got - want).max())
+    # BigVGAN-large widths: the first ConvTranspose is 1536 -> 768 (C_in beyond a resident tile: streaming
+    # conv-transpose with fp32 loader warps), stage 0 runs 768 channels
+    hp = dict(hp, upsample_initial_channel=1536, resblock_kernel_sizes=[3], resblock_dilation_sizes=[[1, 3]])
+    model, mel, want = _full_size_case("bigvgan", hp, 12, 1, 19, seed=8)
+    model.precision = "tc_f16"
+    got = model(mel.to(DEV)).cpu().numpy()
+    assert np.isfinite(got).all()
+    assert np.abs(got - want).max() <= 1e-3, np.abs(got - want).max()
 
 
 @pytest.mark.parametrize("prec", ["fp32", "tc_f16"])
