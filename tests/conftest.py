@@ -10,6 +10,15 @@ if ROOT not in sys.path:
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 
+# The CPU oracle (oneDNN convs on small channel counts) gets slower, not faster, beyond ~16 threads: on the
+# 128-thread GPU box the wide-model oracle took minutes.  Cap the threads the test process uses.
+try:
+    import torch
+    torch.set_num_threads(min(16, os.cpu_count() or 1))
+except Exception:  # pragma: no cover
+    pass
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
