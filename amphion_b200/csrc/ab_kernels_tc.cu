@@ -232,33 +232,45 @@ __global__ void __launch_bounds__(WW * 32 + 64, MINB) tc_conv_kernel(TcConvParam
       const int nitems = g.m * nchw;
       const int RD = g.ring_depth;
       uint8_t* ring = smem + (size_t)warp * ((size_t)RD * RING_SLOT_BYTES);
-      auto issue = [&](int it) {
-        const int i = it / nchw, ch = hsel + (it - i * nchw) * NWG;
-        const int tb = T0 + i * 128 + q4 * 32;
-        const uint32_t slot = smem_u32(ring + (size_t)(it % RD) * RING_SLOT_BYTES);
+      const uint32_t ring_u32 = smem_u32(ring);
+      // item = (M-tile i, 16-column chunk ch); no divisions in the loop: both the issue side and the consume
+      // side walk (i, ch, slot) incrementally.  The four 16-byte units a lane copies per item are
+      // (channel c0 + 4k, rows 4*r4 .. 4*r4+3), k = 0..3.
+      const int r4 = lane & 7, c0 = lane >> 3;
+      const uint32_t sm_lane = (uint32_t)(c0 * 128 + r4 * 16);
+      const int64_t g_lane = bCT + (int64_t)c0 * p.T + 4 * r4;
+      const int64_t kT4 = 4 * (int64_t)p.T;
+      int ii = 0, ich = hsel, islot = 0;             // issue cursor
+      auto issue = [&]() {
+        const int tb = T0 + ii * 128 + q4 * 32;
+        const uint32_t slot = ring_u32 + (uint32_t)islot * RING_SLOT_BYTES + sm_lane;
+        const int64_t base = g_lane + (int64_t)(ich * 16) * p.T + tb;
+        const bool tok = tb + 4 * r4 < p.T;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          const int u = lane + 32 * k, c = u >> 3, r4 = u & 7;
-          const int co = ch * 16 + c, t = tb + 4 * r4;
-          const bool ok = co < p.C && t < p.T;
-          const int64_t off = bCT + (int64_t)co * p.T + t;
-          if (p.residual && !(g.skip & 4)) cp_async16(slot + (uint32_t)(c * 128 + r4 * 16), ok ? p.residual + off : p.residual, ok ? 16u : 0u);
-          if (p.acc_prev && !(g.skip & 4)) cp_async16(slot + 2048u + (uint32_t)(c * 128 + r4 * 16), ok ? p.acc_prev + off : p.acc_prev, ok ? 16u : 0u);
+          const bool ok = tok && (ich * 16 + c0 + 4 * k) < p.C;
+          const int64_t off = base + k * kT4;
+          if (has_res) cp_async16(slot + (uint32_t)(k * 512), ok ? p.residual + off : p.residual, ok ? 16u : 0u);
+          if (has_acc) cp_async16(slot + 2048u + (uint32_t)(k * 512), ok ? p.acc_prev + off : p.acc_prev, ok ? 16u : 0u);
         }
         cp_async_commit();
+        ich += NWG;
+        if (ich >= nch) { ich = hsel; ++ii; }
+        islot = islot + 1 == RD ? 0 : islot + 1;
       };
-      for (int it = 0; it < RD - 1; ++it) {
-        if (it < nitems) issue(it); else cp_async_commit();
+      int issued = 0;
+      for (; issued < RD - 1; ++issued) {
+        if (issued < nitems) issue(); else cp_async_commit();
       }
+      int i = 0, ch = hsel, cslot = 0;               // consume cursor
       for (int it = 0; it < nitems; ++it) {
-        if (it + RD - 1 < nitems) issue(it + RD - 1); else cp_async_commit();
-        const int i = it / nchw, ch = hsel + (it - i * nchw) * NWG;
+        if (issued < nitems) { issue(); ++issued; } else cp_async_commit();
         uint32_t r[16];
         tc_ld16(tmem + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(i * g.Np + ch * 16), r);
         if (RD == 4) cp_async_wait_group<3>(); else if (RD == 3) cp_async_wait_group<2>(); else cp_async_wait_group<1>();
         __syncwarp();
         tc_wait_ld();
-        const float* rs = reinterpret_cast<const float*>(ring + (size_t)(it % RD) * RING_SLOT_BYTES);
+        const float* rs = reinterpret_cast<const float*>(ring + (size_t)cslot * RING_SLOT_BYTES);
         const int row = i * 128 + q4 * 32 + lane;
         const int t = T0 + row;
         const bool ok = row < g.V && t < p.T;
@@ -293,6 +305,9 @@ __global__ void __launch_bounds__(WW * 32 + 64, MINB) tc_conv_kernel(TcConvParam
             *reinterpret_cast<uint4*>(yi + (size_t)h * p.T * 8) = q;
           }
         }
+        ch += NWG;
+        if (ch >= nch) { ch = hsel; ++i; }
+        cslot = cslot + 1 == RD ? 0 : cslot + 1;
         __syncwarp();
       }
       cp_async_wait_all();
