@@ -390,7 +390,7 @@ int ab_generator_finalize(ab_generator* g, int32_t precision, void* stream) {
 // ---------------------------------------------------------------------------
 namespace {
 constexpr int NBUF = 7;  // fp32: R0 R1 U P0 P1 TMP ACT
-constexpr int NIMG = 3;  // 16-bit operand images: U P0 P1
+constexpr int NIMG = 4;  // 16-bit operand images: U P0 P1 R (stage output, HiFi-GAN)
 
 size_t stage_max_image_bytes(const ab_generator* g, int64_t B, int64_t T) {
   size_t mx = 0;
@@ -470,7 +470,8 @@ int ab_generator_forward(ab_generator* g, const float* dev_mel, int64_t B, int64
   uint16_t* img[NIMG];
   for (int i = 0; i < NIMG; ++i)
     img[i] = reinterpret_cast<uint16_t*>(static_cast<char*>(dev_workspace) + NBUF * bufsz + i * imgsz);
-  uint16_t *U16 = img[0], *P16[2] = {img[1], img[2]};
+  uint16_t *U16 = img[0], *P16[2] = {img[1], img[2]}, *R16 = img[3];
+  const uint16_t* r_img = nullptr;   // operand image of lrelu(stage input, 0.1) when the previous stage emitted it
   float *R[2] = {buf[0], buf[1]}, *U = buf[2], *P[2] = {buf[3], buf[4]}, *TMP = buf[5], *ACT = buf[6];
   const bool big = g->cfg.kind == AB_GEN_BIGVGAN;
   const bool tc = g->precision != AB_PREC_FP32;
@@ -509,7 +510,7 @@ int ab_generator_forward(ab_generator* g, const float* dev_mel, int64_t B, int64
     int r;
     if (gc) {
       GcParams gp;
-      gp.x = x; gp.xsb = xsb; gp.xsc = xsc; gp.xst = xst; gp.y = y; gp.w = g->tcptr(c.w); gp.bias = g->fptr(c.b);
+      gp.x = x; gp.xsb = xsb; gp.xsc = xsc; gp.xst = xst; gp.ximg = nullptr; gp.y = y; gp.w = g->tcptr(c.w); gp.bias = g->fptr(c.b);
       gp.residual = residual; gp.B = (int)B; gp.Cin = c.cin; gp.Cout = c.cout; gp.Tin = Tn; gp.mode = 0;
       gp.k = c.k; gp.d = c.d; gp.u = 1; gp.pre_slope = pre_slope; gp.post_tanh = post_tanh;
       gp.precision = g->precision; gp.yimg = nullptr; gp.img_slope = 1.0f;
@@ -604,7 +605,8 @@ int ab_generator_forward(ab_generator* g, const float* dev_mel, int64_t B, int64
       rc = launch_gemmconv_stream(sp, st);
     } else if (tc && g->slots[sg.up.w].tc_kind == 2) {
       GcParams gp;
-      gp.x = R[cur_r]; gp.xsb = (int64_t)cin * Tn; gp.xsc = Tn; gp.xst = 1; gp.y = U; gp.w = g->tcptr(sg.up.w); gp.bias = g->fptr(sg.up.b); gp.residual = nullptr;
+      gp.x = R[cur_r]; gp.xsb = (int64_t)cin * Tn; gp.xsc = Tn; gp.xst = 1; gp.y = U; gp.w = g->tcptr(sg.up.w);
+      gp.ximg = (r_img != nullptr && (cin % 16) == 0) ? r_img : nullptr; gp.bias = g->fptr(sg.up.b); gp.residual = nullptr;
       gp.B = (int)B; gp.Cin = cin; gp.Cout = sg.ch; gp.Tin = Tn; gp.mode = 1; gp.k = sg.up.k; gp.d = 1; gp.u = sg.u;
       gp.pre_slope = tp.pre_slope; gp.post_tanh = 0; gp.precision = g->precision;
       // HiFi-GAN: every consumer of U applies lrelu(., 0.1) first (hifigan.py:95) -> emit that operand image
@@ -622,6 +624,7 @@ int ab_generator_forward(ab_generator* g, const float* dev_mel, int64_t B, int64
     float* Rout = R[cur_r ^ 1];
     const int64_t sb = (int64_t)C * Tn, sc = Tn;
     const bool use_tc = tc && tc_conv_supported(C, sg.blocks[0].k);
+    bool stage_img_written = false;
     for (int j = 0; j < nk; ++j) {
       const BlockRef& blk = sg.blocks[j];
       const float* cur = U;
@@ -632,6 +635,9 @@ int ab_generator_forward(ab_generator* g, const float* dev_mel, int64_t B, int64
         const bool last = p == nd - 1;
         float* dst = last ? Rout : P[pp];
         uint16_t* dst_img = (last || big) ? nullptr : P16[pp];
+        // the stage output feeds the next ConvTranspose through lrelu(., 0.1) (hifigan.py:206): emit that image
+        const bool stage_img = last && j == nk - 1 && !big && i + 1 < g->stages.size();
+        if (stage_img) dst_img = R16;
         if (!last) pp ^= 1;
         // xs = rb_0(x) ; xs += rb_j(x) ; x = xs / num_kernels  (hifigan.py:208-214)
         const float* accp = (last && j > 0) ? Rout : nullptr;
@@ -646,6 +652,7 @@ int ab_generator_forward(ab_generator* g, const float* dev_mel, int64_t B, int64
                           cur_img, dst_img);
             if (rc != AB_OK) return rc;
             cur_img = dst_img;
+            if (stage_img) stage_img_written = true;
           } else if (pair) {
             rc = conv(blk.c1[p], cur, sb, sc, 1, TMP, Tn, 0.1f, nullptr, nullptr, 1.0f, 0);
             if (rc != AB_OK) return rc;
@@ -688,6 +695,7 @@ int ab_generator_forward(ab_generator* g, const float* dev_mel, int64_t B, int64
     }
     cur_r ^= 1;
     cin = C;
+    r_img = stage_img_written ? R16 : nullptr;
   }
   // post: leaky_relu(x) with the DEFAULT slope 0.01 (hifigan.py:215) or
   // activation_post (bigvgan.py:327); conv_post; tanh
@@ -753,7 +761,7 @@ int ab_conv1d_forward(const float* dev_x, const float* dev_w, const float* dev_b
     rc = launch_gc_pack_weight(w_t, gimg, 0, (int)cin, (int)cout, k, d, precision, st);
     if (rc != AB_OK) return rc;
     GcParams gp;
-    gp.x = dev_x; gp.xsb = cin * T; gp.xsc = T; gp.xst = 1; gp.y = dev_y; gp.w = gimg; gp.bias = dev_bias;
+    gp.x = dev_x; gp.xsb = cin * T; gp.xsc = T; gp.xst = 1; gp.ximg = nullptr; gp.y = dev_y; gp.w = gimg; gp.bias = dev_bias;
     gp.residual = dev_residual; gp.B = (int)B; gp.Cin = (int)cin; gp.Cout = (int)cout; gp.Tin = (int)T; gp.mode = 0;
     gp.k = k; gp.d = d; gp.u = 1; gp.pre_slope = pre_slope; gp.post_tanh = post_tanh; gp.precision = precision;
     gp.yimg = nullptr; gp.img_slope = 1.0f;
@@ -794,7 +802,7 @@ int ab_conv_transpose1d_forward(const float* dev_x, const float* dev_w, const fl
     rc = launch_gc_pack_weight(w_t, img, 1, (int)cin, (int)cout, k, u, precision, st);
     if (rc != AB_OK) return rc;
     GcParams gp;
-    gp.x = dev_x; gp.xsb = cin * Tin; gp.xsc = Tin; gp.xst = 1; gp.y = dev_y; gp.w = img; gp.bias = dev_bias; gp.residual = nullptr;
+    gp.x = dev_x; gp.xsb = cin * Tin; gp.xsc = Tin; gp.xst = 1; gp.ximg = nullptr; gp.y = dev_y; gp.w = img; gp.bias = dev_bias; gp.residual = nullptr;
     gp.B = (int)B; gp.Cin = (int)cin; gp.Cout = (int)cout; gp.Tin = (int)Tin; gp.mode = 1; gp.k = k; gp.d = 1; gp.u = u;
     gp.pre_slope = pre_slope; gp.post_tanh = 0; gp.precision = precision;
     gp.yimg = nullptr; gp.img_slope = 1.0f;

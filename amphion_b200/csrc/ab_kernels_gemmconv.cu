@@ -154,7 +154,21 @@ __global__ void __launch_bounds__(GC_THREADS, 1) gemmconv_kernel(GcParams p, GcG
     const int nbias = g.mode ? g.NB * g.cc : g.NB * g.Nb;
     for (int i = threadIdx.x; i < nbias; i += GC_WORKERS)
       bias_s[i] = (p.bias != nullptr && i < p.Cout) ? __ldg(p.bias + i) : 0.f;
-    {
+    if (p.ximg != nullptr) {
+      // operand image in: register-free cp.async burst, zero fill outside [0, Tin)
+      const int c8n = g.Kp >> 3;
+      const uint16_t* xb = p.ximg + (size_t)b * c8n * p.Tin * 8;
+      for (int c8 = warp; c8 < c8n; c8 += GC_WORKER_WARPS) {
+        const uint16_t* xc = xb + (size_t)c8 * p.Tin * 8;
+        for (int row = lane; row < g.rowsA; row += 32) {
+          const int t = R0 - g.row0_time + row;
+          const bool ok = t >= 0 && t < p.Tin;
+          cp_async16(sA + unit_offset(g.rowsA, c8, row), ok ? (const void*)(xc + (size_t)t * 8) : (const void*)xb,
+                     ok ? 16u : 0u);
+        }
+      }
+      cp_async_wait_all();
+    } else {
       const int ngrp = (g.rowsA + 127) >> 7;
       const int c8n = g.Kp >> 3;
       const float* xb = p.x + (int64_t)b * p.xsb;
@@ -834,7 +848,8 @@ int launch_gc_pack_weight(const float* w_t, void* image, int mode, int cin, int 
 }
 
 int launch_gemmconv(const GcParams& p, cudaStream_t s) {
-  if (!p.x || !p.y || !p.w) return fail(AB_ERR_ARG, "gemmconv: null argument");
+  if ((!p.x && !p.ximg) || !p.y || !p.w) return fail(AB_ERR_ARG, "gemmconv: null argument");
+  if (p.ximg && (p.Cin % 16) != 0) return fail(AB_ERR_UNSUPPORTED, "gemmconv: operand-image input needs C_in %% 16 == 0");
   if (p.B <= 0 || p.Tin <= 0) return fail(AB_ERR_ARG, "gemmconv: bad shape");
   if (p.precision != AB_PREC_TC_F16 && p.precision != AB_PREC_TC_BF16) return fail(AB_ERR_ARG, "gemmconv: bad precision");
   GcGeom g;

@@ -34,6 +34,7 @@ struct TcConvParams {
 struct GcParams {
   const float* x;         // [B, Cin, Tin] fp32 with element strides xsb / xsc / xst
   int64_t xsb, xsc, xst;
+  const uint16_t* ximg;   // optional: already activated operand image [B][ceil16(Cin)/8][Tin][8] (then x is unused)
   float* y;               // conv: [B, Cout, Tin]; conv-transpose: [B, Cout, Tin*u]
   const void* w;          // operand image built by launch_gc_pack_weight
   const float* bias;      // nullable
