@@ -400,11 +400,18 @@ int launch_conv_transpose1d_fp32(const ConvTParams& p, cudaStream_t s) {
 //                              u[2q+1] = 2 sum_m f[10-2m] xh[q-2+m],  xh = replicate(x)
 //   act  (snake.py:51-61,110-122): v = u + 1/(b+1e-9) * sin(u*a)^2
 //   down (filter.py:92-99):    y[t] = sum_j f[j] v[clamp(2t+j-5, 0, 2T-1)]
-// One CTA per (batch, channel, 1024-sample tile).  HBM-bound by design
-// (4 B read + 4 B written per element).
+// One CTA = (batch, group of 8 channels, 960-sample tile); every warp owns 120 consecutive outputs for all
+// 8 channels and works on private shared-memory windows, so there are no block-level barriers in the loop.
+// The kernel is instruction-issue bound (ncu: ~80 % of issue slots), so the design minimises instructions per
+// sample: 16-byte window fetches, taps pre-scaled by the x2 gain (exact: power of two), per-channel
+// exp / reciprocal computed once per CTA, and a lane-private transposition buffer for the operand image.
 // ===========================================================================
 namespace {
-constexpr int AT = 1024;
+constexpr int SN_WS = 120;                 // outputs per warp segment (30 lanes x 4)
+constexpr int SN_XS = 136;                 // xs[m] = xh[t0 - 8 + m]            (34 float4)
+constexpr int SN_VS = 256;                 // vs[n] = vh[2*t0 - 7 + n]          (64 groups of 4 = 2 full rounds)
+constexpr int SN_TR = 8 * 32 * 2;          // image transposition: [8 ch][32 lanes] x 8 B, lane-private
+constexpr int WT = 8 * SN_WS;              // outputs per CTA tile (8 warps)
 
 __device__ __forceinline__ float snake_eval(float u, float a, float invb) {
   // sin(u*a)^2 with explicit range reduction to [-pi, pi] before the MUFU
@@ -416,111 +423,119 @@ __device__ __forceinline__ float snake_eval(float u, float a, float invb) {
   return fmaf(invb, sv * sv, u);
 }
 
-// One CTA = (batch, group of 8 channels, 1024-sample tile); the 8 channels are processed one after the
-// other through the same shared-memory buffers so that the fp16 operand image (8 channels = 16 B per time
-// step, the unit the tensor-core kernels stage) can be written with coalesced 16-byte stores.
-// Per channel: phase 1 computes the 2x-rate samples v = snake(up(x)) four at a time from one 7-sample
-// window of x (filters in registers, 4 x LDS.64 per 4 samples); phase 2 computes four consecutive outputs
-// per thread from an 18-sample window of v (5 x LDS.128).
-template <int MINB>
-__global__ void __launch_bounds__(NT, MINB) activation1d_kernel(SnakeParams p) {
-  __shared__ __align__(16) float xs[AT + 16];       // xs[n] = xhat[t0 - 5 + n]
-  __shared__ __align__(16) float vs[2 * AT + 24];   // vs[n] = v[clamp(2*t0 - 5 + n, 0, 2T-1)]
-  const int t0 = blockIdx.x * AT, c8 = blockIdx.y, b = blockIdx.z;
-  const int T = p.T;
-  float fu[12], fd[12];
+template <int BF16>
+__device__ __forceinline__ uint32_t cvt_pair(float lo, float hi) {
+  uint32_t r;
+  if (BF16) asm("cvt.rn.satfinite.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  else asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+
+// All 8 channels of one warp segment.  FAST: the whole window [t0-8, t0+128) lies inside the row and rows are
+// 16-byte aligned, so the fetch is one float4 per lane and no index is clamped; otherwise (sequence edges,
+// odd T) every index is replicate-clamped exactly as the reference's padding does.
+template <bool FAST, int BF16>
+__device__ __forceinline__ void snake_segment(const SnakeParams& p, const float* __restrict__ xb, int c8, int b, int t0,
+                                              const float (*prm)[2], float* xs, float* vs, uint2* tr, int lane) {
+  const int T = p.T, C = p.C;
+  float fu2[12], fd[12];
 #pragma unroll
   for (int j = 0; j < 12; ++j) {
-    fu[j] = __ldg(p.f_up + j);
+    fu2[j] = 2.0f * __ldg(p.f_up + j);
     fd[j] = __ldg(p.f_down + j);
   }
-  float out[4][8];
-#pragma unroll
-  for (int k = 0; k < 4; ++k)
-#pragma unroll
-    for (int cg = 0; cg < 8; ++cg) out[k][cg] = 0.f;
-  const int i0 = 2 * t0 - 5;
-  const int imax = 2 * T - 1;
-  const int tl = 4 * threadIdx.x;
-  // x rows are software-pipelined: the next channel's samples are fetched into registers while the
-  // current channel is being computed, so the global-load latency is off the critical path
-  constexpr int XL = (AT + 12 + NT - 1) / NT;   // x samples per thread
-  float xnext[XL];
+  const int i0 = 2 * t0 - 7, imax = 2 * T - 1;
+  const int tl = 4 * lane;
+  float4 nf0 = make_float4(0.f, 0.f, 0.f, 0.f), nf1 = nf0;   // FAST prefetch registers
+  float ne[5] = {0.f, 0.f, 0.f, 0.f, 0.f};                     // edge prefetch registers
   auto fetch = [&](int c) {
-    const float* xr = p.x + ((int64_t)b * p.C + c) * T;
+    const float* xr = xb + (int64_t)c * T;
+    if (FAST) {
+      const float4* x4 = reinterpret_cast<const float4*>(xr + t0 - 8);
+      nf0 = __ldg(x4 + lane);
+      if (lane < 2) nf1 = __ldg(x4 + 32 + lane);
+    } else {
 #pragma unroll
-    for (int q = 0; q < XL; ++q) {
-      const int n = threadIdx.x + NT * q;
-      const int t = min(max(t0 - 5 + n, 0), T - 1);
-      xnext[q] = (n < AT + 12) ? __ldg(xr + t) : 0.f;
+      for (int q = 0; q < 5; ++q) {
+        const int m = lane + 32 * q;
+        const int t = min(max(t0 - 8 + m, 0), T - 1);
+        ne[q] = (m < SN_XS) ? __ldg(xr + t) : 0.f;
+      }
     }
   };
-  if (c8 * 8 < p.C) fetch(c8 * 8);
+  const int c_first = c8 * 8;
+  if (c_first < C) fetch(c_first);
 #pragma unroll 1
   for (int cg = 0; cg < 8; ++cg) {
-    const int c = c8 * 8 + cg;
-    if (c >= p.C) break;                       // block-uniform
-    float a = __ldg(p.alpha + c), bb = __ldg(p.beta + c);
-    if (p.logscale) {
-      a = expf(a);
-      bb = expf(bb);
+    const int c = c_first + cg;
+    if (c >= C) {
+      if (p.yimg != nullptr) tr[cg * 32 + lane] = make_uint2(0u, 0u);   // padding channels of the image
+      continue;
     }
-    const float invb = 1.0f / (bb + 1e-9f);
-    __syncthreads();                           // previous channel's reads of xs / vs are done
+    const float a = prm[cg][0], invb = prm[cg][1];
+    __syncwarp();
+    if (FAST) {
+      *reinterpret_cast<float4*>(xs + 4 * lane) = nf0;
+      if (lane < 2) *reinterpret_cast<float4*>(xs + 128 + 4 * lane) = nf1;
+    } else {
 #pragma unroll
-    for (int q = 0; q < XL; ++q) {
-      const int n = threadIdx.x + NT * q;
-      if (n < AT + 12) xs[n] = xnext[q];
+      for (int q = 0; q < 5; ++q) {
+        const int m = lane + 32 * q;
+        if (m < SN_XS) xs[m] = ne[q];
+      }
     }
-    __syncthreads();
-    if (cg + 1 < 8 && c + 1 < p.C) fetch(c + 1);
-    // ---- phase 1: groups of 4 consecutive 2x-rate samples (2*AT + 12 of them)
-    for (int j = threadIdx.x; j < (2 * AT + 12) / 4; j += NT) {
+    __syncwarp();
+    if (c + 1 < C && cg + 1 < 8) fetch(c + 1);
+    // phase 1: 256 samples of the 2x-rate signal = 64 groups of 4 (two rounds).  Group j holds
+    // v[i0 + 4j .. +3] = (u[2q+1], u[2q+2], u[2q+3], u[2q+4]), q = t0 - 4 + 2j, from xh[q-2 .. q+4] = xs[2j+2 .. 2j+8]
+#pragma unroll
+    for (int rnd = 0; rnd < 2; ++rnd) {
+      const int j = lane + 32 * rnd;
       const int n0 = 4 * j;
       float v0, v1, v2, v3;
-      if (i0 + n0 >= 0 && i0 + n0 + 3 <= imax) {
-        // i0 + n0 is odd: samples (odd, even, odd, even); the first two read xhat[t0-5+2j+m], the last two +1
+      if (FAST || (i0 + n0 >= 0 && i0 + n0 + 3 <= imax)) {
         float w[8];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          const float2 t2 = *reinterpret_cast<const float2*>(xs + 2 * j + 2 * q);
+          const float2 t2 = *reinterpret_cast<const float2*>(xs + 2 * j + 2 + 2 * q);
           w[2 * q] = t2.x;
           w[2 * q + 1] = t2.y;
         }
         float u0 = 0.f, u1 = 0.f, u2 = 0.f, u3 = 0.f;
 #pragma unroll
         for (int m = 0; m < 6; ++m) {
-          u0 = fmaf(fu[10 - 2 * m], w[m], u0);
-          u1 = fmaf(fu[11 - 2 * m], w[m], u1);
-          u2 = fmaf(fu[10 - 2 * m], w[m + 1], u2);
-          u3 = fmaf(fu[11 - 2 * m], w[m + 1], u3);
+          u0 = fmaf(fu2[10 - 2 * m], w[m], u0);
+          u1 = fmaf(fu2[11 - 2 * m], w[m], u1);
+          u2 = fmaf(fu2[10 - 2 * m], w[m + 1], u2);
+          u3 = fmaf(fu2[11 - 2 * m], w[m + 1], u3);
         }
-        v0 = snake_eval(2.0f * u0, a, invb);
-        v1 = snake_eval(2.0f * u1, a, invb);
-        v2 = snake_eval(2.0f * u2, a, invb);
-        v3 = snake_eval(2.0f * u3, a, invb);
+        v0 = snake_eval(u0, a, invb);
+        v1 = snake_eval(u1, a, invb);
+        v2 = snake_eval(u2, a, invb);
+        v3 = snake_eval(u3, a, invb);
       } else {
         float vv[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {      // sequence edges: replicate-clamped index, generic taps
+        for (int k = 0; k < 4; ++k) {      // sequence edges: replicate-clamped 2x-rate index, generic taps
           const int ic = min(max(i0 + n0 + k, 0), imax);
           const int q = ic >> 1, odd = ic & 1;
-          const float* xp = xs + (q - 3 + odd - (t0 - 5));
+          const int xi = min(max(q - 3 + odd - (t0 - 8), 0), SN_XS - 6);
+          const float* xp = xs + xi;
           float u = 0.f;
 #pragma unroll
-          for (int m = 0; m < 6; ++m) u = fmaf(odd ? fu[10 - 2 * m] : fu[11 - 2 * m], xp[m], u);
-          vv[k] = snake_eval(2.0f * u, a, invb);
+          for (int m = 0; m < 6; ++m) u = fmaf(odd ? fu2[10 - 2 * m] : fu2[11 - 2 * m], xp[m], u);
+          vv[k] = snake_eval(u, a, invb);
         }
         v0 = vv[0]; v1 = vv[1]; v2 = vv[2]; v3 = vv[3];
       }
       *reinterpret_cast<float4*>(vs + n0) = make_float4(v0, v1, v2, v3);
     }
-    __syncthreads();
-    // ---- phase 2: four consecutive outputs per thread: y[t] = sum_j fd[j] * vs[2*(t - t0) + j]
-    {
-      float w[20];
+    __syncwarp();
+    // phase 2: y[t0 + tl + k] = sum_j fd[j] vs[2*(tl + k) + j + 2]
+    if (lane < SN_WS / 4) {
+      float w[24];
 #pragma unroll
-      for (int q = 0; q < 5; ++q) {
+      for (int q = 0; q < 6; ++q) {
         const float4 t4 = *reinterpret_cast<const float4*>(vs + 2 * tl + 4 * q);
         w[4 * q] = t4.x; w[4 * q + 1] = t4.y; w[4 * q + 2] = t4.z; w[4 * q + 3] = t4.w;
       }
@@ -529,19 +544,12 @@ __global__ void __launch_bounds__(NT, MINB) activation1d_kernel(SnakeParams p) {
       for (int k = 0; k < 4; ++k) {
         float acc = 0.f;
 #pragma unroll
-        for (int j = 0; j < 12; ++j) acc = fmaf(fd[j], w[2 * k + j], acc);
+        for (int j = 0; j < 12; ++j) acc = fmaf(fd[j], w[2 * k + j + 2], acc);
         y[k] = acc;
       }
-      // out[k][cg] with a compile-time cg: unrolled select keeps the accumulators in registers
-#pragma unroll
-      for (int q = 0; q < 8; ++q)
-        if (q == cg) {
-#pragma unroll
-          for (int k = 0; k < 4; ++k) out[k][q] = y[k];
-        }
       if (p.y != nullptr) {
-        float* yr = p.y + ((int64_t)b * p.C + c) * T + t0 + tl;
-        if (t0 + tl + 3 < T && (T & 3) == 0) {
+        float* yr = p.y + ((int64_t)b * C + c) * T + t0 + tl;
+        if (FAST || (t0 + tl + 3 < T && (T & 3) == 0)) {
           *reinterpret_cast<float4*>(yr) = make_float4(y[0], y[1], y[2], y[3]);
         } else {
 #pragma unroll
@@ -549,190 +557,62 @@ __global__ void __launch_bounds__(NT, MINB) activation1d_kernel(SnakeParams p) {
             if (t0 + tl + k < T) yr[k] = y[k];
         }
       }
+      if (p.yimg != nullptr) tr[cg * 32 + lane] = make_uint2(cvt_pair<BF16>(y[0], y[1]), cvt_pair<BF16>(y[2], y[3]));
     }
   }
-  if (p.yimg != nullptr) {
-    const int c8n = (int)gridDim.y;
-    uint16_t* yi = p.yimg + ((size_t)b * c8n + c8) * (size_t)T * 8;
+  // operand image: 8 channels = 16 B per time step; every lane re-reads its own 4 rows x 8 channels
+  if (p.yimg != nullptr && lane < SN_WS / 4) {
+    uint2 h[8];
+#pragma unroll
+    for (int cg = 0; cg < 8; ++cg) h[cg] = tr[cg * 32 + lane];
+    uint16_t* yi = p.yimg + (((size_t)b * gridDim.y + c8) * (size_t)T + t0 + tl) * 8;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      const int t = t0 + tl + k;
-      if (t < T) {
-        uint4 q;
-        if (p.bf16) {
-          asm("cvt.rn.satfinite.bf16x2.f32 %0, %1, %2;" : "=r"(q.x) : "f"(out[k][1]), "f"(out[k][0]));
-          asm("cvt.rn.satfinite.bf16x2.f32 %0, %1, %2;" : "=r"(q.y) : "f"(out[k][3]), "f"(out[k][2]));
-          asm("cvt.rn.satfinite.bf16x2.f32 %0, %1, %2;" : "=r"(q.z) : "f"(out[k][5]), "f"(out[k][4]));
-          asm("cvt.rn.satfinite.bf16x2.f32 %0, %1, %2;" : "=r"(q.w) : "f"(out[k][7]), "f"(out[k][6]));
-        } else {
-          asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(q.x) : "f"(out[k][1]), "f"(out[k][0]));
-          asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(q.y) : "f"(out[k][3]), "f"(out[k][2]));
-          asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(q.z) : "f"(out[k][5]), "f"(out[k][4]));
-          asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(q.w) : "f"(out[k][7]), "f"(out[k][6]));
-        }
-        *reinterpret_cast<uint4*>(yi + (size_t)t * 8) = q;
+      uint4 q;
+      const uint32_t sel = (k & 1) ? 0x7632u : 0x5410u;
+      if (k < 2) {
+        q.x = __byte_perm(h[0].x, h[1].x, sel); q.y = __byte_perm(h[2].x, h[3].x, sel);
+        q.z = __byte_perm(h[4].x, h[5].x, sel); q.w = __byte_perm(h[6].x, h[7].x, sel);
+      } else {
+        q.x = __byte_perm(h[0].y, h[1].y, sel); q.y = __byte_perm(h[2].y, h[3].y, sel);
+        q.z = __byte_perm(h[4].y, h[5].y, sel); q.w = __byte_perm(h[6].y, h[7].y, sel);
       }
+      if (FAST || t0 + tl + k < T) *reinterpret_cast<uint4*>(yi + (size_t)k * 8) = q;
     }
   }
 }
-}  // namespace
 
-// Warp-autonomous variant: every warp owns 120 consecutive outputs (30 lanes x 4) of the CTA's 960-sample
-// tile for all 8 channels of the group and keeps its own x / v windows in shared memory, so the only
-// synchronisation is __syncwarp and warps hide each other's latencies freely.
-namespace {
-constexpr int WS = 120;                 // outputs per warp
-constexpr int WT = 8 * WS;              // outputs per CTA tile
+template <int BF16>
 __global__ void __launch_bounds__(NT, 3) activation1d_warp_kernel(SnakeParams p) {
-  __shared__ __align__(16) float xs_all[8][WS + 16];        // xs[n] = xhat[t0 - 5 + n], n < WS + 11
-  __shared__ __align__(16) float vs_all[8][2 * WS + 16];    // vs[n] = v[clamp(2*t0 - 5 + n)], n < 2*WS + 12
+  __shared__ __align__(16) float win_all[8][SN_XS + SN_VS + SN_TR];
+  __shared__ float prm[8][2];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float* xs = xs_all[warp];
-  float* vs = vs_all[warp];
-  const int t0 = blockIdx.x * WT + warp * WS, c8 = blockIdx.y, b = blockIdx.z;
+  const int t0 = blockIdx.x * WT + warp * SN_WS, c8 = blockIdx.y, b = blockIdx.z;
   const int T = p.T;
-  float fu[12], fd[12];
-#pragma unroll
-  for (int j = 0; j < 12; ++j) {
-    fu[j] = __ldg(p.f_up + j);
-    fd[j] = __ldg(p.f_down + j);
+  if (threadIdx.x < 8) {
+    const int c = c8 * 8 + threadIdx.x;
+    float a = 0.f, bb = 1.f;
+    if (c < p.C) {
+      a = __ldg(p.alpha + c);
+      bb = __ldg(p.beta + c);
+      if (p.logscale) {
+        a = expf(a);
+        bb = expf(bb);
+      }
+    }
+    prm[threadIdx.x][0] = a;
+    prm[threadIdx.x][1] = 1.0f / (bb + 1e-9f);
   }
-  float out[4][8];
-#pragma unroll
-  for (int k = 0; k < 4; ++k)
-#pragma unroll
-    for (int cg = 0; cg < 8; ++cg) out[k][cg] = 0.f;
-  const int i0 = 2 * t0 - 5;
-  const int imax = 2 * T - 1;
-  const int tl = 4 * lane;                       // lanes 0..29 produce outputs
-  const bool active = t0 < T;                    // warp-uniform
-  constexpr int XL = 5;                          // ceil((WS + 11) / 32)
-  float xnext[XL];
-  auto fetch = [&](int c) {
-    const float* xr = p.x + ((int64_t)b * p.C + c) * T;
-#pragma unroll
-    for (int q = 0; q < XL; ++q) {
-      const int n = lane + 32 * q;
-      const int t = min(max(t0 - 5 + n, 0), T - 1);
-      xnext[q] = (n < WS + 11) ? __ldg(xr + t) : 0.f;
-    }
-  };
-  if (active && c8 * 8 < p.C) fetch(c8 * 8);
-#pragma unroll 1
-  for (int cg = 0; cg < 8; ++cg) {
-    const int c = c8 * 8 + cg;
-    if (c >= p.C || !active) break;
-    float a = __ldg(p.alpha + c), bb = __ldg(p.beta + c);
-    if (p.logscale) {
-      a = expf(a);
-      bb = expf(bb);
-    }
-    const float invb = 1.0f / (bb + 1e-9f);
-    __syncwarp();
-#pragma unroll
-    for (int q = 0; q < XL; ++q) {
-      const int n = lane + 32 * q;
-      if (n < WS + 11) xs[n] = xnext[q];
-    }
-    __syncwarp();
-    if (cg + 1 < 8 && c + 1 < p.C) fetch(c + 1);
-    // phase 1: 2*WS + 12 = 252 samples = 63 groups of 4
-    for (int j = lane; j < (2 * WS + 12) / 4; j += 32) {
-      const int n0 = 4 * j;
-      float v0, v1, v2, v3;
-      if (i0 + n0 >= 0 && i0 + n0 + 3 <= imax) {
-        float w[8];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const float2 t2 = *reinterpret_cast<const float2*>(xs + 2 * j + 2 * q);
-          w[2 * q] = t2.x;
-          w[2 * q + 1] = t2.y;
-        }
-        float u0 = 0.f, u1 = 0.f, u2 = 0.f, u3 = 0.f;
-#pragma unroll
-        for (int m = 0; m < 6; ++m) {
-          u0 = fmaf(fu[10 - 2 * m], w[m], u0);
-          u1 = fmaf(fu[11 - 2 * m], w[m], u1);
-          u2 = fmaf(fu[10 - 2 * m], w[m + 1], u2);
-          u3 = fmaf(fu[11 - 2 * m], w[m + 1], u3);
-        }
-        v0 = snake_eval(2.0f * u0, a, invb);
-        v1 = snake_eval(2.0f * u1, a, invb);
-        v2 = snake_eval(2.0f * u2, a, invb);
-        v3 = snake_eval(2.0f * u3, a, invb);
-      } else {
-        float vv[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int ic = min(max(i0 + n0 + k, 0), imax);
-          const int q = ic >> 1, odd = ic & 1;
-          const float* xp = xs + (q - 3 + odd - (t0 - 5));
-          float u = 0.f;
-#pragma unroll
-          for (int m = 0; m < 6; ++m) u = fmaf(odd ? fu[10 - 2 * m] : fu[11 - 2 * m], xp[m], u);
-          vv[k] = snake_eval(2.0f * u, a, invb);
-        }
-        v0 = vv[0]; v1 = vv[1]; v2 = vv[2]; v3 = vv[3];
-      }
-      *reinterpret_cast<float4*>(vs + n0) = make_float4(v0, v1, v2, v3);
-    }
-    __syncwarp();
-    if (lane < WS / 4) {
-      float w[20];
-#pragma unroll
-      for (int q = 0; q < 5; ++q) {
-        const float4 t4 = *reinterpret_cast<const float4*>(vs + 2 * tl + 4 * q);
-        w[4 * q] = t4.x; w[4 * q + 1] = t4.y; w[4 * q + 2] = t4.z; w[4 * q + 3] = t4.w;
-      }
-      float y[4];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        float acc = 0.f;
-#pragma unroll
-        for (int j = 0; j < 12; ++j) acc = fmaf(fd[j], w[2 * k + j], acc);
-        y[k] = acc;
-      }
-#pragma unroll
-      for (int q = 0; q < 8; ++q)
-        if (q == cg) {
-#pragma unroll
-          for (int k = 0; k < 4; ++k) out[k][q] = y[k];
-        }
-      if (p.y != nullptr) {
-        float* yr = p.y + ((int64_t)b * p.C + c) * T + t0 + tl;
-        if (t0 + tl + 3 < T && (T & 3) == 0) {
-          *reinterpret_cast<float4*>(yr) = make_float4(y[0], y[1], y[2], y[3]);
-        } else {
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            if (t0 + tl + k < T) yr[k] = y[k];
-        }
-      }
-    }
-  }
-  if (p.yimg != nullptr && active && lane < WS / 4) {
-    const int c8n = (int)gridDim.y;
-    uint16_t* yi = p.yimg + ((size_t)b * c8n + c8) * (size_t)T * 8;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int t = t0 + tl + k;
-      if (t < T) {
-        uint4 q;
-        if (p.bf16) {
-          asm("cvt.rn.satfinite.bf16x2.f32 %0, %1, %2;" : "=r"(q.x) : "f"(out[k][1]), "f"(out[k][0]));
-          asm("cvt.rn.satfinite.bf16x2.f32 %0, %1, %2;" : "=r"(q.y) : "f"(out[k][3]), "f"(out[k][2]));
-          asm("cvt.rn.satfinite.bf16x2.f32 %0, %1, %2;" : "=r"(q.z) : "f"(out[k][5]), "f"(out[k][4]));
-          asm("cvt.rn.satfinite.bf16x2.f32 %0, %1, %2;" : "=r"(q.w) : "f"(out[k][7]), "f"(out[k][6]));
-        } else {
-          asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(q.x) : "f"(out[k][1]), "f"(out[k][0]));
-          asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(q.y) : "f"(out[k][3]), "f"(out[k][2]));
-          asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(q.z) : "f"(out[k][5]), "f"(out[k][4]));
-          asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(q.w) : "f"(out[k][7]), "f"(out[k][6]));
-        }
-        *reinterpret_cast<uint4*>(yi + (size_t)t * 8) = q;
-      }
-    }
-  }
+  __syncthreads();
+  if (t0 >= T) return;                           // warp-uniform; no block barriers below
+  float* xs = win_all[warp];
+  float* vs = xs + SN_XS;
+  uint2* tr = reinterpret_cast<uint2*>(vs + SN_VS);
+  const float* xb = p.x + (int64_t)b * p.C * T;
+  const bool fast = t0 >= 8 && t0 + 128 <= T && (T & 3) == 0 && (reinterpret_cast<uintptr_t>(p.x) & 15) == 0 &&
+                    (p.y == nullptr || (reinterpret_cast<uintptr_t>(p.y) & 15) == 0);
+  if (fast) snake_segment<true, BF16>(p, xb, c8, b, t0, prm, xs, vs, tr, lane);
+  else snake_segment<false, BF16>(p, xb, c8, b, t0, prm, xs, vs, tr, lane);
 }
 }  // namespace
 
@@ -742,18 +622,10 @@ int launch_activation1d(const SnakeParams& p, cudaStream_t s) {
   if (p.y == nullptr && p.yimg == nullptr) return fail(AB_ERR_ARG, "activation1d: no output requested");
   // channel groups: the operand image covers ceil16(C) channels (padding groups are written as zeros)
   const int c8n = p.yimg ? (int)(ceil_div(p.C, 16) * 2) : (int)ceil_div(p.C, 8);
-  static const int warp_variant = [] { const char* e = getenv("AB_SNAKE_WARP"); return e ? atoi(e) : 1; }();   // default: warp-autonomous (13 % faster)
-  if (warp_variant) {
-    dim3 gridw((unsigned)ceil_div(p.T, WT), (unsigned)c8n, (unsigned)p.B);
-    activation1d_warp_kernel<<<gridw, NT, 0, s>>>(p);
-    AB_LAUNCH_CHECK("activation1d_warp_kernel");
-    return AB_OK;
-  }
-  dim3 grid((unsigned)ceil_div(p.T, AT), (unsigned)c8n, (unsigned)p.B);
-  static const int occ = [] { const char* e = getenv("AB_SNAKE_OCC"); return e ? atoi(e) : 3; }();
-  if (occ >= 4) activation1d_kernel<4><<<grid, NT, 0, s>>>(p);
-  else activation1d_kernel<3><<<grid, NT, 0, s>>>(p);
-  AB_LAUNCH_CHECK("activation1d_kernel");
+  dim3 grid((unsigned)ceil_div(p.T, WT), (unsigned)c8n, (unsigned)p.B);
+  if (p.bf16) activation1d_warp_kernel<1><<<grid, NT, 0, s>>>(p);
+  else activation1d_warp_kernel<0><<<grid, NT, 0, s>>>(p);
+  AB_LAUNCH_CHECK("activation1d_warp_kernel");
   return AB_OK;
 }
 
