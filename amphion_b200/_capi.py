@@ -10,7 +10,7 @@ AB_MAX_STAGES = 8
 AB_MAX_KERNELS = 8
 AB_MAX_DILATIONS = 8
 
-GEN_HIFIGAN, GEN_BIGVGAN = 0, 1
+GEN_HIFIGAN, GEN_BIGVGAN, GEN_NSFHIFIGAN = 0, 1, 2
 ACT_LRELU, ACT_SNAKE, ACT_SNAKEBETA = 0, 1, 2
 PRECISIONS = {"fp32": 0, "tc_f16": 1, "tc_bf16": 2}
 

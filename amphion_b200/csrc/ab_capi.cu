@@ -54,6 +54,7 @@ struct Slot {
   int stride;         // ConvTranspose1d stride (SLOT_CONVT_W)
   int dilation;       // Conv1d dilation (SLOT_CONV_W)
   int tc_kind;        // 0 none, 1 tc_conv image (square, C <= 256), 2 gemmconv image, 3 streaming gemmconv image
+  float gain = 1.0f;  // applied to the fp32 image at load time (NSF-HiFiGAN: 2 on every ups weight / bias)
 };
 
 struct ConvRef {   // one weight-normed conv of the model
@@ -169,7 +170,8 @@ ActRef make_act(ab_generator* g, const std::string& prefix, int ch, bool has_bet
 }
 
 int validate_config(const ab_generator_config& c) {
-  if (c.kind != AB_GEN_HIFIGAN && c.kind != AB_GEN_BIGVGAN) return fail(AB_ERR_ARG, "config: unknown generator kind %d", c.kind);
+  if (c.kind != AB_GEN_HIFIGAN && c.kind != AB_GEN_BIGVGAN && c.kind != AB_GEN_NSFHIFIGAN)
+    return fail(AB_ERR_ARG, "config: unknown generator kind %d", c.kind);
   if (c.n_mel <= 0 || c.upsample_initial_channel <= 0) return fail(AB_ERR_ARG, "config: n_mel / upsample_initial_channel must be positive");
   if (c.num_upsamples <= 0 || c.num_upsamples > AB_MAX_STAGES) return fail(AB_ERR_ARG, "config: num_upsamples %d out of range", c.num_upsamples);
   if (c.num_kernels <= 0 || c.num_kernels > AB_MAX_KERNELS) return fail(AB_ERR_ARG, "config: num_kernels %d out of range", c.num_kernels);
@@ -188,6 +190,16 @@ int validate_config(const ab_generator_config& c) {
   }
   if (c.kind == AB_GEN_BIGVGAN && c.activation != AB_ACT_SNAKE && c.activation != AB_ACT_SNAKEBETA)
     return fail(AB_ERR_ARG, "config: BigVGAN activation must be snake or snakebeta");
+  if (c.kind == AB_GEN_NSFHIFIGAN) {
+    // noise_convs[i]: Conv1d(1, C, 2s, stride s, padding s/2) with s = prod(rates[i+1:]) (nsfhifigan.py:223-236);
+    // for odd s > 1 its output is one sample short and the reference truncates the stage (:264-266)
+    for (int i = 0; i + 1 < c.num_upsamples; ++i) {
+      int64_t sf = 1;
+      for (int j = i + 1; j < c.num_upsamples; ++j) sf *= c.upsample_rates[j];
+      if (sf > 1 && (sf & 1))
+        return fail(AB_ERR_UNSUPPORTED, "config: NSF-HiFiGAN stage %d: odd source stride %lld truncates the stage", i, (long long)sf);
+    }
+  }
   return AB_OK;
 }
 
@@ -228,6 +240,7 @@ int ab_generator_create(const ab_generator_config* cfg, ab_generator** out) {
     const std::string upname = "ups." + std::to_string(i) + (big ? ".0" : "");
     st.up = make_conv(g, upname, cin, ch, cfg->upsample_kernel_sizes[i], 1, true);
     g->slots[st.up.w].stride = st.u;
+    if (cfg->kind == AB_GEN_NSFHIFIGAN) g->slots[st.up.w].gain = g->slots[st.up.b].gain = 2.0f;   // x = x + x (:269-271)
     for (int j = 0; j < cfg->num_kernels; ++j) {
       BlockRef blk;
       blk.k = cfg->resblock_kernel_sizes[j];
@@ -331,6 +344,10 @@ static int load_common(ab_generator* g, const char* name, const float* dev_g, co
   } else {
     int rc = launch_repack_weight(dev_v, dev_g, dst, (int)s.shape[0], (int)s.shape[1], (int)s.shape[2],
                                   s.kind == SLOT_CONVT_W ? 1 : 0, st);
+    if (rc != AB_OK) return rc;
+  }
+  if (s.gain != 1.0f) {
+    int rc = launch_scale_inplace(dst, s.bytes / sizeof(float), s.gain, st);
     if (rc != AB_OK) return rc;
   }
   s.loaded = true;

@@ -80,4 +80,6 @@ int launch_activation1d(const SnakeParams& p, cudaStream_t s);
 int launch_repack_weight(const float* v, const float* g, float* dst, int d0, int d1, int k,
                          int transposed, cudaStream_t s);
 
+int launch_scale_inplace(float* p, size_t n, float gain, cudaStream_t s);
+
 }  // namespace ab

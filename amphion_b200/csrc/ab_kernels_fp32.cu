@@ -4,6 +4,8 @@
 // Amphion reference root).
 #include <stdlib.h>
 
+#include <algorithm>
+
 #include "ab_common.cuh"
 
 namespace ab {
@@ -679,6 +681,20 @@ int launch_repack_weight(const float* v, const float* g, float* dst, int d0, int
   if (d0 <= 0 || d1 <= 0 || k <= 0) return fail(AB_ERR_ARG, "repack_weight: bad shape");
   repack_weight_kernel<<<d0, 256, 0, s>>>(v, g, dst, d0, d1, k, transposed);
   AB_LAUNCH_CHECK("repack_weight_kernel");
+  return AB_OK;
+}
+
+namespace {
+__global__ void scale_inplace_kernel(float* p, size_t n, float gain) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] *= gain;
+}
+}  // namespace
+
+int launch_scale_inplace(float* p, size_t n, float gain, cudaStream_t s) {
+  if (n == 0) return AB_OK;
+  const int blocks = (int)std::min<size_t>((n + 255) / 256, 148 * 8);
+  scale_inplace_kernel<<<blocks, 256, 0, s>>>(p, n, gain);
+  AB_LAUNCH_CHECK("scale_inplace_kernel");
   return AB_OK;
 }
 

@@ -1,4 +1,4 @@
-"""Batching helpers with the reference's signatures (utils/util.py:114-182)."""
+"""Batching helpers with the reference's signatures (utils/util.py:61-182)."""
 from __future__ import annotations
 
 import torch
@@ -26,3 +26,21 @@ def pad_mels_to_tensors(mels, batched=None):
         tensors.append(t)
         mel_frames.append(frames)
     return tensors, mel_frames
+
+
+def pad_f0_to_tensors(f0s, batched=None):
+    """Zero-pad a list of 1-D f0 tracks ``[T_i]`` into ``[b, T_max]`` batches of ``batched``
+    utterances (``None`` = one batch) — utils/util.py:61-111; the batches stay on the device of
+    the inputs (the reference builds CPU tensors)."""
+    tensors = []
+    if len(f0s) == 0:
+        return tensors
+    step = len(f0s) if batched is None else int(batched)
+    for start in range(0, len(f0s), step):
+        group = f0s[start:start + step]
+        size = max(int(f.shape[-1]) for f in group)
+        t = torch.zeros(len(group), size, dtype=torch.float32, device=group[0].device)
+        for i, f in enumerate(group):
+            t[i, : f.shape[-1]] = f
+        tensors.append(t)
+    return tensors

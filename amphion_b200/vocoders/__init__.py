@@ -2,12 +2,13 @@
 (models/vocoders/vocoder_inference.py:39-75)."""
 from .bigvgan import BigVGAN
 from .hifigan import HiFiGAN
+from .nsfhifigan import NSFHiFiGAN
 from .gan_vocoder_inference import synthesis_audios, vocoder_inference
 
 # same shape as the reference's registries: generator name -> class / functions
-_vocoders = {"hifigan": HiFiGAN, "bigvgan": BigVGAN}
-_vocoder_forward_funcs = {"hifigan": vocoder_inference, "bigvgan": vocoder_inference}
-_vocoder_infer_funcs = {"hifigan": synthesis_audios, "bigvgan": synthesis_audios}
+_vocoders = {"hifigan": HiFiGAN, "bigvgan": BigVGAN, "nsfhifigan": NSFHiFiGAN}
+_vocoder_forward_funcs = {"hifigan": vocoder_inference, "bigvgan": vocoder_inference, "nsfhifigan": vocoder_inference}
+_vocoder_infer_funcs = {"hifigan": synthesis_audios, "bigvgan": synthesis_audios, "nsfhifigan": synthesis_audios}
 
-__all__ = ["HiFiGAN", "BigVGAN", "vocoder_inference", "synthesis_audios", "_vocoders",
+__all__ = ["HiFiGAN", "BigVGAN", "NSFHiFiGAN", "vocoder_inference", "synthesis_audios", "_vocoders",
            "_vocoder_forward_funcs", "_vocoder_infer_funcs"]

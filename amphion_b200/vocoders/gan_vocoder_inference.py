@@ -5,15 +5,13 @@ from __future__ import annotations
 
 import torch
 
-from ..util import pad_mels_to_tensors
+from ..util import pad_f0_to_tensors, pad_mels_to_tensors
 
 
 def vocoder_inference(cfg, model, mels, f0s=None, device=None, fast_inference=False):
     """mels [B, n_mel, T] (any device / strides) -> audios [B, T*hop] on the CPU,
     detached fp32 — the reference's output contract (:38).  ``fast_inference``
     is accepted and ignored, as in the reference."""
-    if f0s is not None:
-        raise NotImplementedError("amphion_b200: f0-conditioned generators (NSF-HiFiGAN) are not on this path yet")
     if getattr(cfg.preprocess, "extract_amplitude_phase", False):
         raise NotImplementedError("amphion_b200: amplitude/phase generators (APNet) are not on this path yet")
     model.eval()
@@ -21,7 +19,11 @@ def vocoder_inference(cfg, model, mels, f0s=None, device=None, fast_inference=Fa
         if device is None:
             device = next(model.parameters()).device
         mels = mels.to(device, non_blocking=True)
-        output = model.forward(mels).squeeze(1).detach()
+        if f0s is None:
+            output = model.forward(mels)
+        else:  # f0-conditioned generators (NSF-HiFiGAN), :36
+            output = model.forward(mels, f0s.to(device, non_blocking=True))
+        output = output.squeeze(1).detach()
         # the reference's `.cpu()` (:38) lands in pageable memory; a pinned buffer is
         # still a CPU tensor and lets the D2H copy run at full PCIe rate
         host = torch.empty(output.shape, dtype=output.dtype, pin_memory=True)
@@ -36,14 +38,14 @@ def synthesis_audios(cfg, model, mels, f0s=None, batch_size=None, fast_inference
     utterance alone (B=1) on its zero-padded mel (:59-75); the generator has no
     cross-batch op, so running the padded batch in ONE forward gives the same
     samples with one launch sequence and one D2H copy per batch."""
-    if f0s is not None:
-        raise NotImplementedError("amphion_b200: f0-conditioned generators are not on this path yet")
     device = next(model.parameters()).device
     hop = model.cfg.preprocess.hop_size
     audios = []
     mel_batches, mel_frames = pad_mels_to_tensors([m.to(device) for m in mels], batch_size)
-    for mel_batch, mel_frame in zip(mel_batches, mel_frames):
-        out = vocoder_inference(cfg, model, mel_batch, device=device, fast_inference=fast_inference)
+    # f0 tracks are padded per batch exactly like the mels (:55-56, :76-95)
+    f0_batches = pad_f0_to_tensors([f.to(device) for f in f0s], batch_size) if f0s is not None else [None] * len(mel_batches)
+    for mel_batch, mel_frame, f0_batch in zip(mel_batches, mel_frames, f0_batches):
+        out = vocoder_inference(cfg, model, mel_batch, f0s=f0_batch, device=device, fast_inference=fast_inference)
         for i in range(mel_batch.shape[0]):
             audios.append(out[i, : int(mel_frame[i]) * hop].clone())
     return audios

@@ -71,7 +71,7 @@ class ConvBlock(nn.Module):
 class NativeGenerator(nn.Module):
     """Base class: owns the C-ABI handle, the packed-parameter arena and the workspace."""
 
-    kind = None       # "hifigan" | "bigvgan"
+    kind = None       # "hifigan" | "bigvgan" | "nsfhifigan"
     hp_key = None     # cfg.model.<hp_key>
 
     def __init__(self):
@@ -90,7 +90,7 @@ class NativeGenerator(nn.Module):
     def _c_config(self):
         hp = self._hp()
         c = _capi.GeneratorConfig()
-        c.kind = _capi.GEN_HIFIGAN if self.kind == "hifigan" else _capi.GEN_BIGVGAN
+        c.kind = {"hifigan": _capi.GEN_HIFIGAN, "bigvgan": _capi.GEN_BIGVGAN, "nsfhifigan": _capi.GEN_NSFHIFIGAN}[self.kind]
         c.n_mel = int(self.cfg.preprocess.n_mel)
         c.upsample_initial_channel = int(hp.upsample_initial_channel)
         rates, ksz = list(hp.upsample_rates), list(hp.upsample_kernel_sizes)

@@ -39,7 +39,13 @@ extern "C" {
 #define AB_MAX_KERNELS 8
 #define AB_MAX_DILATIONS 8
 
-enum ab_generator_kind { AB_GEN_HIFIGAN = 0, AB_GEN_BIGVGAN = 1 };
+/* AB_GEN_NSFHIFIGAN: NSFHiFiGAN.forward (models/vocoders/gan/generator/nsfhifigan.py:262-283).  As written in the
+ * reference the harmonic source never reaches the output: `x_source = x[:, :, :length]` (:269) overwrites the
+ * noise-conv result, so every stage computes x = ups(x) + ups(x).  The native path reproduces exactly that: the
+ * HiFi-GAN pipeline with the transposed-conv weights and biases doubled at load time (exact, power of two); the
+ * tensor list is HiFi-GAN's (m_source.* / noise_convs.* do not influence the samples).  Configurations whose
+ * noise conv would come out shorter than the stage (odd product of the later upsample rates, :264-266) are refused. */
+enum ab_generator_kind { AB_GEN_HIFIGAN = 0, AB_GEN_BIGVGAN = 1, AB_GEN_NSFHIFIGAN = 2 };
 enum ab_activation { AB_ACT_LRELU = 0, AB_ACT_SNAKE = 1, AB_ACT_SNAKEBETA = 2 };
 /* arithmetic of the k-tap channel-mixing convolutions */
 enum ab_precision {
@@ -54,8 +60,9 @@ int ab_version(void);
 int ab_device_is_sm100(void);
 
 /* ------------------------------------------------------------------------
- * Generator: HiFiGAN.forward  (models/vocoders/gan/generator/hifigan.py:203-219)
- *            BigVGAN.forward  (models/vocoders/gan/generator/bigvgan.py:313-331)
+ * Generator: HiFiGAN.forward     (models/vocoders/gan/generator/hifigan.py:203-219)
+ *            BigVGAN.forward     (models/vocoders/gan/generator/bigvgan.py:313-331)
+ *            NSFHiFiGAN.forward  (models/vocoders/gan/generator/nsfhifigan.py:262-283)
  * The config mirrors cfg.model.{hifigan,bigvgan}.* + cfg.preprocess.n_mel
  * (hifigan.py:151-201, bigvgan.py:232-311).
  * ---------------------------------------------------------------------- */

@@ -318,7 +318,49 @@ def bigvgan_forward(params, hp, mel, return_stages=False):
     return (out, stages) if return_stages else out
 
 
-def generator_forward(kind, params, hp, mel, return_stages=False):
+def nsfhifigan_forward(params, hp, mel, f0, return_stages=False):
+    """nsfhifigan.py:262-283.  ``har_source`` (:263) is [B, 1, T_f0 * upp]; ``noise_convs[i]`` (:223-236) maps it
+    to length floor((L + 2*(s//2) - 2s) / s) + 1 with s = prod(rates[i+1:]) (kernel 1 for the last stage), and
+    its VALUES are dropped by ``x_source = x[:, :, :length]`` (:269) — so only that length is restated here
+    (the source itself draws torch.rand / torch.randn, sine_excitation.py:42,84, and cannot be a fixture)."""
+    x = _t(np.asarray(mel, np.float32)) if not isinstance(mel, torch.Tensor) else mel.float()
+    rates = [int(u) for u in hp["upsample_rates"]]
+    upp = int(np.prod(rates))
+    src_len = int(np.asarray(f0).shape[1]) * upp
+    stages = []
+    with torch.no_grad():
+        x = conv1d(x, get_weight(params, "conv_pre"), _bias(params, "conv_pre"), padding=3)
+        nk = len(hp["resblock_kernel_sizes"])
+        for i, (u, k) in enumerate(zip(rates, hp["upsample_kernel_sizes"])):
+            x = F.leaky_relu(x, LRELU_SLOPE)
+            x = conv_transpose1d(x, get_weight(params, f"ups.{i}"), _bias(params, f"ups.{i}"),
+                                 stride=u, padding=(k - u) // 2)
+            if i + 1 < len(rates):
+                s = int(np.prod(rates[i + 1:]))
+                x_source_len = (src_len + 2 * (s // 2) - 2 * s) // s + 1
+            else:
+                x_source_len = src_len
+            length = min(x.shape[-1], x_source_len)
+            x = x[:, :, :length]
+            x_source = x[:, :, :length]          # sic (:269)
+            x = x + x_source
+            xs = None
+            for j in range(nk):
+                r = resblock1(params, f"resblocks.{i * nk + j}", x, hp["resblock_kernel_sizes"][j],
+                              hp["resblock_dilation_sizes"][j])
+                xs = r if xs is None else xs + r
+            x = xs / nk
+            stages.append(x.numpy().copy())
+        x = F.leaky_relu(x)
+        x = conv1d(x, get_weight(params, "conv_post"), _bias(params, "conv_post"), padding=3)
+        x = torch.tanh(x)
+    out = x.numpy()
+    return (out, stages) if return_stages else out
+
+
+def generator_forward(kind, params, hp, mel, return_stages=False, f0=None):
+    if kind == "nsfhifigan":
+        return nsfhifigan_forward(params, hp, mel, f0, return_stages)
     fn = hifigan_forward if kind == "hifigan" else bigvgan_forward
     return fn(params, hp, mel, return_stages)
 
@@ -326,9 +368,9 @@ def generator_forward(kind, params, hp, mel, return_stages=False):
 # --------------------------------------------------------------------------
 # plumbing above the generator
 # --------------------------------------------------------------------------
-def vocoder_inference(kind, params, hp, mels):
+def vocoder_inference(kind, params, hp, mels, f0s=None):
     """models/vocoders/gan/gan_vocoder_inference.py:11-38 -> [B, T*hop]."""
-    return generator_forward(kind, params, hp, mels)[:, 0, :]
+    return generator_forward(kind, params, hp, mels, f0=f0s)[:, 0, :]
 
 
 def pad_mels(mels, batched=None):
@@ -348,13 +390,28 @@ def pad_mels(mels, batched=None):
     return tensors, frames
 
 
-def synthesis_audios(kind, params, hp, mels, hop_size, batch_size=None):
-    """gan_vocoder_inference.py:41-75: per-utterance B=1 forward on the
-    zero-padded mel, trimmed to frames*hop."""
+def pad_f0s(f0s, batched=None):
+    """utils/util.py:61-111: zero-pad a list of [T_i] f0 tracks into [b, Tmax] batches."""
+    groups = [f0s] if batched is None else [f0s[s:s + batched] for s in range(0, len(f0s), batched)]
+    tensors = []
+    for g in groups:
+        if not g:
+            continue
+        t = np.zeros((len(g), max(f.shape[-1] for f in g)), np.float32)
+        for i, f in enumerate(g):
+            t[i, :f.shape[-1]] = f
+        tensors.append(t)
+    return tensors
+
+
+def synthesis_audios(kind, params, hp, mels, hop_size, batch_size=None, f0s=None):
+    """gan_vocoder_inference.py:41-96: per-utterance B=1 forward on the
+    zero-padded mel (and f0), trimmed to frames*hop."""
     out = []
     batches, frames = pad_mels(mels, batch_size)
-    for mb, fr in zip(batches, frames):
+    f0_batches = pad_f0s(f0s, batch_size) if f0s is not None else [None] * len(batches)
+    for mb, fr, fb in zip(batches, frames, f0_batches):
         for i in range(mb.shape[0]):
-            a = vocoder_inference(kind, params, hp, mb[i:i + 1])[0]
+            a = vocoder_inference(kind, params, hp, mb[i:i + 1], None if fb is None else fb[i:i + 1])[0]
             out.append(a[: int(fr[i]) * hop_size])
     return out

@@ -50,6 +50,12 @@ GOLDEN_MODELS = {
 }
 
 
+# NSF-HiFiGAN fixture (needs f0 and cfg.preprocess.sample_rate; no per-stage hooks) — tests/golden/gen_golden.py:gen_nsfhifigan
+GOLDEN_NSF = ("nsfhifigan", dict(resblock="1", harmonic_num=8, upsample_rates=[4, 2, 2], upsample_kernel_sizes=[8, 4, 4],
+                                 upsample_initial_channel=64, resblock_kernel_sizes=[3, 7, 11],
+                                 resblock_dilation_sizes=[[1, 3, 5]] * 3), 20)
+
+
 @pytest.fixture(scope="session")
 def golden_models():
     return GOLDEN_MODELS

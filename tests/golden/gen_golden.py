@@ -66,6 +66,7 @@ warnings.filterwarnings("ignore")
 
 from models.vocoders.gan.generator.hifigan import HiFiGAN  # noqa: E402
 from models.vocoders.gan.generator.bigvgan import BigVGAN  # noqa: E402
+from models.vocoders.gan.generator.nsfhifigan import NSFHiFiGAN  # noqa: E402
 from modules.anti_aliasing.act import Activation1d  # noqa: E402
 from modules.activation_functions.snake import SnakeBeta  # noqa: E402
 import utils.mel as rmel  # noqa: E402
@@ -135,6 +136,45 @@ HP_BIGVGAN_RB2 = dict(resblock="2", upsample_rates=[2, 2], upsample_kernel_sizes
                       resblock_dilation_sizes=[[1, 2], [2, 6]], activation="snake", snake_logscale=False)
 
 
+HP_NSF = dict(resblock="1", harmonic_num=8, upsample_rates=[4, 2, 2], upsample_kernel_sizes=[8, 4, 4],
+              upsample_initial_channel=64, resblock_kernel_sizes=[3, 7, 11], resblock_dilation_sizes=[[1, 3, 5]] * 3)
+
+
+def gen_nsfhifigan():
+    """NSF-HiFiGAN (nsfhifigan.py:181-283).  The harmonic source is random (SineGen draws rand/randn), yet the
+    output is not: `x_source = x[:, :, :length]` (:269) adds x to itself, so the source only contributes its
+    length.  The fixture stores two runs under different torch seeds to pin exactly that, plus the f0-aware
+    plumbing (gan_vocoder_inference.py:76-95)."""
+    import models.vocoders.gan.gan_vocoder_inference as gvi
+    n_mel, B, T = 20, 2, 17
+    pre = NS(n_mel=n_mel, hop_size=int(np.prod(HP_NSF["upsample_rates"])), sample_rate=24000,
+             extract_amplitude_phase=False)
+    cfg = NS(preprocess=pre, model=NS(nsfhifigan=NS(**HP_NSF)))
+    torch.manual_seed(41)
+    model = NSFHiFiGAN(cfg).eval()
+    g = torch.Generator().manual_seed(42)
+    mel = torch.randn(B, n_mel, T, generator=g)
+    f0 = torch.rand(B, T, generator=g) * 300 + 80
+    f0[:, 3:6] = 0.0                                  # unvoiced frames
+    with torch.no_grad():
+        torch.manual_seed(1)
+        wav = model(mel, f0).numpy()
+        torch.manual_seed(2)
+        wav2 = model(mel, f0 * 0.5).numpy()           # other source, other noise: same samples
+        wav_long_f0 = model(mel, torch.cat([f0, f0[:, :4]], dim=1)).numpy()   # f0 longer than the mel: no truncation
+    out = {"mel": mel.numpy(), "f0": f0.numpy(), "wav": wav, "wav_other_source": wav2, "wav_long_f0": wav_long_f0}
+    mels = [torch.randn(n_mel, t, generator=g) for t in (7, 11, 4)]
+    f0s = [torch.rand(t, generator=g) * 200 + 100 for t in (7, 11, 4)]
+    auds = gvi.synthesis_audios(cfg, model, mels, f0s=f0s, batch_size=2)
+    for i, (m, f, a) in enumerate(zip(mels, f0s, auds)):
+        out[f"pl_mel{i}"], out[f"pl_f0{i}"], out[f"pl_audio{i}"] = m.numpy(), f.numpy(), a.numpy()
+    for k, v in sd_np(model).items():
+        out["sd:" + k] = v
+    np.savez(os.path.join(HERE, "nsfhifigan.npz"), **out)
+    print("nsfhifigan wav", wav.shape, "absmax", float(np.abs(wav).max()), "source-independent:",
+          bool((wav == wav2).all()), bool((wav == wav_long_f0).all()), [a.shape for a in auds])
+
+
 def gen_activation1d():
     torch.manual_seed(7)
     act = Activation1d(activation=SnakeBeta(6, alpha_logscale=True))
@@ -195,6 +235,9 @@ def gen_plumbing(cfg, model):
 
 
 if __name__ == "__main__":
+    if sys.argv[1:] == ["nsfhifigan"]:     # later additions regenerate alone, the older fixtures stay byte-identical
+        gen_nsfhifigan()
+        sys.exit(0)
     cfg, model = gen_generator("hifigan_rb1", "hifigan", HP_HIFIGAN_RB1, 16, 2, 24, seed=1234)
     gen_plumbing(cfg, model)
     gen_generator("hifigan_rb2", "hifigan", HP_HIFIGAN_RB2, 20, 1, 19, seed=11, mel_dist="logmel")
@@ -202,3 +245,4 @@ if __name__ == "__main__":
     gen_generator("bigvgan_rb2", "bigvgan", HP_BIGVGAN_RB2, 12, 1, 33, seed=31)
     gen_activation1d()
     gen_mel()
+    gen_nsfhifigan()

@@ -4,16 +4,19 @@ from types import SimpleNamespace as NS
 import numpy as np
 import torch
 
-from conftest import GOLDEN_MODELS, load_golden
+from conftest import GOLDEN_MODELS, GOLDEN_NSF, load_golden
 
 HP_V1 = dict(resblock="1", upsample_rates=[8, 8, 2, 2], upsample_kernel_sizes=[16, 16, 4, 4],
              upsample_initial_channel=512, resblock_kernel_sizes=[3, 7, 11],
              resblock_dilation_sizes=[[1, 3, 5]] * 3)
 HP_BIGVGAN_BASE = dict(HP_V1, activation="snakebeta", snake_logscale=True)
+# egs/vocoder/gan/nsfhifigan/exp_config.json:16-48
+HP_NSF_EXP = dict(resblock="1", harmonic_num=8, upsample_rates=[8, 4, 2, 2, 2], upsample_kernel_sizes=[16, 8, 4, 4, 4],
+                  upsample_initial_channel=768, resblock_kernel_sizes=[3, 7, 11], resblock_dilation_sizes=[[1, 3, 5]] * 3)
 
 
 def make_cfg(kind, hp, n_mel):
-    pre = NS(n_mel=n_mel, hop_size=int(np.prod(hp["upsample_rates"])), extract_amplitude_phase=False)
+    pre = NS(n_mel=n_mel, hop_size=int(np.prod(hp["upsample_rates"])), extract_amplitude_phase=False, sample_rate=24000)
     return NS(preprocess=pre, model=NS(generator=kind, **{kind: NS(**hp)}))
 
 
@@ -28,7 +31,7 @@ def build_model(kind, hp, n_mel, state_dict=None, seed=None):
 
 
 def golden_model(name):
-    kind, hp, n_mel = GOLDEN_MODELS[name]
+    kind, hp, n_mel = GOLDEN_NSF if name == "nsfhifigan" else GOLDEN_MODELS[name]
     g, sd = load_golden(name)
     return kind, hp, g, sd, build_model(kind, hp, n_mel, sd)
 

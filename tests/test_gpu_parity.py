@@ -9,7 +9,7 @@ import pytest
 import torch
 
 from conftest import GOLDEN_MODELS, load_golden
-from helpers import HP_BIGVGAN_BASE, HP_V1, build_model, golden_model, make_cfg, randomize_snake, sd_numpy
+from helpers import HP_BIGVGAN_BASE, HP_NSF_EXP, HP_V1, build_model, golden_model, make_cfg, randomize_snake, sd_numpy
 from oracle import generator as og
 from oracle import mel as om
 
@@ -306,6 +306,52 @@ def test_bigvgan_wide_layers_match_oracle():
     got = model(mel.to(DEV)).cpu().numpy()
     assert np.isfinite(got).all()
     assert np.abs(got - want).max() <= 1e-3, np.abs(got - want).max()
+
+
+def test_nsfhifigan_matches_reference_fixture():
+    """NSFHiFiGAN.forward (nsfhifigan.py:262-283) against the output of the reference module: the fixture
+    pins that the (random) harmonic source never reaches the samples, only `x = x + x` does."""
+    from amphion_b200.vocoders import synthesis_audios, vocoder_inference
+    kind, hp, g, sd, model = golden_model("nsfhifigan")
+    model = model.to(DEV)
+    mel, f0 = torch.from_numpy(g["mel"]).to(DEV), torch.from_numpy(g["f0"]).to(DEV)
+    for prec, tol in (("fp32", 2e-5), ("tc_f16", 5e-4), ("tc_bf16", 4e-3)):
+        model.precision = prec
+        wav = model(mel, f0)
+        assert wav.shape == g["wav"].shape and wav.is_cuda
+        assert np.abs(wav.cpu().numpy() - g["wav"]).max() <= tol, (prec, np.abs(wav.cpu().numpy() - g["wav"]).max())
+    model.precision = "fp32"
+    longer = model(mel, torch.cat([f0, f0[:, :4]], dim=1))          # f0 longer than the mel: nothing is truncated
+    np.testing.assert_allclose(longer.cpu().numpy(), g["wav_long_f0"], atol=2e-5)
+    with pytest.raises(NotImplementedError):                          # shorter: the reference truncates each stage
+        model(mel, f0[:, :11])
+    with pytest.raises(ValueError):
+        model(mel, f0[:1])
+    # f0-aware plumbing (gan_vocoder_inference.py:36, :76-95)
+    mels = [torch.from_numpy(g[f"pl_mel{i}"]) for i in range(3)]
+    f0s = [torch.from_numpy(g[f"pl_f0{i}"]) for i in range(3)]
+    auds = synthesis_audios(model.cfg, model, mels, f0s=f0s, batch_size=2)
+    for i, a in enumerate(auds):
+        assert a.device.type == "cpu" and a.shape == g[f"pl_audio{i}"].shape
+        np.testing.assert_allclose(a.numpy(), g[f"pl_audio{i}"], atol=2e-5)
+    out = vocoder_inference(model.cfg, model, mel.cpu(), f0s=f0.cpu(), device=DEV)
+    np.testing.assert_allclose(out.numpy(), g["wav"][:, 0], atol=2e-5)
+
+
+def test_nsfhifigan_exp_config_matches_oracle():
+    """The shipped recipe's architecture (egs/vocoder/gan/nsfhifigan/exp_config.json: 768 channels, rates
+    8.4.2.2.2 — the first ConvTranspose is 768 -> 384, streaming kernel) at a CPU-checkable length."""
+    model = build_model("nsfhifigan", HP_NSF_EXP, 100, seed=3)
+    g = torch.Generator().manual_seed(4)
+    mel = torch.randn(1, 100, 14, generator=g)
+    f0 = torch.rand(1, 14, generator=g) * 400 + 60
+    want = og.generator_forward("nsfhifigan", sd_numpy(model), HP_NSF_EXP, mel.numpy(), f0=f0.numpy())
+    model = model.to(DEV)
+    for prec, tol in (("fp32", 1e-4), ("tc_f16", 1e-3)):
+        model.precision = prec
+        got = model(mel.to(DEV), f0.to(DEV)).cpu().numpy()
+        assert got.shape == (1, 1, 14 * 256)
+        assert np.abs(got - want).max() <= tol, (prec, np.abs(got - want).max())
 
 
 @pytest.mark.parametrize("prec", ["fp32", "tc_f16"])

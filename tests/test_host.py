@@ -10,7 +10,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import GOLDEN_MODELS, ROOT, load_golden
+from conftest import GOLDEN_MODELS, GOLDEN_NSF, ROOT, load_golden
 from helpers import build_model, make_cfg
 
 
@@ -67,6 +67,30 @@ def test_state_dict_keys_and_shapes_match_reference(name):
     for k in sd:
         assert tuple(msd[k].shape) == sd[k].shape, k
     model.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()}, strict=True)
+
+
+def test_nsfhifigan_module_matches_reference_layout():
+    from amphion_b200 import _capi
+    kind, hp, n_mel = GOLDEN_NSF
+    _, sd = load_golden("nsfhifigan")
+    model = build_model(kind, hp, n_mel, seed=41)        # the fixture's seed: same construction order => same weights
+    msd = model.state_dict()
+    assert list(msd.keys()) == list(sd.keys())
+    for k, v in msd.items():
+        np.testing.assert_array_equal(v.numpy(), sd[k], err_msg=k)
+    # tensor table of the C ABI = HiFi-GAN's; the source / noise-conv parameters are not consumed
+    h = model._ensure_handle()
+    names = [_capi.lib.ab_generator_tensor_name(h, i).decode() for i in range(_capi.lib.ab_generator_num_tensors(h))]
+    assert "ups.0.weight" in names and not any(n.startswith(("m_source", "noise_convs")) for n in names)
+    # the reference's ResBlock2 cannot be constructed (nsfhifigan.py:111): same TypeError here
+    with pytest.raises(TypeError):
+        build_model(kind, dict(hp, resblock="2"), n_mel)
+    # odd source stride (rates [..., 3, 3]) truncates the stage in the reference: refused by the C ABI
+    bad = build_model(kind, dict(hp, upsample_rates=[4, 3, 3], upsample_kernel_sizes=[8, 5, 5]), n_mel)
+    with pytest.raises(RuntimeError, match="odd source stride"):
+        bad._ensure_handle()
+    with pytest.raises(RuntimeError, match="CUDA"):      # no CPU fallback
+        model(torch.zeros(1, n_mel, 4), torch.zeros(1, 4))
 
 
 def test_seeded_init_reproduces_reference_weights():

@@ -3,7 +3,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import GOLDEN_MODELS, load_golden
+from conftest import GOLDEN_MODELS, GOLDEN_NSF, load_golden
 from oracle import generator as og
 from oracle import mel as om
 
@@ -16,6 +16,25 @@ def test_generator_matches_reference(name):
     for i, s in enumerate(stages):
         np.testing.assert_allclose(s, g[f"stage{i}"], atol=2e-6, rtol=1e-5)
     np.testing.assert_allclose(wav, g["wav"], atol=1e-6, rtol=0)
+
+
+def test_nsfhifigan_oracle_matches_reference():
+    # the reference's output does not depend on the (random) harmonic source: nsfhifigan.py:269
+    kind, hp, _ = GOLDEN_NSF
+    g, sd = load_golden("nsfhifigan")
+    np.testing.assert_array_equal(g["wav"], g["wav_other_source"])
+    np.testing.assert_array_equal(g["wav"], g["wav_long_f0"])
+    wav = og.generator_forward(kind, sd, hp, g["mel"], f0=g["f0"])
+    np.testing.assert_allclose(wav, g["wav"], atol=1e-6, rtol=0)
+    mels = [g[f"pl_mel{i}"] for i in range(3)]
+    f0s = [g[f"pl_f0{i}"] for i in range(3)]
+    auds = og.synthesis_audios(kind, sd, hp, mels, hop_size=16, batch_size=2, f0s=f0s)
+    for i, a in enumerate(auds):
+        assert a.shape == g[f"pl_audio{i}"].shape
+        np.testing.assert_allclose(a, g[f"pl_audio{i}"], atol=1e-6)
+    # a source shorter than the mel truncates every stage (:264-268)
+    short = og.generator_forward(kind, sd, hp, g["mel"], f0=g["f0"][:, :11])
+    assert short.shape[-1] == 11 * 16
 
 
 def test_fold_weight_norm_matches_torch():
