@@ -9,7 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libamphion_b200.so")
-SOURCES = ["ab_capi.cu", "ab_kernels_fp32.cu", "ab_kernels_tc.cu", "ab_kernels_gemmconv.cu", "ab_mel.cu"]
+SOURCES = ["ab_capi.cu", "ab_kernels_fp32.cu", "ab_kernels_tc.cu", "ab_kernels_gemmconv.cu", "ab_mel.cu", "ab_pcm.cu"]
 
 
 def _nvcc() -> str:

@@ -206,6 +206,21 @@ int ab_mel_forward(ab_mel* m, const float* dev_wav, int64_t batch, int64_t sampl
                    float* dev_mel, float* dev_energy, void* dev_workspace, size_t workspace_bytes,
                    void* stream);
 
+/* ------------------------------------------------------------------------
+ * Waveform -> 16-bit PCM: the arithmetic of save_audio (utils/io.py:49-76) on the device, applied to a
+ * batch of generator outputs before the D2H copy.
+ *   dev_wav [batch, samples] fp32 with row stride `row_stride`; dev_lengths [batch] int64 valid samples per
+ *   row (NULL = all `samples`); turn_up: scale each row by volume_peak / max|w| over its valid samples
+ *   (io.py:59-62); silence: zero samples put before and after each row (fs // 20 for add_silence, io.py:64-68);
+ *   dev_out [batch, out_stride] int16, out_stride even and >= samples + 2*silence; the tail of every row
+ *   beyond silence + length + silence is zero.  Quantiser: clamp(floor(w * 32768 + 0.5), -32768, 32767)
+ *   (torchaudio 2.0.2 sox_io, PCM_S 16 — io.py:76).  Workspace: ab_pcm16_workspace_bytes(batch) when turn_up. */
+size_t ab_pcm16_workspace_bytes(int64_t batch);
+int ab_pcm16_forward(const float* dev_wav, int64_t batch, int64_t samples, int64_t row_stride,
+                     const int64_t* dev_lengths, int32_t turn_up, float volume_peak, int64_t silence,
+                     int16_t* dev_out, int64_t out_stride, void* dev_workspace, size_t workspace_bytes,
+                     void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -175,6 +175,24 @@ def gen_nsfhifigan():
           bool((wav == wav2).all()), bool((wav == wav_long_f0).all()), [a.shape for a in auds])
 
 
+def gen_save_audio():
+    """utils/io.py:49-76 with torchaudio.save intercepted: the float tensor it is handed is the fixture."""
+    import utils.io as rio
+    got = {}
+    rio.torchaudio.save = lambda path, wav, fs, **kw: got.__setitem__(path, (wav.numpy().copy(), fs, dict(kw)))
+    g = torch.Generator().manual_seed(9)
+    w = (torch.randn(3000, generator=g) * 0.2).numpy()
+    w[100] = -0.73                                     # the peak is a negative sample
+    out = {"w": w}
+    for ts in (0, 1):
+        for sil in (0, 1):
+            rio.save_audio(f"k{ts}{sil}", w, 16000, add_silence=bool(sil), turn_up=bool(ts))
+            out[f"float_turnup{ts}_silence{sil}"] = got[f"k{ts}{sil}"][0]
+    assert got["k00"][2] == dict(encoding="PCM_S", bits_per_sample=16)
+    np.savez(os.path.join(HERE, "save_audio.npz"), **out)
+    print("save_audio", {k: v.shape for k, v in out.items()})
+
+
 def gen_activation1d():
     torch.manual_seed(7)
     act = Activation1d(activation=SnakeBeta(6, alpha_logscale=True))
@@ -235,8 +253,9 @@ def gen_plumbing(cfg, model):
 
 
 if __name__ == "__main__":
-    if sys.argv[1:] == ["nsfhifigan"]:     # later additions regenerate alone, the older fixtures stay byte-identical
-        gen_nsfhifigan()
+    if sys.argv[1:] and set(sys.argv[1:]) <= {"nsfhifigan", "save_audio"}:   # later additions regenerate alone
+        for name in sys.argv[1:]:
+            {"nsfhifigan": gen_nsfhifigan, "save_audio": gen_save_audio}[name]()
         sys.exit(0)
     cfg, model = gen_generator("hifigan_rb1", "hifigan", HP_HIFIGAN_RB1, 16, 2, 24, seed=1234)
     gen_plumbing(cfg, model)
@@ -246,3 +265,4 @@ if __name__ == "__main__":
     gen_activation1d()
     gen_mel()
     gen_nsfhifigan()
+    gen_save_audio()

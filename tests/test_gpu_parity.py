@@ -485,3 +485,42 @@ def test_mel_full_size_properties():
     m2, _ = taco.mel_spectrogram(y[5:6])
     # batch independence (cuFFT may pick a different plan for another batch count: not bit-equal)
     torch.testing.assert_close(m2[0], m[5], atol=2e-5, rtol=0)
+
+
+def test_save_audio_matches_oracle(tmp_path):
+    """utils/io.py:49-76 on the device: bit-exact against the oracle (float stage pinned by the reference
+    fixture, quantiser restated — see oracle/io.py)."""
+    import wave
+    from oracle import io as oio
+    from amphion_b200.io import save_audio, save_audios, waveform_to_pcm16
+    g, _ = load_golden("save_audio")
+    for ts in (0, 1):
+        for sil in (0, 1):
+            p = tmp_path / f"a{ts}{sil}.wav"
+            save_audio(p, g["w"], 16000, add_silence=bool(sil), turn_up=bool(ts))
+            with wave.open(str(p)) as f:
+                assert (f.getnchannels(), f.getsampwidth(), f.getframerate()) == (1, 2, 16000)
+                got = np.frombuffer(f.readframes(f.getnframes()), "<i2")
+            want = oio.pcm16(g[f"float_turnup{ts}_silence{sil}"])[0]
+            np.testing.assert_array_equal(got, want)
+    # batch with ragged lengths (down to one sample), odd sizes, a constant row and clipping
+    gen = torch.Generator().manual_seed(3)
+    wav = torch.randn(5, 4097, generator=gen) * 0.7
+    wav[4] = 0.25
+    lens = [4097, 1, 1000, 333, 4096]
+    pcm = waveform_to_pcm16(wav.to(DEV), lens, silence=7, turn_up=True, volume_peak=0.9).cpu().numpy()
+    assert pcm.shape == (5, 4097 + 14 + 1)
+    for b, n in enumerate(lens):
+        want = oio.pcm16(oio.save_audio_float(wav[b, :n].numpy(), 140, add_silence=True, turn_up=True))[0]
+        np.testing.assert_array_equal(pcm[b, : n + 14], want)
+        assert not pcm[b, n + 14:].any()
+    plain = waveform_to_pcm16((wav * 3).to(DEV)).cpu().numpy()
+    np.testing.assert_array_equal(plain[:, :4097], oio.pcm16((wav * 3).numpy()))
+    paths = [tmp_path / f"b{i}.wav" for i in range(5)]
+    save_audios(paths, wav.to(DEV), 22050, lengths=lens, add_silence=True)
+    with wave.open(str(paths[2])) as f:
+        assert f.getnframes() == 1000 + 2 * (22050 // 20)
+    # full-size property: a config-2 sized batch quantises to the same values as the oracle's formula
+    big = torch.rand(8, 262144, generator=gen) * 2 - 1
+    got = waveform_to_pcm16(big.to(DEV)).cpu().numpy()
+    np.testing.assert_array_equal(got, oio.pcm16(big.numpy()))

@@ -162,3 +162,16 @@ def test_mel_filterbank_host_matches_oracle():
     from oracle import mel as om
     for args in [(22050, 1024, 80, 0, 8000), (16000, 512, 40, 50, 7600), (24000, 1024, 100, 0, None)]:
         np.testing.assert_allclose(mel.librosa_mel_fn(*args).numpy(), om.slaney_mel_filterbank(*args), atol=1e-7)
+
+
+def test_wav_writer_roundtrip(tmp_path):
+    import wave
+    from amphion_b200.io import write_wav_pcm16
+    x = (np.arange(-5, 6) * 3000).astype(np.int16)
+    write_wav_pcm16(tmp_path / "a.wav", x, 24000)
+    with wave.open(str(tmp_path / "a.wav")) as f:
+        assert (f.getnchannels(), f.getsampwidth(), f.getframerate(), f.getnframes()) == (1, 2, 24000, 11)
+        np.testing.assert_array_equal(np.frombuffer(f.readframes(11), "<i2"), x)
+    from amphion_b200.io import save_audio
+    with pytest.raises(RuntimeError):                    # no CPU fallback: the quantiser only exists as a CUDA kernel
+        save_audio(tmp_path / "b.wav", np.zeros(16, np.float32), 16000)

@@ -5,6 +5,7 @@ import torch
 
 from conftest import GOLDEN_MODELS, GOLDEN_NSF, load_golden
 from oracle import generator as og
+from oracle import io as oio
 from oracle import mel as om
 
 
@@ -121,3 +122,16 @@ def test_mel_filterbank_matches_torchaudio():
     ta = pytest.importorskip("torchaudio")
     fb = ta.functional.melscale_fbanks(513, 0.0, 8000.0, 80, 22050, norm="slaney", mel_scale="slaney").T.numpy()
     np.testing.assert_allclose(om.slaney_mel_filterbank(22050, 1024, 80, 0, 8000), fb, atol=5e-7)
+
+
+def test_save_audio_oracle_matches_reference():
+    g, _ = load_golden("save_audio")
+    for ts in (0, 1):
+        for sil in (0, 1):
+            got = oio.save_audio_float(g["w"], 16000, add_silence=bool(sil), turn_up=bool(ts))
+            np.testing.assert_array_equal(got, g[f"float_turnup{ts}_silence{sil}"])
+    assert np.abs(g["float_turnup1_silence0"]).max() == np.float32(0.9) or abs(np.abs(g["float_turnup1_silence0"]).max() - 0.9) < 1e-7
+    # quantiser known answers (sox: (x * 2^31 + 0x8000) >> 16, clipped)
+    x = np.array([0.0, 0.5, -0.5, 1.0, -1.0, 1.5, -1.5, 1 / 32768, 1.5 / 32768, -1.5 / 32768, 0.49 / 32768, -0.51 / 32768],
+                 np.float32)
+    np.testing.assert_array_equal(oio.pcm16(x), [0, 16384, -16384, 32767, -32768, 32767, -32768, 1, 2, -1, 0, -1])
