@@ -30,6 +30,8 @@ class GeneratorConfig(C.Structure):
         ("resblock_dilation_sizes", (C.c_int32 * AB_MAX_DILATIONS) * AB_MAX_KERNELS),
         ("activation", C.c_int32),
         ("snake_logscale", C.c_int32),
+        ("gin_channels", C.c_int32),
+        ("conv_post_no_bias", C.c_int32),
     ]
 
 
@@ -68,6 +70,7 @@ SIGNATURES = {
     "ab_generator_finalize": (C.c_int, [_P, C.c_int32, _P]),
     "ab_generator_workspace_bytes": (C.c_size_t, [_P, C.c_int64, C.c_int64]),
     "ab_generator_forward": (C.c_int, [_P, _P, C.c_int64, C.c_int64, _I64P, _P, _P, C.c_size_t, _P]),
+    "ab_generator_forward_cond": (C.c_int, [_P, _P, C.c_int64, C.c_int64, _I64P, _P, C.c_int64, _P, _P, C.c_size_t, _P]),
     "ab_generator_last_launches": (C.c_int, [_P]),
     "ab_generator_set_profiling": (C.c_int, [_P, C.c_int32]),
     "ab_generator_get_profile": (C.c_int, [_P, C.POINTER(ProfileEntry), C.c_int32, C.POINTER(C.c_int32)]),

@@ -96,6 +96,7 @@ struct ab_generator {
   int launches = 0;
 
   ConvRef conv_pre, conv_post;
+  int cond_w = -1, cond_b = -1;   // HiFiGAN_vits global conditioning (hifigan.py:424-425)
   ActRef act_post;
   std::vector<StageRef> stages;
 
@@ -145,7 +146,8 @@ struct ab_generator {
 
 namespace {
 
-ConvRef make_conv(ab_generator* g, const std::string& name, int cin, int cout, int k, int d, bool transposed) {
+ConvRef make_conv(ab_generator* g, const std::string& name, int cin, int cout, int k, int d, bool transposed,
+                  bool has_bias = true) {
   ConvRef c;
   c.cin = cin;
   c.cout = cout;
@@ -156,7 +158,7 @@ ConvRef make_conv(ab_generator* g, const std::string& name, int cin, int cout, i
   else
     c.w = g->add_slot(name + ".weight", SLOT_CONV_W, {cout, cin, k});
   g->slots[c.w].dilation = d;
-  c.b = g->add_slot(name + ".bias", SLOT_VEC, {cout});
+  c.b = has_bias ? g->add_slot(name + ".bias", SLOT_VEC, {cout}) : -1;
   return c;
 }
 
@@ -190,6 +192,9 @@ int validate_config(const ab_generator_config& c) {
   }
   if (c.kind == AB_GEN_BIGVGAN && c.activation != AB_ACT_SNAKE && c.activation != AB_ACT_SNAKEBETA)
     return fail(AB_ERR_ARG, "config: BigVGAN activation must be snake or snakebeta");
+  if (c.gin_channels < 0 || c.gin_channels > 65536) return fail(AB_ERR_ARG, "config: gin_channels %d out of range", c.gin_channels);
+  if ((c.gin_channels > 0 || c.conv_post_no_bias) && c.kind != AB_GEN_HIFIGAN)
+    return fail(AB_ERR_ARG, "config: gin_channels / conv_post_no_bias belong to the HiFi-GAN kind (HiFiGAN_vits)");
   if (c.kind == AB_GEN_NSFHIFIGAN) {
     // noise_convs[i]: Conv1d(1, C, 2s, stride s, padding s/2) with s = prod(rates[i+1:]) (nsfhifigan.py:223-236);
     // for odd s > 1 its output is one sample short and the reference truncates the stage (:264-266)
@@ -265,7 +270,11 @@ int ab_generator_create(const ab_generator_config* cfg, ab_generator** out) {
     g->stages.push_back(st);
   }
   if (big) g->act_post = make_act(g, "activation_post", ch, has_beta);
-  g->conv_post = make_conv(g, "conv_post", ch, 1, 7, 1, false);
+  g->conv_post = make_conv(g, "conv_post", ch, 1, 7, 1, false, !cfg->conv_post_no_bias);
+  if (cfg->gin_channels > 0) {
+    g->cond_w = g->add_slot("cond.weight", SLOT_VEC, {c0, cfg->gin_channels, 1});
+    g->cond_b = g->add_slot("cond.bias", SLOT_VEC, {c0});
+  }
 
   // tensor-core operand images live behind the fp32 images; reserve worst case
   size_t tc = 0;
@@ -468,10 +477,12 @@ int ab_generator_get_profile(ab_generator* g, ab_profile_entry* out, int32_t max
   return AB_OK;
 }
 
-int ab_generator_forward(ab_generator* g, const float* dev_mel, int64_t B, int64_t T,
-                         const int64_t mel_strides[3], float* dev_wav, void* dev_workspace,
-                         size_t workspace_bytes, void* stream) {
+static int forward_impl(ab_generator* g, const float* dev_mel, int64_t B, int64_t T, const int64_t mel_strides[3],
+                        const float* dev_g, int64_t g_batch_stride, float* dev_wav, void* dev_workspace,
+                        size_t workspace_bytes, void* stream) {
   if (!g || !dev_mel || !dev_wav || !mel_strides) return fail(AB_ERR_ARG, "forward: null argument");
+  if (dev_g != nullptr && g->cond_w < 0) return fail(AB_ERR_STATE, "forward: conditioning given but the generator has gin_channels == 0");
+  if (dev_g != nullptr && g_batch_stride < g->cfg.gin_channels) return fail(AB_ERR_ARG, "forward: g row stride < gin_channels");
   if (!g->finalized) return fail(AB_ERR_STATE, "forward: finalize() the generator first");
   if (B <= 0 || T <= 0) return fail(AB_ERR_ARG, "forward: batch and frames must be positive (got %lld, %lld)", (long long)B, (long long)T);
   if (B > 65535) return fail(AB_ERR_UNSUPPORTED, "forward: batch %lld > 65535", (long long)B);
@@ -594,6 +605,12 @@ int ab_generator_forward(ab_generator* g, const float* dev_mel, int64_t B, int64
   rc = conv(g->conv_pre, dev_mel, mel_strides[0], mel_strides[1], mel_strides[2], R[0], (int)T, 1.0f,
             nullptr, nullptr, 1.0f, 0);
   if (rc != AB_OK) return rc;
+  if (dev_g != nullptr) {   // x = x + cond(g)  (hifigan.py:429-430)
+    ++launches;
+    rc = launch_cond_add(R[0], dev_g, g_batch_stride, g->fptr(g->cond_w), g->fptr(g->cond_b), (int)B, C0,
+                         g->cfg.gin_channels, (int)T, st);
+    if (rc != AB_OK) return rc;
+  }
   int cur_r = 0;
   int Tn = (int)T;
   int cin = C0;
@@ -728,6 +745,18 @@ int ab_generator_forward(ab_generator* g, const float* dev_mel, int64_t B, int64
   if (rc != AB_OK) return rc;
   g->launches = launches;
   return AB_OK;
+}
+
+int ab_generator_forward(ab_generator* g, const float* dev_mel, int64_t B, int64_t T,
+                         const int64_t mel_strides[3], float* dev_wav, void* dev_workspace,
+                         size_t workspace_bytes, void* stream) {
+  return forward_impl(g, dev_mel, B, T, mel_strides, nullptr, 0, dev_wav, dev_workspace, workspace_bytes, stream);
+}
+
+int ab_generator_forward_cond(ab_generator* g, const float* dev_x, int64_t B, int64_t T, const int64_t x_strides[3],
+                              const float* dev_g, int64_t g_batch_stride, float* dev_wav, void* dev_workspace,
+                              size_t workspace_bytes, void* stream) {
+  return forward_impl(g, dev_x, B, T, x_strides, dev_g, g_batch_stride, dev_wav, dev_workspace, workspace_bytes, stream);
 }
 
 // ---------------------------------------------------------------------------

@@ -81,5 +81,8 @@ int launch_repack_weight(const float* v, const float* g, float* dst, int d0, int
                          int transposed, cudaStream_t s);
 
 int launch_scale_inplace(float* p, size_t n, float gain, cudaStream_t s);
+// x[b, c, :] += bias[c] + sum_i w[c, i] * g[b, i]   (1x1 conditioning conv on a per-utterance vector, hifigan.py:429-430)
+int launch_cond_add(float* x, const float* g, int64_t g_batch_stride, const float* w, const float* bias, int B, int C,
+                    int gin, int T, cudaStream_t s);
 
 }  // namespace ab

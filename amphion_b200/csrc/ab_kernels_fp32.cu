@@ -690,6 +690,35 @@ __global__ void scale_inplace_kernel(float* p, size_t n, float gain) {
 }
 }  // namespace
 
+namespace {
+// one CTA per (channel, batch): warp-reduced dot product, then the row update
+__global__ void __launch_bounds__(128) cond_add_kernel(float* __restrict__ x, const float* __restrict__ g, int64_t gsb,
+                                                       const float* __restrict__ w, const float* __restrict__ bias,
+                                                       int C, int gin, int T) {
+  const int c = blockIdx.x, b = blockIdx.y;
+  const float* gr = g + (int64_t)b * gsb;
+  const float* wr = w + (int64_t)c * gin;
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < gin; i += 128) acc = fmaf(__ldg(wr + i), __ldg(gr + i), acc);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  __shared__ float part[4];
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  const float v = ((part[0] + part[1]) + (part[2] + part[3])) + (bias ? __ldg(bias + c) : 0.f);
+  float* xr = x + ((int64_t)b * C + c) * T;
+  for (int t = threadIdx.x; t < T; t += 128) xr[t] += v;
+}
+}  // namespace
+
+int launch_cond_add(float* x, const float* g, int64_t g_batch_stride, const float* w, const float* bias, int B, int C,
+                    int gin, int T, cudaStream_t s) {
+  if (B <= 0 || C <= 0 || gin <= 0 || T <= 0 || B > 65535) return fail(AB_ERR_ARG, "cond_add: bad shape");
+  cond_add_kernel<<<dim3((unsigned)C, (unsigned)B), 128, 0, s>>>(x, g, g_batch_stride, w, bias, C, gin, T);
+  AB_LAUNCH_CHECK("cond_add_kernel");
+  return AB_OK;
+}
+
 int launch_scale_inplace(float* p, size_t n, float gain, cudaStream_t s) {
   if (n == 0) return AB_OK;
   const int blocks = (int)std::min<size_t>((n + 255) / 256, 148 * 8);

@@ -1,7 +1,7 @@
 """Native GAN vocoders behind the reference's registry/dispatch surface
 (models/vocoders/vocoder_inference.py:39-75)."""
 from .bigvgan import BigVGAN
-from .hifigan import HiFiGAN
+from .hifigan import HiFiGAN, HiFiGAN_vits
 from .nsfhifigan import NSFHiFiGAN
 from .gan_vocoder_inference import synthesis_audios, vocoder_inference
 
@@ -10,5 +10,5 @@ _vocoders = {"hifigan": HiFiGAN, "bigvgan": BigVGAN, "nsfhifigan": NSFHiFiGAN}
 _vocoder_forward_funcs = {"hifigan": vocoder_inference, "bigvgan": vocoder_inference, "nsfhifigan": vocoder_inference}
 _vocoder_infer_funcs = {"hifigan": synthesis_audios, "bigvgan": synthesis_audios, "nsfhifigan": synthesis_audios}
 
-__all__ = ["HiFiGAN", "BigVGAN", "NSFHiFiGAN", "vocoder_inference", "synthesis_audios", "_vocoders",
+__all__ = ["HiFiGAN", "HiFiGAN_vits", "BigVGAN", "NSFHiFiGAN", "vocoder_inference", "synthesis_audios", "_vocoders",
            "_vocoder_forward_funcs", "_vocoder_infer_funcs"]

@@ -113,6 +113,8 @@ class NativeGenerator(nn.Module):
             c.snake_logscale = int(bool(hp.snake_logscale))
         else:
             c.activation = _capi.ACT_LRELU
+        c.gin_channels = int(getattr(self, "gin_channels", 0))
+        c.conv_post_no_bias = int(getattr(self, "conv_post_no_bias", False))
         return c
 
     # ---- parameter packing ---------------------------------------------------
@@ -166,6 +168,10 @@ class NativeGenerator(nn.Module):
     # ---- forward ---------------------------------------------------------------
     def forward(self, x):
         """mel [B, n_mel, T] (any strides) -> wav [B, 1, T*hop], fp32, same device."""
+        return self._forward_native(x)
+
+    def _forward_native(self, x, g=None):
+        """``g`` [B, gin_channels] (HiFiGAN_vits conditioning) or None."""
         _capi.require_cuda(x, f"{type(self).__name__}.forward")
         if x.dim() != 3 or x.shape[1] != int(self.cfg.preprocess.n_mel):
             raise ValueError(f"expected mel of shape [B, {self.cfg.preprocess.n_mel}, T], got {tuple(x.shape)}")
@@ -187,8 +193,13 @@ class NativeGenerator(nn.Module):
             wbase = (self._workspace.data_ptr() + 255) // 256 * 256
             wav = torch.empty(B, 1, T * hop, dtype=torch.float32, device=x.device)
             strides = _capi.shape_array(x.stride())
-            _capi.check(lib.ab_generator_forward(h, _capi.ptr(x), B, T, strides, _capi.ptr(wav), C.c_void_p(wbase),
-                                                 need, _capi.stream_ptr()), "ab_generator_forward")
+            if g is None:
+                _capi.check(lib.ab_generator_forward(h, _capi.ptr(x), B, T, strides, _capi.ptr(wav), C.c_void_p(wbase),
+                                                     need, _capi.stream_ptr()), "ab_generator_forward")
+            else:
+                _capi.check(lib.ab_generator_forward_cond(h, _capi.ptr(x), B, T, strides, _capi.ptr(g), g.stride(0),
+                                                          _capi.ptr(wav), C.c_void_p(wbase), need, _capi.stream_ptr()),
+                            "ab_generator_forward_cond")
             self.last_launches = lib.ab_generator_last_launches(h)
         return wav
 

@@ -82,6 +82,9 @@ typedef struct ab_generator_config {
   int32_t resblock_dilation_sizes[AB_MAX_KERNELS][AB_MAX_DILATIONS];
   int32_t activation;                           /* ab_activation; LRELU for HiFi-GAN */
   int32_t snake_logscale;                       /* cfg.model.bigvgan.snake_logscale */
+  /* HiFiGAN_vits (hifigan.py:376-449, the decoder inside VITS): kind AB_GEN_HIFIGAN plus */
+  int32_t gin_channels;                         /* > 0: tensors "cond.weight" [C0, gin, 1], "cond.bias" [C0] (:424-425) */
+  int32_t conv_post_no_bias;                    /* 1: conv_post = Conv1d(ch, 1, 7, bias=False) (:421), no "conv_post.bias" */
 } ab_generator_config;
 
 int ab_generator_create(const ab_generator_config* cfg, ab_generator** out);
@@ -120,6 +123,12 @@ size_t ab_generator_workspace_bytes(const ab_generator* g, int64_t batch, int64_
 int ab_generator_forward(ab_generator* g, const float* dev_mel, int64_t batch, int64_t frames,
                          const int64_t mel_strides[3], float* dev_wav, void* dev_workspace,
                          size_t workspace_bytes, void* stream);
+/* HiFiGAN_vits.forward(x, g) (hifigan.py:427-445): as above with x = conv_pre(x) + cond(g) when dev_g is given.
+ * dev_g [B, gin_channels] fp32 with row stride g_batch_stride (the reference's g is [B, gin, 1]); NULL = no
+ * conditioning (`if g is not None`, :429).  Needs a generator created with gin_channels > 0. */
+int ab_generator_forward_cond(ab_generator* g, const float* dev_x, int64_t batch, int64_t frames,
+                              const int64_t x_strides[3], const float* dev_g, int64_t g_batch_stride,
+                              float* dev_wav, void* dev_workspace, size_t workspace_bytes, void* stream);
 /* number of kernels the last forward enqueued (bench.py's gpu_launches) */
 int ab_generator_last_launches(const ab_generator* g);
 

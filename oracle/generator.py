@@ -318,6 +318,32 @@ def bigvgan_forward(params, hp, mel, return_stages=False):
     return (out, stages) if return_stages else out
 
 
+def hifigan_vits_forward(params, hp, x, g=None):
+    """HiFiGAN_vits.forward (hifigan.py:427-445): plain conv_pre, ``x + cond(g)`` with g [B, gin, 1], HiFi-GAN
+    stages (the residual blocks are called without a mask, :437-441), bias-free conv_post."""
+    x = _t(np.asarray(x, np.float32)) if not isinstance(x, torch.Tensor) else x.float()
+    with torch.no_grad():
+        x = conv1d(x, get_weight(params, "conv_pre"), _bias(params, "conv_pre"), padding=3)
+        if g is not None:
+            x = x + conv1d(_t(np.asarray(g, np.float32)), get_weight(params, "cond"), _bias(params, "cond"))
+        nk = len(hp["resblock_kernel_sizes"])
+        rb = resblock1 if str(hp["resblock"]) == "1" else resblock2
+        for i, (u, k) in enumerate(zip(hp["upsample_rates"], hp["upsample_kernel_sizes"])):
+            x = F.leaky_relu(x, LRELU_SLOPE)
+            x = conv_transpose1d(x, get_weight(params, f"ups.{i}"), _bias(params, f"ups.{i}"),
+                                 stride=u, padding=(k - u) // 2)
+            xs = None
+            for j in range(nk):
+                r = rb(params, f"resblocks.{i * nk + j}", x, hp["resblock_kernel_sizes"][j],
+                       hp["resblock_dilation_sizes"][j])
+                xs = r if xs is None else xs + r
+            x = xs / nk
+        x = F.leaky_relu(x)
+        x = conv1d(x, get_weight(params, "conv_post"), None, padding=3)
+        x = torch.tanh(x)
+    return x.numpy()
+
+
 def nsfhifigan_forward(params, hp, mel, f0, return_stages=False):
     """nsfhifigan.py:262-283.  ``har_source`` (:263) is [B, 1, T_f0 * upp]; ``noise_convs[i]`` (:223-236) maps it
     to length floor((L + 2*(s//2) - 2s) / s) + 1 with s = prod(rates[i+1:]) (kernel 1 for the last stage), and

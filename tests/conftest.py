@@ -56,6 +56,22 @@ GOLDEN_NSF = ("nsfhifigan", dict(resblock="1", harmonic_num=8, upsample_rates=[4
                                  resblock_dilation_sizes=[[1, 3, 5]] * 3), 20)
 
 
+# HiFiGAN_vits fixtures (positional constructor; tests/golden/gen_golden.py:gen_hifigan_vits)
+GOLDEN_VITS = {
+    "a": dict(initial_channel=24, resblock="1", resblock_kernel_sizes=[3, 7, 11], resblock_dilation_sizes=[[1, 3, 5]] * 3,
+              upsample_rates=[4, 2], upsample_initial_channel=64, upsample_kernel_sizes=[8, 4], gin_channels=10),
+    "b": dict(initial_channel=12, resblock="2", resblock_kernel_sizes=[3, 5], resblock_dilation_sizes=[[1, 2], [2, 6]],
+              upsample_rates=[2, 2], upsample_initial_channel=32, upsample_kernel_sizes=[4, 4], gin_channels=0),
+}
+
+
+def load_golden_vits(tag):
+    z = np.load(os.path.join(GOLDEN, "hifigan_vits.npz"))
+    d = {k[len(tag) + 1:]: z[k] for k in z.files if k.startswith(tag + ":")}
+    sd = {k[3:]: v for k, v in d.items() if k.startswith("sd:")}
+    return {k: v for k, v in d.items() if not k.startswith("sd:")}, sd
+
+
 @pytest.fixture(scope="session")
 def golden_models():
     return GOLDEN_MODELS

@@ -64,7 +64,7 @@ import warnings  # noqa: E402
 
 warnings.filterwarnings("ignore")
 
-from models.vocoders.gan.generator.hifigan import HiFiGAN  # noqa: E402
+from models.vocoders.gan.generator.hifigan import HiFiGAN, HiFiGAN_vits  # noqa: E402
 from models.vocoders.gan.generator.bigvgan import BigVGAN  # noqa: E402
 from models.vocoders.gan.generator.nsfhifigan import NSFHiFiGAN  # noqa: E402
 from modules.anti_aliasing.act import Activation1d  # noqa: E402
@@ -175,6 +175,34 @@ def gen_nsfhifigan():
           bool((wav == wav2).all()), bool((wav == wav_long_f0).all()), [a.shape for a in auds])
 
 
+VITS_ARGS = dict(initial_channel=24, resblock="1", resblock_kernel_sizes=[3, 7, 11],
+                 resblock_dilation_sizes=[[1, 3, 5]] * 3, upsample_rates=[4, 2], upsample_initial_channel=64,
+                 upsample_kernel_sizes=[8, 4], gin_channels=10)
+VITS_ARGS_RB2 = dict(initial_channel=12, resblock="2", resblock_kernel_sizes=[3, 5], resblock_dilation_sizes=[[1, 2], [2, 6]],
+                     upsample_rates=[2, 2], upsample_initial_channel=32, upsample_kernel_sizes=[4, 4], gin_channels=0)
+
+
+def gen_hifigan_vits():
+    """HiFiGAN_vits (hifigan.py:376-449), the decoder inside VITS: with and without the global conditioning."""
+    out = {}
+    for tag, args, seed, B, T in (("a", VITS_ARGS, 51, 2, 19), ("b", VITS_ARGS_RB2, 52, 1, 23)):
+        torch.manual_seed(seed)
+        model = HiFiGAN_vits(**args).eval()
+        gen = torch.Generator().manual_seed(seed + 1)
+        x = torch.randn(B, args["initial_channel"], T, generator=gen)
+        out[f"{tag}:x"] = x.numpy()
+        with torch.no_grad():
+            out[f"{tag}:wav"] = model(x).numpy()
+            if args["gin_channels"]:
+                g = torch.randn(B, args["gin_channels"], 1, generator=gen)
+                out[f"{tag}:g"] = g.numpy()
+                out[f"{tag}:wav_g"] = model(x, g=g).numpy()
+        for k, v in sd_np(model).items():
+            out[f"{tag}:sd:" + k] = v
+    np.savez(os.path.join(HERE, "hifigan_vits.npz"), **out)
+    print("hifigan_vits", out["a:wav"].shape, out["b:wav"].shape, float(np.abs(out["a:wav_g"] - out["a:wav"]).max()))
+
+
 def gen_save_audio():
     """utils/io.py:49-76 with torchaudio.save intercepted: the float tensor it is handed is the fixture."""
     import utils.io as rio
@@ -253,9 +281,10 @@ def gen_plumbing(cfg, model):
 
 
 if __name__ == "__main__":
-    if sys.argv[1:] and set(sys.argv[1:]) <= {"nsfhifigan", "save_audio"}:   # later additions regenerate alone
+    LATER = {"nsfhifigan": gen_nsfhifigan, "save_audio": gen_save_audio, "hifigan_vits": gen_hifigan_vits}
+    if sys.argv[1:] and set(sys.argv[1:]) <= set(LATER):   # later additions regenerate alone
         for name in sys.argv[1:]:
-            {"nsfhifigan": gen_nsfhifigan, "save_audio": gen_save_audio}[name]()
+            LATER[name]()
         sys.exit(0)
     cfg, model = gen_generator("hifigan_rb1", "hifigan", HP_HIFIGAN_RB1, 16, 2, 24, seed=1234)
     gen_plumbing(cfg, model)
@@ -266,3 +295,4 @@ if __name__ == "__main__":
     gen_mel()
     gen_nsfhifigan()
     gen_save_audio()
+    gen_hifigan_vits()

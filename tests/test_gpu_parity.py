@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import GOLDEN_MODELS, load_golden
+from conftest import GOLDEN_MODELS, GOLDEN_VITS, load_golden, load_golden_vits
 from helpers import HP_BIGVGAN_BASE, HP_NSF_EXP, HP_V1, build_model, golden_model, make_cfg, randomize_snake, sd_numpy
 from oracle import generator as og
 from oracle import mel as om
@@ -524,3 +524,45 @@ def test_save_audio_matches_oracle(tmp_path):
     big = torch.rand(8, 262144, generator=gen) * 2 - 1
     got = waveform_to_pcm16(big.to(DEV)).cpu().numpy()
     np.testing.assert_array_equal(got, oio.pcm16(big.numpy()))
+
+
+@pytest.mark.parametrize("tag", sorted(GOLDEN_VITS))
+def test_hifigan_vits_matches_reference_fixture(tag):
+    """HiFiGAN_vits.forward(x, g) (hifigan.py:427-445), the VITS waveform decoder."""
+    from amphion_b200.vocoders import HiFiGAN_vits
+    g, sd = load_golden_vits(tag)
+    model = HiFiGAN_vits(**GOLDEN_VITS[tag])
+    model.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()}, strict=True)
+    model = model.to(DEV).eval()
+    x = torch.from_numpy(g["x"]).to(DEV)
+    for prec, tol in (("fp32", 2e-5), ("tc_f16", 5e-4)):
+        model.precision = prec
+        got = model(x).cpu().numpy()
+        assert got.shape == g["wav"].shape
+        assert np.abs(got - g["wav"]).max() <= tol, (prec, np.abs(got - g["wav"]).max())
+        if "g" in g:
+            cond = torch.from_numpy(g["g"]).to(DEV)
+            got = model(x, g=cond).cpu().numpy()
+            assert np.abs(got - g["wav_g"]).max() <= tol, (prec, np.abs(got - g["wav_g"]).max())
+            got2 = model(x, g=cond[:, :, 0]).cpu().numpy()            # [B, gin] is accepted too
+            np.testing.assert_array_equal(got, got2)
+    if "g" not in g:
+        with pytest.raises(AttributeError):                            # the reference has no `cond` module either
+            model(x, g=torch.zeros(x.shape[0], 4, 1, device=DEV))
+
+
+def test_hifigan_vits_decoder_size_matches_oracle():
+    """VITS decoder geometry (config/vits.json: inter_channels 192, 512 ch, rates 8.8.2.2, gin 256), CPU-checkable."""
+    from amphion_b200.vocoders import HiFiGAN_vits
+    args = dict(initial_channel=192, resblock="1", resblock_kernel_sizes=[3, 7, 11], resblock_dilation_sizes=[[1, 3, 5]] * 3,
+                upsample_rates=[8, 8, 2, 2], upsample_initial_channel=512, upsample_kernel_sizes=[16, 16, 4, 4],
+                gin_channels=256)
+    torch.manual_seed(6)
+    model = HiFiGAN_vits(**args).eval()
+    gen = torch.Generator().manual_seed(7)
+    x, cond = torch.randn(2, 192, 21, generator=gen), torch.randn(2, 256, 1, generator=gen)
+    want = og.hifigan_vits_forward(sd_numpy(model), args, x.numpy(), cond.numpy())
+    model = model.to(DEV)
+    got = model(x.to(DEV), g=cond.to(DEV)).cpu().numpy()
+    assert got.shape == (2, 1, 21 * 256)
+    assert np.abs(got - want).max() <= 1e-3, np.abs(got - want).max()

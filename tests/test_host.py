@@ -10,7 +10,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import GOLDEN_MODELS, GOLDEN_NSF, ROOT, load_golden
+from conftest import GOLDEN_MODELS, GOLDEN_NSF, GOLDEN_VITS, ROOT, load_golden, load_golden_vits
 from helpers import build_model, make_cfg
 
 
@@ -175,3 +175,19 @@ def test_wav_writer_roundtrip(tmp_path):
     from amphion_b200.io import save_audio
     with pytest.raises(RuntimeError):                    # no CPU fallback: the quantiser only exists as a CUDA kernel
         save_audio(tmp_path / "b.wav", np.zeros(16, np.float32), 16000)
+
+
+@pytest.mark.parametrize("tag,seed", [("a", 51), ("b", 52)])
+def test_hifigan_vits_module_matches_reference_layout(tag, seed):
+    from amphion_b200 import _capi
+    from amphion_b200.vocoders import HiFiGAN_vits
+    _, sd = load_golden_vits(tag)
+    torch.manual_seed(seed)
+    model = HiFiGAN_vits(**GOLDEN_VITS[tag])
+    msd = model.state_dict()
+    assert list(msd.keys()) == list(sd.keys())
+    for k, v in msd.items():
+        np.testing.assert_array_equal(v.numpy(), sd[k], err_msg=k)
+    h = model._ensure_handle()
+    names = [_capi.lib.ab_generator_tensor_name(h, i).decode() for i in range(_capi.lib.ab_generator_num_tensors(h))]
+    assert "conv_post.bias" not in names and ("cond.weight" in names) == (GOLDEN_VITS[tag]["gin_channels"] > 0)

@@ -3,7 +3,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import GOLDEN_MODELS, GOLDEN_NSF, load_golden
+from conftest import GOLDEN_MODELS, GOLDEN_NSF, GOLDEN_VITS, load_golden, load_golden_vits
 from oracle import generator as og
 from oracle import io as oio
 from oracle import mel as om
@@ -135,3 +135,12 @@ def test_save_audio_oracle_matches_reference():
     x = np.array([0.0, 0.5, -0.5, 1.0, -1.0, 1.5, -1.5, 1 / 32768, 1.5 / 32768, -1.5 / 32768, 0.49 / 32768, -0.51 / 32768],
                  np.float32)
     np.testing.assert_array_equal(oio.pcm16(x), [0, 16384, -16384, 32767, -32768, 32767, -32768, 1, 2, -1, 0, -1])
+
+
+@pytest.mark.parametrize("tag", sorted(GOLDEN_VITS))
+def test_hifigan_vits_oracle_matches_reference(tag):
+    g, sd = load_golden_vits(tag)
+    hp = GOLDEN_VITS[tag]
+    np.testing.assert_allclose(og.hifigan_vits_forward(sd, hp, g["x"]), g["wav"], atol=1e-6, rtol=0)
+    if "g" in g:
+        np.testing.assert_allclose(og.hifigan_vits_forward(sd, hp, g["x"], g["g"]), g["wav_g"], atol=1e-6, rtol=0)
