@@ -411,6 +411,7 @@ int launch_conv_transpose1d_fp32(const ConvTParams& p, cudaStream_t s) {
 namespace {
 constexpr int SN_WS = 120;                 // outputs per warp segment (30 lanes x 4)
 constexpr int SN_XS = 136;                 // xs[m] = xh[t0 - 8 + m]            (34 float4)
+constexpr int SN_XR = 3;                   // x windows in flight per warp (cp.async ring, two channels ahead)
 constexpr int SN_VS = 256;                 // vs[n] = vh[2*t0 - 7 + n]          (64 groups of 4 = 2 full rounds)
 constexpr int SN_TR = 8 * 32 * 2;          // image transposition: [8 ch][32 lanes] x 8 B, lane-private
 constexpr int WT = 8 * SN_WS;              // outputs per CTA tile (8 warps)
@@ -448,14 +449,18 @@ __device__ __forceinline__ void snake_segment(const SnakeParams& p, const float*
   }
   const int i0 = 2 * t0 - 7, imax = 2 * T - 1;
   const int tl = 4 * lane;
-  float4 nf0 = make_float4(0.f, 0.f, 0.f, 0.f), nf1 = nf0;   // FAST prefetch registers
-  float ne[5] = {0.f, 0.f, 0.f, 0.f, 0.f};                     // edge prefetch registers
-  auto fetch = [&](int c) {
+  float ne[5] = {0.f, 0.f, 0.f, 0.f, 0.f};                     // edge path: prefetch registers
+  // FAST: 16-byte cp.async straight into a 3-deep ring of windows, issued two channels ahead (DRAM latency under
+  // load exceeds one channel's compute); one commit group per channel, empty groups keep the count uniform
+  float* const xs_ring = xs;
+  auto fetch = [&](int c, int slot) {
     const float* xr = xb + (int64_t)c * T;
     if (FAST) {
-      const float4* x4 = reinterpret_cast<const float4*>(xr + t0 - 8);
-      nf0 = __ldg(x4 + lane);
-      if (lane < 2) nf1 = __ldg(x4 + 32 + lane);
+      const float* src = xr + t0 - 8;
+      const uint32_t dst = (uint32_t)__cvta_generic_to_shared(xs_ring + slot * SN_XS);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16u * lane), "l"(src + 4 * lane) : "memory");
+      if (lane < 2)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 512u + 16u * lane), "l"(src + 128 + 4 * lane) : "memory");
     } else {
 #pragma unroll
       for (int q = 0; q < 5; ++q) {
@@ -466,7 +471,15 @@ __device__ __forceinline__ void snake_segment(const SnakeParams& p, const float*
     }
   };
   const int c_first = c8 * 8;
-  if (c_first < C) fetch(c_first);
+  if (FAST) {
+#pragma unroll
+    for (int pre = 0; pre < 2; ++pre) {
+      if (c_first + pre < C) fetch(c_first + pre, pre);
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+  } else if (c_first < C) {
+    fetch(c_first, 0);
+  }
 #pragma unroll 1
   for (int cg = 0; cg < 8; ++cg) {
     const int c = c_first + cg;
@@ -475,19 +488,23 @@ __device__ __forceinline__ void snake_segment(const SnakeParams& p, const float*
       continue;
     }
     const float a = prm[cg][0], invb = prm[cg][1];
-    __syncwarp();
     if (FAST) {
-      *reinterpret_cast<float4*>(xs + 4 * lane) = nf0;
-      if (lane < 2) *reinterpret_cast<float4*>(xs + 128 + 4 * lane) = nf1;
+      asm volatile("cp.async.wait_group 1;" ::: "memory");   // this channel's window has landed (the next may be in flight)
+      __syncwarp();                                          // ... for every lane; also: phase 2 of cg-1 is done with vs
+      xs = xs_ring + (cg % SN_XR) * SN_XS;
+      // slot (cg + 2) % 3 was read in iteration cg - 1, which every lane has left
+      if (c + 2 < C && cg + 2 < 8) fetch(c + 2, (cg + 2) % SN_XR);
+      asm volatile("cp.async.commit_group;" ::: "memory");
     } else {
+      __syncwarp();
 #pragma unroll
       for (int q = 0; q < 5; ++q) {
         const int m = lane + 32 * q;
         if (m < SN_XS) xs[m] = ne[q];
       }
+      __syncwarp();
+      if (c + 1 < C && cg + 1 < 8) fetch(c + 1, 0);
     }
-    __syncwarp();
-    if (c + 1 < C && cg + 1 < 8) fetch(c + 1);
     // phase 1: 256 samples of the 2x-rate signal = 64 groups of 4 (two rounds).  Group j holds
     // v[i0 + 4j .. +3] = (u[2q+1], u[2q+2], u[2q+3], u[2q+4]), q = t0 - 4 + 2j, from xh[q-2 .. q+4] = xs[2j+2 .. 2j+8]
 #pragma unroll
@@ -586,7 +603,7 @@ __device__ __forceinline__ void snake_segment(const SnakeParams& p, const float*
 
 template <int BF16>
 __global__ void __launch_bounds__(NT, 3) activation1d_warp_kernel(SnakeParams p) {
-  __shared__ __align__(16) float win_all[8][SN_XS + SN_VS + SN_TR];
+  __shared__ __align__(16) float win_all[8][SN_XR * SN_XS + SN_VS + SN_TR];
   __shared__ float prm[8][2];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int t0 = blockIdx.x * WT + warp * SN_WS, c8 = blockIdx.y, b = blockIdx.z;
@@ -608,7 +625,7 @@ __global__ void __launch_bounds__(NT, 3) activation1d_warp_kernel(SnakeParams p)
   __syncthreads();
   if (t0 >= T) return;                           // warp-uniform; no block barriers below
   float* xs = win_all[warp];
-  float* vs = xs + SN_XS;
+  float* vs = xs + SN_XR * SN_XS;
   uint2* tr = reinterpret_cast<uint2*>(vs + SN_VS);
   const float* xb = p.x + (int64_t)b * p.C * T;
   const bool fast = t0 >= 8 && t0 + 128 <= T && (T & 3) == 0 && (reinterpret_cast<uintptr_t>(p.x) & 15) == 0 &&

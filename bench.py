@@ -330,6 +330,16 @@ def run_native(args, rank, local_rank, world):
                         whole_step=dict(tflops=samples_step / world * fps / (ms_step / 1e3) / 1e12,
                                         frac_of_tensor_peak=samples_step / world * fps / (ms_step / 1e3) / 1e12 / pk["tensor"]),
                         classes={k: dict(launches=v["launches"], ms=round(v["ms"], 3)) for k, v in prof.items()})
+        # DRAM traffic of the dominant kernel: measured once under ncu (profiles/r1_tc_traffic.json, same workload,
+        # batch and precision), per launch like `achieved`; null when no capture matches this configuration
+        roofline["algorithmic_bytes_per_launch"] = d["bytes"] / max(d["launches"], 1)
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r1_tc_traffic.json")))
+            if dom == "tc_conv" and args.precision == "tc_f16" and (tr["workload"], tr["batch"], tr["frames"]) == (args.workload, B, T):
+                roofline["traffic"] = tr["bytes_per_launch"]
+                roofline["traffic_source"] = "profiles/r1_tc_traffic.json (ncu dram__bytes_read+write, mean of the %d tc_conv launches of one forward)" % tr["launches"]
+        except (OSError, KeyError, ValueError):
+            pass
         cpu = None
         if world == 1 and not args.no_cpu_baseline and args.workload == "hifigan_v1":
             v, cores, dt, sample = cpu_oracle_samples_per_sec(T, batch=2, repeats=2)
