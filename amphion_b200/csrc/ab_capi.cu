@@ -585,9 +585,9 @@ static int forward_impl(ab_generator* g, const float* dev_mel, int64_t B, int64_
 
   // wide single conv on the streaming tensor-core kernel (operand image in)
   auto gs_conv = [&](const ConvRef& c, const uint16_t* ximg, float* y, int Tn, const float* residual,
-                     const float* acc_prev, float out_div) -> int {
+                     const float* acc_prev, float out_div, const float* x = nullptr, float pre_slope = 1.0f) -> int {
     GsParams p;
-    p.x = nullptr; p.pre_slope = 1.0f; p.mode = 0; p.u = 1; p.yimg = nullptr; p.img_slope = 1.0f;
+    p.x = x; p.pre_slope = pre_slope; p.mode = 0; p.u = 1; p.yimg = nullptr; p.img_slope = 1.0f;
     p.ximg = ximg; p.y = y; p.w = g->tcptr(c.w); p.bias = g->fptr(c.b); p.residual = residual; p.acc_prev = acc_prev;
     p.B = (int)B; p.Cin = c.cin; p.Cout = c.cout; p.T = Tn; p.k = c.k; p.d = c.d; p.out_div = out_div;
     p.precision = g->precision;
@@ -687,6 +687,17 @@ static int forward_impl(ab_generator* g, const float* dev_mel, int64_t B, int64_
             if (rc != AB_OK) return rc;
             cur_img = dst_img;
             if (stage_img) stage_img_written = true;
+          } else if (tc && g->slots[blk.c1[p].w].tc_kind == 3) {
+            // wide ResBlocks (C > 256, e.g. NSF-HiFiGAN's 384-channel stage): streaming kernel, fp32 in, lrelu in the loaders
+            if (pair) {
+              rc = gs_conv(blk.c1[p], nullptr, TMP, Tn, nullptr, nullptr, 1.0f, cur, 0.1f);
+              if (rc != AB_OK) return rc;
+              rc = gs_conv(blk.c2[p], nullptr, dst, Tn, cur, accp, div, TMP, 0.1f);
+            } else {
+              rc = gs_conv(blk.c1[p], nullptr, dst, Tn, cur, accp, div, cur, 0.1f);
+            }
+            if (rc != AB_OK) return rc;
+            cur_img = nullptr;
           } else if (pair) {
             rc = conv(blk.c1[p], cur, sb, sc, 1, TMP, Tn, 0.1f, nullptr, nullptr, 1.0f, 0);
             if (rc != AB_OK) return rc;
