@@ -68,7 +68,7 @@ struct TcGeom {
   long long* dbg;  // debug: per-CTA phase timestamps (AB_TC_DEBUG_TIMING=1), else nullptr
 };
 
-constexpr int DBG_BLOCKS = 2048, DBG_SLOTS = 8;
+constexpr int DBG_BLOCKS = 2048, DBG_SLOTS = 10;   // 0-5 phase stamps, 6 smid, 7 globaltimer, 8 weight-wait cycles, 9 A-wait cycles
 
 template <int WW, int MINB, int BF16>
 __global__ void __launch_bounds__(WW * 32 + 64, MINB) tc_conv_kernel(TcConvParams p, TcGeom g) {
@@ -121,6 +121,14 @@ __global__ void __launch_bounds__(WW * 32 + 64, MINB) tc_conv_kernel(TcConvParam
     while (clock64() - t0 < wait) __nanosleep(500);
   }
   stamp(0);
+  if (g.dbg != nullptr && threadIdx.x == 0 && blockIdx.x < DBG_BLOCKS) {   // debug: which SM, absolute time
+    uint32_t smid;
+    asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
+    g.dbg[blockIdx.x * DBG_SLOTS + 6] = smid;
+    long long gt;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
+    g.dbg[blockIdx.x * DBG_SLOTS + 7] = gt;
+  }
 
   if (warp < WW) {
     // ===================== worker warps =====================
@@ -382,15 +390,20 @@ __global__ void __launch_bounds__(WW * 32 + 64, MINB) tc_conv_kernel(TcConvParam
     const uint32_t kstepB = 2u * (uint32_t)g.Np;
     const uint32_t a16 = sA >> 4, w16 = sW >> 4, stage16 = g.stage_bytes >> 4;
     int it = 0;
+    long long wait_w = 0, wait_a = 0;   // debug: cycles the issuer spent waiting for weight stages / the operand tile
     for (int conv = 0; conv < p.nconv; ++conv) {
+      const long long ta = g.dbg ? clock64() : 0;
       mbar_wait(bar_aready, (uint32_t)conv & 1u, 30);
+      if (g.dbg) wait_a += clock64() - ta;
       tc_fence_after();
       const int dil = conv == 0 ? p.d1 : 1;
       for (int j = 0; j < p.k; ++j) {
         for (int kc = 0; kc < g.nkc; ++kc, ++it) {
           const int s = it % g.nstages;
           const uint32_t ph = (uint32_t)(it / g.nstages) & 1u;
+          const long long tw = g.dbg ? clock64() : 0;
           mbar_wait(bar_full(s), ph, 31);
+          if (g.dbg) wait_w += clock64() - tw;
           tc_fence_after();
           const bool two = nks_total - kc * 2 >= 2;
           uint32_t alo = desc_lo_sw32(a16 + (uint32_t)(kc * 2) * kstepA + (uint32_t)(j * dil) * 2u);
@@ -411,6 +424,10 @@ __global__ void __launch_bounds__(WW * 32 + 64, MINB) tc_conv_kernel(TcConvParam
       }
       if (elected) tc_commit(bar_accfull);
       __syncwarp();
+    }
+    if (g.dbg != nullptr && elected && blockIdx.x < DBG_BLOCKS) {
+      g.dbg[blockIdx.x * DBG_SLOTS + 8] = wait_w;
+      g.dbg[blockIdx.x * DBG_SLOTS + 9] = wait_a;
     }
     tc_fence_before();
   }
@@ -623,12 +640,24 @@ int launch_tc_conv(const TcConvParams& p, cudaStream_t s) {
     static std::vector<long long> h(DBG_BLOCKS * DBG_SLOTS);
     AB_CUDA_TRY(cudaMemcpy(h.data(), dbg_buf, sizeof(long long) * h.size(), cudaMemcpyDeviceToHost));
     const int nb = (int)std::min<int64_t>(grid, DBG_BLOCKS);
-    double ph[5] = {0, 0, 0, 0, 0};
+    if (const char* dump = getenv("AB_TC_DEBUG_DUMP")) {   // raw per-CTA records: block smid globaltimer t0..t5
+      if (FILE* f = fopen(dump, "a")) {
+        fprintf(f, "# launch C=%d k=%d d=%d nconv=%d dual=%d grid=%lld\n", p.C, p.k, p.d1, p.nconv, g.dual, (long long)grid);
+        for (int i = 0; i < nb; ++i) {
+          const long long* r = &h[(size_t)i * DBG_SLOTS];
+          fprintf(f, "%d %lld %lld %lld %lld %lld %lld %lld %lld\n", i, r[6], r[7], r[0], r[1], r[2], r[3], r[4], r[5]);
+        }
+        fclose(f);
+      }
+    }
+    double ph[5] = {0, 0, 0, 0, 0}, ww = 0, wa = 0;
     int cnt = 0;
     for (int i = 0; i < nb; ++i) {
       const long long* r = &h[(size_t)i * DBG_SLOTS];
       if (r[5] == 0) continue;
       ++cnt;
+      ww += (double)r[8];
+      wa += (double)r[9];
       ph[0] += (double)(r[1] - r[0]);
       if (p.nconv == 2) {
         ph[1] += (double)(r[2] - r[1]);
@@ -643,9 +672,9 @@ int launch_tc_conv(const TcConvParams& p, cudaStream_t s) {
       const double ideal = (double)g.m * (g.Np / 2.0) * (g.Np / 16.0) * p.k;   // cycles per conv at 8192 flop/clk/SM
       fprintf(stderr,
               "[tc_timing] C=%d k=%d d=%d nconv=%d dual=%d img=%d staged=%d m=%d V=%d tiles=%lld stages=%d | cycles: "
-              "prologue %.0f conv1 %.0f epi1 %.0f conv2 %.0f epi2 %.0f | ideal MMA/conv %.0f\n",
+              "prologue %.0f conv1 %.0f epi1 %.0f conv2 %.0f epi2 %.0f | ideal MMA/conv %.0f | issuer waited: weights %.0f operand tile %.0f\n",
               p.C, p.k, p.d1, p.nconv, g.dual, p.ximg != nullptr, g.staged, g.m, g.V, (long long)grid, g.nstages,
-              ph[0] / cnt, ph[1] / cnt, ph[2] / cnt, ph[3] / cnt, ph[4] / cnt, ideal);
+              ph[0] / cnt, ph[1] / cnt, ph[2] / cnt, ph[3] / cnt, ph[4] / cnt, ideal, ww / cnt, wa / cnt);
     }
   }
   return AB_OK;
