@@ -382,6 +382,33 @@ def test_generator_properties_at_scale(prec):
     assert torch.equal(wp[..., :far], wav[:1, :, :far])
 
 
+def test_config2_full_size_is_consistent_with_checked_sizes():
+    """BASELINE config 2 at its FULL size (HiFi-GAN V1, B=64, 80x1024 -> 64 x 262144 samples, default precision):
+    the CPU oracle cannot afford it (40 TFLOP), so it is tied to sizes the oracle does check through
+    size-independent properties: every row equals the same utterance run alone (B=1), a row equals its own
+    T=256 prefix run away from the right edge (tiling / padding locality), and a 1-utterance, 40-frame window
+    in the middle of the batch agrees with the oracle on its interior."""
+    hp = HP_V1
+    model = build_model("hifigan", hp, 80, seed=1234)
+    sd = sd_numpy(model)
+    model = model.to(DEV)
+    g = torch.Generator().manual_seed(0)
+    mel = torch.randn(64, 80, 1024, generator=g).to(DEV)
+    wav = model(mel)
+    assert wav.shape == (64, 1, 262144) and torch.isfinite(wav).all() and wav.abs().max() <= 1.0
+    for b in (0, 17, 63):
+        assert torch.equal(model(mel[b:b + 1])[0], wav[b])                        # batch independence at full size
+    prefix = model(mel[5:6, :, :256])
+    far = (256 - 40) * 256
+    assert torch.equal(prefix[..., :far], wav[5:6, :, :far])                      # right-edge locality (receptive field)
+    # oracle on a 72-frame window [480, 552) of utterance 33: interior 24 frames are free of edge effects
+    lo, hi = 480, 552
+    want = og.generator_forward("hifigan", sd, hp, mel[33:34, :, lo:hi].cpu().numpy())
+    got = wav[33:34, :, lo * 256: hi * 256].cpu().numpy()
+    mid = slice(24 * 256, 48 * 256)
+    assert np.abs(got[..., mid] - want[..., mid]).max() <= 1e-3, np.abs(got[..., mid] - want[..., mid]).max()
+
+
 def test_plumbing_matches_reference_fixture():
     from amphion_b200.vocoders import synthesis_audios, vocoder_inference
     kind, hp, g0, sd, model = golden_model("hifigan_rb1")
