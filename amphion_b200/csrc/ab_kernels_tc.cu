@@ -64,6 +64,7 @@ struct TcGeom {
   int stagger_groups, first_wave;   // first-wave CTAs start (blockIdx % groups) * stagger_cycles late so that the
   long long stagger_cycles;         // HBM-bound phases of identical tiles do not run in lock-step chip-wide
   float out_scale; // 1 / out_div (the reference divides, hifigan.py:214; <= 1 ulp apart)
+  int korder;      // MMA issue order within a weight stage: 1 = K-half outer / M-tile inner
   int skip;        // debug timing experiments (AB_TC_DEBUG_SKIP bitmask): 1 no fp32 y store, 2 no image store, 4 no residual loads
   long long* dbg;  // debug: per-CTA phase timestamps (AB_TC_DEBUG_TIMING=1), else nullptr
 };
@@ -409,14 +410,29 @@ __global__ void __launch_bounds__(WW * 32 + 64, MINB) tc_conv_kernel(TcConvParam
           uint32_t alo = desc_lo_sw32(a16 + (uint32_t)(kc * 2) * kstepA + (uint32_t)(j * dil) * 2u);
           const uint32_t blo = desc_lo_sw32(w16 + (uint32_t)s * stage16);
           const uint32_t acc0 = (j | kc) != 0 ? 1u : 0u;
-          uint32_t td = tmem;
-          for (int i = 0; i < g.m; ++i) {
-            if (elected) {
-              tc_mma_f16(td, hi | alo, hi | blo, g.idesc, acc0);
-              if (two) tc_mma_f16(td, hi | (alo + kstepA), hi | (blo + kstepB), g.idesc, 1u);
+          // K-half outer, M-tile inner: consecutive MMAs go to different accumulator tiles, so the second K half
+          // of a tile is issued m MMAs after the first instead of right behind it (accumulate dependency)
+          if (g.korder) {
+            for (int h = 0; h < (two ? 2 : 1); ++h) {
+              uint32_t ah = alo + (uint32_t)h * kstepA;
+              const uint32_t bh = blo + (uint32_t)h * kstepB;
+              uint32_t td = tmem;
+              for (int i = 0; i < g.m; ++i) {
+                if (elected) tc_mma_f16(td, hi | ah, hi | bh, g.idesc, h ? 1u : acc0);
+                ah += 256u;   // 128 rows x 32 B
+                td += (uint32_t)g.Np;
+              }
             }
-            alo += 256u;   // 128 rows x 32 B
-            td += (uint32_t)g.Np;
+          } else {
+            uint32_t td = tmem;
+            for (int i = 0; i < g.m; ++i) {
+              if (elected) {
+                tc_mma_f16(td, hi | alo, hi | blo, g.idesc, acc0);
+                if (two) tc_mma_f16(td, hi | (alo + kstepA), hi | (blo + kstepB), g.idesc, 1u);
+              }
+              alo += 256u;   // 128 rows x 32 B
+              td += (uint32_t)g.Np;
+            }
           }
           if (elected) tc_commit(bar_empty(s));
           __syncwarp();
@@ -553,6 +569,9 @@ int make_geom(const TcConvParams& p, TcGeom& g) {
   g.out_scale = 1.0f / p.out_div;
   static const int skip = [] { const char* e = getenv("AB_TC_DEBUG_SKIP"); return e ? atoi(e) : 0; }();
   g.skip = skip;
+  // measured (profiles/r1_tc_phase_timing_v9.txt): K-half-outer issue is 19 % faster at m = 8 and 7 % slower at m = 2
+  static const int korder = [] { const char* e = getenv("AB_TC_KORDER"); return e ? atoi(e) : 2; }();
+  g.korder = korder == 2 ? (g.m >= 4 ? 1 : 0) : korder;
   // stagger: period model = MMA issue time + HBM time of the tile at ~4.5 TB/s chip-wide
   static const int stag = [] { const char* e = getenv("AB_TC_STAGGER"); return e ? atoi(e) : 0; }();
   g.stagger_groups = stag;
@@ -603,8 +622,8 @@ int launch_tc_conv(const TcConvParams& p, cudaStream_t s) {
     AB_CUDA_TRY(cudaFuncSetAttribute(tc_conv_kernel<8, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_LIMIT));
     AB_CUDA_TRY(cudaFuncSetAttribute(tc_conv_kernel<4, 2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
     AB_CUDA_TRY(cudaFuncSetAttribute(tc_conv_kernel<4, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
-    AB_CUDA_TRY(cudaFuncSetAttribute(tc_conv_kernel<8, 2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
-    AB_CUDA_TRY(cudaFuncSetAttribute(tc_conv_kernel<8, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
+    AB_CUDA_TRY(cudaFuncSetAttribute(tc_conv_kernel<8, 2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_LIMIT));
+    AB_CUDA_TRY(cudaFuncSetAttribute(tc_conv_kernel<8, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_LIMIT));
     AB_CUDA_TRY(cudaFuncSetAttribute(tc_conv_kernel<4, 3, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 74 * 1024));
     AB_CUDA_TRY(cudaFuncSetAttribute(tc_conv_kernel<4, 3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 74 * 1024));
     configured = true;
@@ -612,7 +631,9 @@ int launch_tc_conv(const TcConvParams& p, cudaStream_t s) {
   const int64_t grid = (int64_t)p.B * g.tiles;
   if (grid > 0x7fffffffll) return fail(AB_ERR_UNSUPPORTED, "tc_conv: grid too large");
   // single mode: request > half of the SM's shared memory so exactly one CTA (512 TMEM columns) is resident
-  const uint32_t smem = g.dual ? g.smem_bytes : std::max<uint32_t>(g.smem_bytes, 120u * 1024u);
+  // debug: AB_TC_SOLO=1 keeps the half-tile geometry but lets only one CTA reside per SM (stand-alone phase times)
+  static const bool solo = [] { const char* e = getenv("AB_TC_SOLO"); return e && e[0] == '1'; }();
+  const uint32_t smem = (g.dual && !(solo && g.dual == 2)) ? g.smem_bytes : std::max<uint32_t>(g.smem_bytes, 120u * 1024u);
   static const bool dbg_on = [] { const char* e = getenv("AB_TC_DEBUG_TIMING"); return e && e[0] == '1'; }();
   static long long* dbg_buf = nullptr;
   if (dbg_on) {  // debug only: the one place the library allocates, never on the product path
