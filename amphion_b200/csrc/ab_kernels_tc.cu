@@ -71,6 +71,33 @@ struct TcGeom {
 
 constexpr int DBG_BLOCKS = 2048, DBG_SLOTS = 10;   // 0-5 phase stamps, 6 smid, 7 globaltimer, 8 weight-wait cycles, 9 A-wait cycles
 
+// MMAs of one weight stage (tap j, 32-channel K chunk), fully unrolled for M accumulator tiles.  The issuing
+// thread is the bottleneck of the MMA phases (a few extra instructions per MMA cost tens of percent), so the
+// per-MMA work is two uniform adds and the instruction itself: compile-time tile count, issue order and
+// accumulate flag.  KOUTER: K-half outer / M-tile inner (m consecutive MMAs share the B descriptor).
+template <int M, bool KOUTER, int FIRST>
+__device__ __forceinline__ void issue_stage(uint32_t elected, uint32_t tmem, uint32_t np, uint64_t hi, uint32_t alo,
+                                            uint32_t blo, uint32_t kstepA, uint32_t kstepB, uint32_t idesc, bool two) {
+  if (KOUTER) {
+#pragma unroll
+    for (int i = 0; i < M; ++i)
+      if (elected) tc_mma_f16_c<FIRST ? 0 : 1>(tmem + (uint32_t)i * np, hi | (alo + 256u * i), hi | blo, idesc);
+    if (two) {
+#pragma unroll
+      for (int i = 0; i < M; ++i)
+        if (elected) tc_mma_f16_c<1>(tmem + (uint32_t)i * np, hi | (alo + kstepA + 256u * i), hi | (blo + kstepB), idesc);
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < M; ++i) {
+      if (elected) {
+        tc_mma_f16_c<FIRST ? 0 : 1>(tmem + (uint32_t)i * np, hi | (alo + 256u * i), hi | blo, idesc);
+        if (two) tc_mma_f16_c<1>(tmem + (uint32_t)i * np, hi | (alo + kstepA + 256u * i), hi | (blo + kstepB), idesc);
+      }
+    }
+  }
+}
+
 template <int WW, int MINB, int BF16>
 __global__ void __launch_bounds__(WW * 32 + 64, MINB) tc_conv_kernel(TcConvParams p, TcGeom g) {
   constexpr int WORKERS = WW * 32;
@@ -410,9 +437,18 @@ __global__ void __launch_bounds__(WW * 32 + 64, MINB) tc_conv_kernel(TcConvParam
           uint32_t alo = desc_lo_sw32(a16 + (uint32_t)(kc * 2) * kstepA + (uint32_t)(j * dil) * 2u);
           const uint32_t blo = desc_lo_sw32(w16 + (uint32_t)s * stage16);
           const uint32_t acc0 = (j | kc) != 0 ? 1u : 0u;
-          // K-half outer, M-tile inner: consecutive MMAs go to different accumulator tiles, so the second K half
-          // of a tile is issued m MMAs after the first instead of right behind it (accumulate dependency)
-          if (g.korder) {
+          // unrolled issue sequences for the common tile counts (K-half outer from m = 4 up, see make_geom)
+          const bool first = acc0 == 0u;
+#define AB_ISSUE(MM, KO)                                                                                            \
+  if (first) issue_stage<MM, KO, 1>(elected, tmem, (uint32_t)g.Np, hi, alo, blo, kstepA, kstepB, g.idesc, two);     \
+  else issue_stage<MM, KO, 0>(elected, tmem, (uint32_t)g.Np, hi, alo, blo, kstepA, kstepB, g.idesc, two)
+          if (g.m == 2 && !g.korder) { AB_ISSUE(2, false); }
+          else if (g.m == 4 && g.korder) { AB_ISSUE(4, true); }
+          else if (g.m == 8 && g.korder) { AB_ISSUE(8, true); }
+          else if (g.m == 1 && !g.korder) { AB_ISSUE(1, false); }
+          else if (g.m == 16 && g.korder) { AB_ISSUE(16, true); }
+#undef AB_ISSUE
+          else if (g.korder) {
             for (int h = 0; h < (two ? 2 : 1); ++h) {
               uint32_t ah = alo + (uint32_t)h * kstepA;
               const uint32_t bh = blo + (uint32_t)h * kstepB;

@@ -71,6 +71,16 @@ __device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t adesc, uint
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// same with the accumulate flag as a compile-time constant: no register -> uniform-register move per MMA
+template <int ACC>
+__device__ __forceinline__ void tc_mma_f16_c(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "n"(ACC)
+      : "memory");
+}
 // Ampere-style async copies (LDGSTS): register-free, so the bytes in flight are not bounded by the
 // register file.  src_bytes = 0 zero-fills the 16-byte destination (used for out-of-range rows).
 __device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src, uint32_t src_bytes) {
