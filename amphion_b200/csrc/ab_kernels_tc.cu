@@ -425,55 +425,68 @@ __global__ void __launch_bounds__(WW * 32 + 64, MINB) tc_conv_kernel(TcConvParam
       if (g.dbg) wait_a += clock64() - ta;
       tc_fence_after();
       const int dil = conv == 0 ? p.d1 : 1;
-      for (int j = 0; j < p.k; ++j) {
-        for (int kc = 0; kc < g.nkc; ++kc, ++it) {
-          const int s = it % g.nstages;
-          const uint32_t ph = (uint32_t)(it / g.nstages) & 1u;
-          const long long tw = g.dbg ? clock64() : 0;
-          mbar_wait(bar_full(s), ph, 31);
-          if (g.dbg) wait_w += clock64() - tw;
-          tc_fence_after();
-          const bool two = nks_total - kc * 2 >= 2;
-          uint32_t alo = desc_lo_sw32(a16 + (uint32_t)(kc * 2) * kstepA + (uint32_t)(j * dil) * 2u);
-          const uint32_t blo = desc_lo_sw32(w16 + (uint32_t)s * stage16);
-          const uint32_t acc0 = (j | kc) != 0 ? 1u : 0u;
-          // unrolled issue sequences for the common tile counts (K-half outer from m = 4 up, see make_geom)
-          const bool first = acc0 == 0u;
-#define AB_ISSUE(MM, KO)                                                                                            \
-  if (first) issue_stage<MM, KO, 1>(elected, tmem, (uint32_t)g.Np, hi, alo, blo, kstepA, kstepB, g.idesc, two);     \
-  else issue_stage<MM, KO, 0>(elected, tmem, (uint32_t)g.Np, hi, alo, blo, kstepA, kstepB, g.idesc, two)
-          if (g.m == 2 && !g.korder) { AB_ISSUE(2, false); }
-          else if (g.m == 4 && g.korder) { AB_ISSUE(4, true); }
-          else if (g.m == 8 && g.korder) { AB_ISSUE(8, true); }
-          else if (g.m == 1 && !g.korder) { AB_ISSUE(1, false); }
-          else if (g.m == 16 && g.korder) { AB_ISSUE(16, true); }
-#undef AB_ISSUE
-          else if (g.korder) {
-            for (int h = 0; h < (two ? 2 : 1); ++h) {
-              uint32_t ah = alo + (uint32_t)h * kstepA;
-              const uint32_t bh = blo + (uint32_t)h * kstepB;
-              uint32_t td = tmem;
-              for (int i = 0; i < g.m; ++i) {
-                if (elected) tc_mma_f16(td, hi | ah, hi | bh, g.idesc, h ? 1u : acc0);
-                ah += 256u;   // 128 rows x 32 B
-                td += (uint32_t)g.Np;
-              }
-            }
-          } else {
+      // the stage loop, specialised once per conv on (tile count, issue order): the issuing thread bounds the MMA
+      // phases, so nothing that is constant over the conv is re-evaluated per weight stage
+      auto run_conv = [&](auto issue_first, auto issue_rest, bool have_first) {
+        for (int j = 0; j < p.k; ++j) {
+          for (int kc = 0; kc < g.nkc; ++kc, ++it) {
+            const int s = it % g.nstages;
+            const uint32_t ph = (uint32_t)(it / g.nstages) & 1u;
+            const long long tw = g.dbg ? clock64() : 0;
+            mbar_wait(bar_full(s), ph, 31);
+            if (g.dbg) wait_w += clock64() - tw;
+            tc_fence_after();
+            const bool two = nks_total - kc * 2 >= 2;
+            const uint32_t alo = desc_lo_sw32(a16 + (uint32_t)(kc * 2) * kstepA + (uint32_t)(j * dil) * 2u);
+            const uint32_t blo = desc_lo_sw32(w16 + (uint32_t)s * stage16);
+            if (have_first && (j | kc) == 0) issue_first(alo, blo, two);
+            else issue_rest(alo, blo, two);
+            if (elected) tc_commit(bar_empty(s));
+            __syncwarp();
+          }
+        }
+      };
+      auto generic = [&](uint32_t alo, uint32_t blo, bool two, uint32_t acc0) {
+        if (g.korder) {
+          for (int h = 0; h < (two ? 2 : 1); ++h) {
+            uint32_t ah = alo + (uint32_t)h * kstepA;
+            const uint32_t bh = blo + (uint32_t)h * kstepB;
             uint32_t td = tmem;
             for (int i = 0; i < g.m; ++i) {
-              if (elected) {
-                tc_mma_f16(td, hi | alo, hi | blo, g.idesc, acc0);
-                if (two) tc_mma_f16(td, hi | (alo + kstepA), hi | (blo + kstepB), g.idesc, 1u);
-              }
-              alo += 256u;   // 128 rows x 32 B
+              if (elected) tc_mma_f16(td, hi | ah, hi | bh, g.idesc, h ? 1u : acc0);
+              ah += 256u;   // 128 rows x 32 B
               td += (uint32_t)g.Np;
             }
           }
-          if (elected) tc_commit(bar_empty(s));
-          __syncwarp();
+        } else {
+          uint32_t td = tmem;
+          for (int i = 0; i < g.m; ++i) {
+            if (elected) {
+              tc_mma_f16(td, hi | alo, hi | blo, g.idesc, acc0);
+              if (two) tc_mma_f16(td, hi | (alo + kstepA), hi | (blo + kstepB), g.idesc, 1u);
+            }
+            alo += 256u;
+            td += (uint32_t)g.Np;
+          }
         }
-      }
+      };
+#define AB_RUN(MM, KO)                                                                                                     \
+  run_conv([&](uint32_t alo, uint32_t blo, bool two) {                                                                     \
+             issue_stage<MM, KO, 1>(elected, tmem, (uint32_t)g.Np, hi, alo, blo, kstepA, kstepB, g.idesc, two);            \
+           },                                                                                                              \
+           [&](uint32_t alo, uint32_t blo, bool two) {                                                                     \
+             issue_stage<MM, KO, 0>(elected, tmem, (uint32_t)g.Np, hi, alo, blo, kstepA, kstepB, g.idesc, two);            \
+           },                                                                                                              \
+           true)
+      if (g.m == 2 && !g.korder) AB_RUN(2, false);
+      else if (g.m == 4 && g.korder) AB_RUN(4, true);
+      else if (g.m == 8 && g.korder) AB_RUN(8, true);
+      else if (g.m == 1 && !g.korder) AB_RUN(1, false);
+      else if (g.m == 16 && g.korder) AB_RUN(16, true);
+      else
+        run_conv([&](uint32_t alo, uint32_t blo, bool two) { generic(alo, blo, two, 0u); },
+                 [&](uint32_t alo, uint32_t blo, bool two) { generic(alo, blo, two, 1u); }, true);
+#undef AB_RUN
       if (elected) tc_commit(bar_accfull);
       __syncwarp();
     }
