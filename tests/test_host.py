@@ -191,3 +191,34 @@ def test_hifigan_vits_module_matches_reference_layout(tag, seed):
     h = model._ensure_handle()
     names = [_capi.lib.ab_generator_tensor_name(h, i).decode() for i in range(_capi.lib.ab_generator_num_tensors(h))]
     assert "conv_post.bias" not in names and ("cond.weight" in names) == (GOLDEN_VITS[tag]["gin_channels"] > 0)
+
+
+def test_f0_padding_and_argument_checks_run_before_any_device_work():
+    from oracle import generator as og
+    from amphion_b200.util import pad_f0_to_tensors
+    from amphion_b200.vocoders import HiFiGAN_vits
+    f0s = [torch.arange(n, dtype=torch.float32) + 1 for n in (5, 9, 2, 7, 3)]
+    for bs in (None, 2, 5):
+        got = pad_f0_to_tensors(f0s, bs)
+        want = og.pad_f0s([f.numpy() for f in f0s], bs)
+        assert len(got) == len(want)
+        for a, b in zip(got, want):
+            np.testing.assert_array_equal(a.numpy(), b)
+    assert pad_f0_to_tensors([], 4) == []
+    kind, hp, n_mel = GOLDEN_NSF
+    model = build_model(kind, hp, n_mel, seed=1)
+    mel = torch.zeros(2, n_mel, 6)
+    with pytest.raises(TypeError):
+        model(mel, None)
+    with pytest.raises(ValueError):
+        model(mel, torch.zeros(3, 6))                       # batch mismatch
+    with pytest.raises(NotImplementedError):
+        model(mel, torch.zeros(2, 4))                       # source shorter than the mel (nsfhifigan.py:264-268)
+    vits = HiFiGAN_vits(**GOLDEN_VITS["b"])                  # gin_channels == 0
+    with pytest.raises(AttributeError):
+        vits(torch.zeros(1, 12, 4), g=torch.zeros(1, 3, 1))
+    vits_g = HiFiGAN_vits(**GOLDEN_VITS["a"])
+    with pytest.raises(ValueError):
+        vits_g(torch.zeros(2, 24, 4), g=torch.zeros(2, 7, 1))   # wrong gin
+    with pytest.raises(NotImplementedError):
+        vits_g(torch.zeros(2, 24, 4), g=torch.zeros(2, 10, 4))  # time-varying conditioning
