@@ -1,8 +1,10 @@
 // C ABI of libamphion_b200: handles, parameter arena, forward plans.
 // See include/amphion_b200.h for the contract and the reference citations.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -94,6 +96,7 @@ struct ab_generator {
   int precision = AB_PREC_FP32;
   int hop = 1;
   int launches = 0;
+  int rb_mode = 2;          // "resblock_fusion" option; AB_RB in the environment sets the initial value
 
   ConvRef conv_pre, conv_post;
   int cond_w = -1, cond_b = -1;   // HiFiGAN_vits global conditioning (hifigan.py:424-425)
@@ -228,6 +231,7 @@ int ab_generator_create(const ab_generator_config* cfg, ab_generator** out) {
   if (rc != AB_OK) return rc;
   ab_generator* g = new ab_generator();
   g->cfg = *cfg;
+  if (const char* e = getenv("AB_RB")) g->rb_mode = std::min(std::max(atoi(e), 0), 3);
   const bool big = cfg->kind == AB_GEN_BIGVGAN;
   const bool has_beta = cfg->activation == AB_ACT_SNAKEBETA;
   const int c0 = cfg->upsample_initial_channel;
@@ -442,7 +446,7 @@ size_t stage_max_elems(const ab_generator* g, int64_t B, int64_t T) {
 size_t ab_generator_workspace_bytes(const ab_generator* g, int64_t B, int64_t T) {
   if (!g || B <= 0 || T <= 0) return 0;
   return NBUF * align_up(stage_max_elems(g, B, T) * sizeof(float), 256) +
-         NIMG * align_up(stage_max_image_bytes(g, B, T), 256);
+         NIMG * align_up(stage_max_image_bytes(g, B, T), 256) + align_up(rb_scratch_bytes(), 256);
 }
 
 int ab_generator_last_launches(const ab_generator* g) { return g ? g->launches : 0; }
@@ -451,6 +455,16 @@ int ab_generator_set_profiling(ab_generator* g, int32_t enable) {
   if (!g) return fail(AB_ERR_ARG, "set_profiling: null handle");
   g->profiling = enable != 0;
   return AB_OK;
+}
+
+int ab_generator_set_option(ab_generator* g, const char* key, int32_t value) {
+  if (!g || !key) return fail(AB_ERR_ARG, "set_option: null argument");
+  if (strcmp(key, "resblock_fusion") == 0) {
+    if (value < 0 || value > 3) return fail(AB_ERR_ARG, "set_option: resblock_fusion must be 0..3 (got %d)", value);
+    g->rb_mode = value;
+    return AB_OK;
+  }
+  return fail(AB_ERR_ARG, "set_option: unknown key '%s'", key);
 }
 
 int ab_generator_get_profile(ab_generator* g, ab_profile_entry* out, int32_t max_entries, int32_t* n_out) {
@@ -499,6 +513,7 @@ static int forward_impl(ab_generator* g, const float* dev_mel, int64_t B, int64_
   for (int i = 0; i < NIMG; ++i)
     img[i] = reinterpret_cast<uint16_t*>(static_cast<char*>(dev_workspace) + NBUF * bufsz + i * imgsz);
   uint16_t *U16 = img[0], *P16[2] = {img[1], img[2]}, *R16 = img[3];
+  float* rb_scratch = reinterpret_cast<float*>(static_cast<char*>(dev_workspace) + NBUF * bufsz + NIMG * imgsz);
   const uint16_t* r_img = nullptr;   // operand image of lrelu(stage input, 0.1) when the previous stage emitted it
   float *R[2] = {buf[0], buf[1]}, *U = buf[2], *P[2] = {buf[3], buf[4]}, *TMP = buf[5], *ACT = buf[6];
   const bool big = g->cfg.kind == AB_GEN_BIGVGAN;
@@ -583,6 +598,38 @@ static int forward_impl(ab_generator* g, const float* dev_mel, int64_t B, int64_
     return r;
   };
 
+  // a chain of `np` (c1[, c2]) pairs of one ResBlock on the persistent fused kernel (ab_kernels_rb.cu)
+  auto rb_chain = [&](const BlockRef& blk, int p0, int np, const float* x, const uint16_t* ximg, float* y, int C, int Tn,
+                      const float* acc_prev, float out_div, uint16_t* yimg) -> int {
+    RbParams rp;
+    memset(&rp, 0, sizeof(rp));
+    const bool pair = !blk.c2.empty();
+    rp.x = x; rp.ximg = ximg; rp.y = y; rp.acc_prev = acc_prev; rp.yimg = yimg;
+    rp.npairs = np; rp.nconv = pair ? 2 : 1;
+    for (int q = 0; q < np; ++q) {
+      rp.dil[q] = blk.c1[p0 + q].d;
+      rp.w[q * rp.nconv] = g->tcptr(blk.c1[p0 + q].w);
+      rp.bias[q * rp.nconv] = g->fptr(blk.c1[p0 + q].b);
+      if (pair) {
+        rp.w[q * 2 + 1] = g->tcptr(blk.c2[p0 + q].w);
+        rp.bias[q * 2 + 1] = g->fptr(blk.c2[p0 + q].b);
+      }
+    }
+    rp.B = (int)B; rp.C = C; rp.T = Tn; rp.k = blk.k;
+    rp.slope = 0.1f; rp.img_slope = 0.1f; rp.out_div = out_div; rp.precision = g->precision;
+    rp.scratch = rb_scratch;
+    ++launches;
+    const double el = (double)B * C * Tn;
+    prof_begin(0, 2.0 * el * C * blk.k * rp.nconv * np,
+               4.0 * (el * (2 + (acc_prev != nullptr)) + (double)rp.nconv * np * C * C * blk.k));
+    const int r = launch_rb(rp, st);
+    prof_end();
+    return r;
+  };
+  // AB_RB: 0 = per-pair kernel of ab_kernels_tc.cu only, 1 = persistent kernel one pair per launch,
+  //        2 (default) = persistent kernel, whole block fused when the cost model prefers it, 3 = always fused
+  const int rb_mode = g->rb_mode;
+
   // wide single conv on the streaming tensor-core kernel (operand image in)
   auto gs_conv = [&](const ConvRef& c, const uint16_t* ximg, float* y, int Tn, const float* residual,
                      const float* acc_prev, float out_div, const float* x = nullptr, float pre_slope = 1.0f) -> int {
@@ -665,6 +712,22 @@ static int forward_impl(ab_generator* g, const float* dev_mel, int64_t B, int64_
       const uint16_t* cur_img = u_img;
       int pp = 0;
       const int nd = (int)blk.dil.size();
+      const bool blk_rb = use_tc && !big && rb_mode > 0 && rb_supported(C, blk.k) && tc_conv_supported(C, blk.k);
+      if (blk_rb && rb_mode >= 2 && nd <= AB_RB_MAX_PAIRS) {
+        // whole block in one launch when the halo recompute costs less than the per-pair HBM round trips
+        const int ncv = blk.c2.empty() ? 1 : 2;
+        const double fused = rb_cost_per_row(C, blk.k, blk.dil.data(), nd, ncv);
+        double split = 0.0;
+        for (int p = 0; p < nd; ++p) split += rb_cost_per_row(C, blk.k, &blk.dil[p], 1, ncv);
+        if (fused > 0.0 && (rb_mode == 3 || fused < split)) {
+          const bool stage_img = j == nk - 1 && i + 1 < g->stages.size();
+          rc = rb_chain(blk, 0, nd, U, u_img, Rout, C, Tn, j > 0 ? Rout : nullptr, j == nk - 1 ? (float)nk : 1.0f,
+                        stage_img ? R16 : nullptr);
+          if (rc != AB_OK) return rc;
+          if (stage_img) stage_img_written = true;
+          continue;
+        }
+      }
       for (int p = 0; p < nd; ++p) {
         const bool last = p == nd - 1;
         float* dst = last ? Rout : P[pp];
@@ -681,7 +744,12 @@ static int forward_impl(ab_generator* g, const float* dev_mel, int64_t B, int64_
         // wide layers (C > 256): streaming kernel, BigVGAN only (it needs the activation as an operand image)
         const bool blk_gs = tc && big && !blk_tc && g->slots[blk.c1[0].w].tc_kind == 3;
         if (!big) {
-          if (blk_tc) {
+          if (blk_rb) {
+            rc = rb_chain(blk, p, 1, cur, cur_img, dst, C, Tn, accp, div, dst_img);
+            if (rc != AB_OK) return rc;
+            cur_img = dst_img;
+            if (stage_img) stage_img_written = true;
+          } else if (blk_tc) {
             rc = tc_convs(blk.c1[p], pair ? &blk.c2[p] : nullptr, cur, dst, C, Tn, 0.1f, 0.1f, cur, accp, div,
                           cur_img, dst_img);
             if (rc != AB_OK) return rc;

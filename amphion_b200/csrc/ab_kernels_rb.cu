@@ -1,0 +1,609 @@
+// Persistent fused ResBlock kernel (sm_100a): a whole ResBlock1 / ResBlock2 chain per time tile.
+//
+//   for p in pairs:  x <- x + c2_p(lrelu(c1_p(lrelu(x, .1)) + b1_p, .1)) + b2_p     (hifigan.py:93-100)
+//                or  x <- x + c_p(lrelu(x, .1)) + b_p                                (hifigan.py:139-144)
+//   y = (x_L + branch_sum) / out_div                                                 (hifigan.py:208-214)
+//
+// One CTA per SM walks over pairs of time tiles (two "slots").  Per slot: one fp16/bf16 operand buffer in
+// shared memory (SWIZZLE_32B K-major rows, time = row, a tap shift = a descriptor row offset, as in
+// ab_kernels_tc.cu), one fp32 accumulator set in TMEM (256 columns) and one fp32 scratch tile in global memory
+// that holds the residual stream x_p between pairs (thread-private, L2-resident: never read by another thread).
+// The chain runs on R = 128*m rows with the block's halo on both sides and is recomputed in the halo, so the
+// block reads its input once and writes its output once.  Roles:
+//   warp 0       weight producer: cp.async.bulk (TMA 1-D) of pre-swizzled weight stages into an mbarrier ring
+//   warp 1       MMA issuer: convs alternate between the two slots
+//   warps 2..17  epilogue / loader warps: while the tensor pipe runs conv s of one slot they run the epilogue
+//                of conv s of the other slot (TMEM -> +bias, lrelu, cvt -> operand buffer; or + residual ->
+//                scratch / output) and load the next tile
+// so the tensor pipe never waits for an epilogue that is shorter than a conv.
+#include <stdlib.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "ab_tc.cuh"
+#include "ab_tc_issue.cuh"
+#include "ab_tc_ptx.cuh"
+
+namespace ab {
+
+using namespace tcx;
+
+namespace {
+
+constexpr int RB_EPI_WARPS = 16;
+constexpr int RB_EPI_THREADS = RB_EPI_WARPS * 32;
+constexpr int RB_THREADS = RB_EPI_THREADS + 64;
+constexpr int RB_MAX_STAGES = 8;
+constexpr int RB_SLOT_COLS = 256;               // TMEM columns per slot
+constexpr uint32_t RB_SMEM_LIMIT = 226 * 1024;      // + 1 KB of static shared memory
+
+struct RbGeom {
+  int Np, nkc, m, R, G, RB;     // padded channels, 32-channel K chunks, M tiles, rows, guard rows, buffer rows
+  int Hlo, V;                   // row of the first valid output, valid outputs per tile
+  int tiles, ntiles;            // per sequence, total
+  int nsteps;                   // convs per tile
+  int kcs;                      // 32-channel chunks per weight stage
+  int nstages;
+  uint32_t stage_bytes, chunk_bytes;
+  uint32_t off_buf1, off_w, off_bias, off_bar, smem_bytes;
+  uint32_t idesc;
+  int korder;
+  float out_scale;
+  long long* dbg;
+};
+
+constexpr int DBG_SLOTS = 8;   // 0 total, 1 mma wait operand, 2 mma wait weights, 3 epi wait acc, 4 producer wait, 5 tiles
+
+// ---- epilogue pieces (one item = 32 rows x 16 channels of one M tile) ---------------------------------------
+template <int BF16>
+__device__ __forceinline__ void store_operand16(uint8_t* buf, int RBrows, int ch, int brow, const float (&v)[16]) {
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    uint4 q;
+    q.x = pack2t<BF16>(v[8 * h + 0], v[8 * h + 1]);
+    q.y = pack2t<BF16>(v[8 * h + 2], v[8 * h + 3]);
+    q.z = pack2t<BF16>(v[8 * h + 4], v[8 * h + 5]);
+    q.w = pack2t<BF16>(v[8 * h + 6], v[8 * h + 7]);
+    *reinterpret_cast<uint4*>(buf + unit_offset(RBrows, ch * 2 + h, brow)) = q;
+  }
+}
+
+template <int BF16>
+__global__ void __launch_bounds__(RB_THREADS, 1) rb_kernel(RbParams p, RbGeom g) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t s0 = smem_u32(smem);
+  float* bias_s = reinterpret_cast<float*>(smem + g.off_bias);   // [nsteps][Np]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + g.off_bar);
+  const uint32_t bar0 = smem_u32(bars);
+  auto bar_full = [&](int s) { return bar0 + 8u * s; };
+  auto bar_empty = [&](int s) { return bar0 + 8u * (RB_MAX_STAGES + s); };
+  auto bar_opnd = [&](int s) { return bar0 + 8u * (2 * RB_MAX_STAGES + s); };
+  auto bar_acc = [&](int s) { return bar0 + 8u * (2 * RB_MAX_STAGES + 2 + s); };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * RB_MAX_STAGES + 4);
+  // per-step parameters are indexed dynamically: keep them in shared memory, not in a local copy of the params
+  __shared__ const void* w_s[2 * AB_RB_MAX_PAIRS];
+  __shared__ const float* b_s[2 * AB_RB_MAX_PAIRS];
+  __shared__ int dil_s[AB_RB_MAX_PAIRS];
+  if (threadIdx.x < 2 * AB_RB_MAX_PAIRS) {
+#pragma unroll
+    for (int i = 0; i < 2 * AB_RB_MAX_PAIRS; ++i)
+      if ((int)threadIdx.x == i) { w_s[i] = p.w[i]; b_s[i] = p.bias[i]; }
+#pragma unroll
+    for (int i = 0; i < AB_RB_MAX_PAIRS; ++i)
+      if ((int)threadIdx.x == i) dil_s[i] = p.dil[i];
+  }
+  __syncthreads();
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < g.nstages; ++s) {
+      mbar_init(bar_full(s), 1);
+      mbar_init(bar_empty(s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(bar_opnd(s), RB_EPI_THREADS);
+      mbar_init(bar_acc(s), 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    fence_proxy_async();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  // biases of every conv of the chain; guard rows of both operand buffers are zeroed once (never written later)
+  for (int i = threadIdx.x; i < g.nsteps * g.Np; i += RB_THREADS) {
+    const int st = i / g.Np, c = i - st * g.Np;
+    const float* src = b_s[st];
+    bias_s[i] = (src != nullptr && c < p.C) ? __ldg(src + c) : 0.f;
+  }
+  {
+    const int c8n = g.Np >> 3;
+    const int ng = g.RB - g.R;   // guard rows below + above (+ padding)
+    for (int u = threadIdx.x; u < 2 * c8n * ng; u += RB_THREADS) {
+      const int s = u / (c8n * ng);
+      const int r = u - s * (c8n * ng);
+      const int c8 = r / ng;
+      int row = r - c8 * ng;
+      if (row >= g.G) row += g.R;
+      *reinterpret_cast<uint4*>(smem + (uint32_t)s * g.off_buf1 + unit_offset(g.RB, c8, row)) = make_uint4(0, 0, 0, 0);
+    }
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const long long t_start = g.dbg ? clock64() : 0;
+  const int npairs_total = (g.ntiles + 1) >> 1;
+
+  if (warp >= 2) {
+    // ===================== epilogue / loader warps =====================
+    const int ew = warp - 2;
+    const int q4 = warp & 3;        // TMEM lane quarter this warp may access
+    const int grp = ew >> 2;        // 0..3: items are dealt round-robin to the four warps of a quarter
+    const int et = threadIdx.x - 64;
+    const int nch = g.Np >> 4;
+    const int c8n = g.Np >> 3;
+    const int nitems = g.m * nch;
+    long long wait_acc = 0;
+    int ntile_done = 0;
+
+    // tile load: operand buffer rows [0, R) <- lrelu(x)[b, :, T0 - Hlo + row] as 16-bit K-major units
+    auto load_tile = [&](int slot, int tile_id) {
+      const int b = tile_id / g.tiles, tl = tile_id - b * g.tiles;
+      const int tbase = tl * g.V - g.Hlo;
+      uint8_t* buf = smem + (uint32_t)slot * g.off_buf1;
+      if (p.ximg != nullptr) {
+        const uint32_t sb = s0 + (uint32_t)slot * g.off_buf1;
+        const uint16_t* xb = p.ximg + (size_t)b * c8n * p.T * 8;
+        for (int u = et; u < c8n * g.R; u += RB_EPI_THREADS) {
+          const int c8 = u / g.R, row = u - c8 * g.R;
+          const int t = tbase + row;
+          const bool ok = t >= 0 && t < p.T;
+          cp_async16(sb + unit_offset(g.RB, c8, row + g.G),
+                     ok ? (const void*)(xb + ((size_t)c8 * p.T + (size_t)t) * 8) : (const void*)xb, ok ? 16u : 0u);
+        }
+      } else {
+        const float* xb = p.x + (int64_t)b * p.C * p.T;
+        for (int u = et; u < c8n * g.R; u += RB_EPI_THREADS) {
+          const int c8 = u / g.R, row = u - c8 * g.R;
+          const int t = tbase + row;
+          const bool ok = t >= 0 && t < p.T;
+          float v[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const int c = c8 * 8 + e;
+            v[e] = (ok && c < p.C) ? lrelu(__ldg(xb + (int64_t)c * p.T + t), p.slope) : 0.f;
+          }
+          uint4 q;
+          q.x = pack2t<BF16>(v[0], v[1]);
+          q.y = pack2t<BF16>(v[2], v[3]);
+          q.z = pack2t<BF16>(v[4], v[5]);
+          q.w = pack2t<BF16>(v[6], v[7]);
+          *reinterpret_cast<uint4*>(buf + unit_offset(g.RB, c8, row + g.G)) = q;
+        }
+      }
+    };
+    auto publish_operand = [&](int slot) {
+      cp_async_wait_all();
+      fence_proxy_async();
+      tc_fence_before();
+      mbar_arrive(bar_opnd(slot));
+    };
+
+    uint32_t ph_acc = 0u;   // phase parity of bar_acc per slot (bit s)
+    {
+      const int q0 = blockIdx.x;
+      if (q0 < npairs_total) {
+        const bool two = 2 * q0 + 1 < g.ntiles;
+        load_tile(0, 2 * q0);
+        cp_async_commit();
+        if (two) load_tile(1, 2 * q0 + 1);
+        cp_async_commit();
+        cp_async_wait_group<1>();
+        fence_proxy_async();
+        tc_fence_before();
+        mbar_arrive(bar_opnd(0));
+        if (two) publish_operand(1);
+      }
+    }
+    for (int q = blockIdx.x; q < npairs_total; q += gridDim.x) {
+      const int nact = (2 * q + 1 < g.ntiles) ? 2 : 1;
+      const int qn = q + gridDim.x;
+      for (int step = 0; step < g.nsteps; ++step) {
+        const int pair = step / p.nconv;
+        const bool is_e1 = p.nconv == 2 && (step & 1) == 0;
+        const bool final_step = step == g.nsteps - 1;
+        const float* bias_c = bias_s + step * g.Np;
+        for (int slot = 0; slot < nact; ++slot) {
+          const int tile_id = 2 * q + slot;
+          const int b = tile_id / g.tiles, tl = tile_id - b * g.tiles;
+          const int tbase = tl * g.V - g.Hlo;
+          uint8_t* buf = smem + (uint32_t)slot * g.off_buf1;
+          const uint32_t tslot = tmem + (uint32_t)(slot * RB_SLOT_COLS) + ((uint32_t)(q4 * 32) << 16);
+          {
+            const long long t0 = g.dbg ? clock64() : 0;
+            mbar_wait(bar_acc(slot), (ph_acc >> slot) & 1u, 40 + slot);
+            if (g.dbg) wait_acc += clock64() - t0;
+          }
+          ph_acc ^= 1u << slot;
+          tc_fence_after();
+          if (is_e1) {
+            // ---- intermediate = lrelu(conv1 + b1) -> operand buffer, zero outside [0, T) (conv2's zero padding)
+            for (int n = grp; n < nitems; n += 4) {
+              const int i = n / nch, ch = n - i * nch;
+              const int row = i * 128 + q4 * 32 + lane;
+              const int t = tbase + row;
+              const bool inr = t >= 0 && t < p.T;
+              uint32_t r[16];
+              tc_ld16(tslot + (uint32_t)(i * g.Np + ch * 16), r);
+              tc_wait_ld();
+              float v[16];
+#pragma unroll
+              for (int e = 0; e < 16; ++e) {
+                const float a = __uint_as_float(r[e]) + bias_c[ch * 16 + e];
+                v[e] = inr ? lrelu(a, p.slope) : 0.f;
+              }
+              store_operand16<BF16>(buf, g.RB, ch, row + g.G, v);
+            }
+            publish_operand(slot);
+          } else if (!final_step) {
+            // ---- x_{p+1} = conv + b + x_p -> scratch (fp32), lrelu(x_{p+1}) -> operand buffer
+            float* scr = p.scratch + ((size_t)blockIdx.x * 2 + slot) * ((size_t)g.R * g.Np);
+            const float* xb = p.x + (int64_t)b * p.C * p.T;
+            for (int n = grp; n < nitems; n += 4) {
+              const int i = n / nch, ch = n - i * nch;
+              const int row = i * 128 + q4 * 32 + lane;
+              const int t = tbase + row;
+              const bool inr = t >= 0 && t < p.T;
+              float* sp = scr + (size_t)(ch * 16) * g.R + row;
+              float res[16];
+              if (pair == 0) {
+                const float* xp = xb + (int64_t)(ch * 16) * p.T + t;
+#pragma unroll
+                for (int e = 0; e < 16; ++e) res[e] = (inr && ch * 16 + e < p.C) ? __ldg(xp + (int64_t)e * p.T) : 0.f;
+              } else {
+#pragma unroll
+                for (int e = 0; e < 16; ++e) res[e] = sp[(size_t)e * g.R];
+              }
+              uint32_t r[16];
+              tc_ld16(tslot + (uint32_t)(i * g.Np + ch * 16), r);
+              tc_wait_ld();
+              float v[16];
+#pragma unroll
+              for (int e = 0; e < 16; ++e) {
+                float a = __uint_as_float(r[e]) + bias_c[ch * 16 + e];
+                a += res[e];
+                sp[(size_t)e * g.R] = a;
+                v[e] = inr ? lrelu(a, p.slope) : 0.f;
+              }
+              store_operand16<BF16>(buf, g.RB, ch, row + g.G, v);
+            }
+            publish_operand(slot);
+          } else {
+            // ---- last conv of the chain: y = ((conv + b) + x_p + branch_sum) / out_div (+ operand image of
+            // lrelu(y, img_slope)); the operand buffer is free, so the next tile's load is issued first
+            const int next_tile = 2 * qn + slot;
+            const bool have_next = qn < npairs_total && next_tile < g.ntiles;
+            if (have_next) load_tile(slot, next_tile);
+            const float* scr = p.scratch ? p.scratch + ((size_t)blockIdx.x * 2 + slot) * ((size_t)g.R * g.Np) : nullptr;
+            const int64_t bCT = (int64_t)b * p.C * p.T;
+            for (int n = grp; n < nitems; n += 4) {
+              const int i = n / nch, ch = n - i * nch;
+              const int row = i * 128 + q4 * 32 + lane;
+              const int t = tbase + row;
+              const bool ok = row >= g.Hlo && row < g.Hlo + g.V && t < p.T;
+              const int64_t off0 = bCT + (int64_t)(ch * 16) * p.T + t;
+              float res[16], acp[16];
+              if (pair == 0) {
+#pragma unroll
+                for (int e = 0; e < 16; ++e) res[e] = (ok && ch * 16 + e < p.C) ? __ldg(p.x + off0 + (int64_t)e * p.T) : 0.f;
+              } else {
+                const float* sp = scr + (size_t)(ch * 16) * g.R + row;
+#pragma unroll
+                for (int e = 0; e < 16; ++e) res[e] = sp[(size_t)e * g.R];
+              }
+              if (p.acc_prev != nullptr) {
+#pragma unroll
+                for (int e = 0; e < 16; ++e) acp[e] = (ok && ch * 16 + e < p.C) ? p.acc_prev[off0 + (int64_t)e * p.T] : 0.f;
+              }
+              uint32_t r[16];
+              tc_ld16(tslot + (uint32_t)(i * g.Np + ch * 16), r);
+              tc_wait_ld();
+              float v[16];
+#pragma unroll
+              for (int e = 0; e < 16; ++e) {
+                float a = __uint_as_float(r[e]) + bias_c[ch * 16 + e];
+                a += res[e];
+                if (p.acc_prev != nullptr) a += acp[e];
+                a *= g.out_scale;
+                v[e] = a;
+                if (ok && ch * 16 + e < p.C) p.y[off0 + (int64_t)e * p.T] = a;
+              }
+              if (p.yimg != nullptr && ok) {
+                uint16_t* yi = p.yimg + (((size_t)b * c8n + (size_t)ch * 2) * p.T + (size_t)t) * 8;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                  uint4 qv;
+                  qv.x = pack2t<BF16>(lrelu(v[8 * h + 0], p.img_slope), lrelu(v[8 * h + 1], p.img_slope));
+                  qv.y = pack2t<BF16>(lrelu(v[8 * h + 2], p.img_slope), lrelu(v[8 * h + 3], p.img_slope));
+                  qv.z = pack2t<BF16>(lrelu(v[8 * h + 4], p.img_slope), lrelu(v[8 * h + 5], p.img_slope));
+                  qv.w = pack2t<BF16>(lrelu(v[8 * h + 6], p.img_slope), lrelu(v[8 * h + 7], p.img_slope));
+                  *reinterpret_cast<uint4*>(yi + (size_t)h * p.T * 8) = qv;
+                }
+              }
+            }
+            ++ntile_done;
+            if (have_next) publish_operand(slot);
+            else tc_fence_before();
+          }
+        }
+      }
+    }
+    if (g.dbg != nullptr && threadIdx.x == 64) {
+      g.dbg[blockIdx.x * DBG_SLOTS + 0] = clock64() - t_start;
+      g.dbg[blockIdx.x * DBG_SLOTS + 3] = wait_acc;
+      g.dbg[blockIdx.x * DBG_SLOTS + 5] = ntile_done;
+    }
+  } else if (warp == 0) {
+    // ===================== weight producer =====================
+    if (lane == 0) {
+      const int groups = g.nkc / g.kcs;          // weight stages per tap
+      const int per_conv = p.k * groups;
+      int it = 0;
+      long long wait_e = 0;
+      for (int q = blockIdx.x; q < npairs_total; q += gridDim.x) {
+        const int nact = (2 * q + 1 < g.ntiles) ? 2 : 1;
+        for (int step = 0; step < g.nsteps; ++step) {
+          const uint8_t* wsrc = static_cast<const uint8_t*>(w_s[step]);
+          for (int slot = 0; slot < nact; ++slot) {
+            for (int l = 0; l < per_conv; ++l, ++it) {
+              const int s = it % g.nstages;
+              const uint32_t ph = (uint32_t)(it / g.nstages) & 1u;
+              const long long t0 = g.dbg ? clock64() : 0;
+              mbar_wait(bar_empty(s), ph ^ 1u, 20);
+              if (g.dbg) wait_e += clock64() - t0;
+              mbar_arrive_expect_tx(bar_full(s), g.stage_bytes);
+              bulk_g2s(s0 + g.off_w + (uint32_t)s * g.stage_bytes, wsrc + (size_t)l * g.stage_bytes, g.stage_bytes,
+                       bar_full(s));
+            }
+          }
+        }
+      }
+      if (g.dbg != nullptr) g.dbg[blockIdx.x * DBG_SLOTS + 4] = wait_e;
+    }
+  } else {
+    // ===================== MMA issuer =====================
+    const uint32_t elected = elect_one_sync();
+    const int nks_total = g.Np >> 4;
+    const uint64_t hi = desc_hi_sw32();
+    const uint32_t kstepA = 2u * (uint32_t)g.RB;
+    const uint32_t kstepB = 2u * (uint32_t)g.Np;
+    const uint32_t w16 = (s0 + g.off_w) >> 4, stage16 = g.stage_bytes >> 4, chunk16 = g.chunk_bytes >> 4;
+    const int groups = g.nkc / g.kcs;
+    const int c = (p.k - 1) >> 1;
+    uint32_t ph_opnd = 0u;
+    int it = 0;
+    long long wait_o = 0, wait_w = 0;
+    for (int q = blockIdx.x; q < npairs_total; q += gridDim.x) {
+      const int nact = (2 * q + 1 < g.ntiles) ? 2 : 1;
+      for (int step = 0; step < g.nsteps; ++step) {
+        const int pair = step / p.nconv;
+        const int dil = (p.nconv == 2 && (step & 1)) ? 1 : dil_s[pair];
+        for (int slot = 0; slot < nact; ++slot) {
+          {
+            const long long t0 = g.dbg ? clock64() : 0;
+            mbar_wait(bar_opnd(slot), (ph_opnd >> slot) & 1u, 30 + slot);
+            if (g.dbg) wait_o += clock64() - t0;
+          }
+          ph_opnd ^= 1u << slot;
+          tc_fence_after();
+          const uint32_t a16 = (s0 + (uint32_t)slot * g.off_buf1) >> 4;
+          const uint32_t td = tmem + (uint32_t)(slot * RB_SLOT_COLS);
+          auto run_conv = [&](auto issue_first, auto issue_rest) {
+            for (int j = 0; j < p.k; ++j) {
+              const uint32_t arow = (uint32_t)(g.G + (j - c) * dil) * 2u;
+              for (int kg = 0; kg < groups; ++kg, ++it) {
+                const int s = it % g.nstages;
+                const uint32_t ph = (uint32_t)(it / g.nstages) & 1u;
+                const long long t0 = g.dbg ? clock64() : 0;
+                mbar_wait(bar_full(s), ph, 31);
+                if (g.dbg) wait_w += clock64() - t0;
+                tc_fence_after();
+                for (int kk = 0; kk < g.kcs; ++kk) {
+                  const int kc = kg * g.kcs + kk;
+                  const bool two = nks_total - kc * 2 >= 2;
+                  const uint32_t alo = desc_lo_sw32(a16 + (uint32_t)(kc * 2) * kstepA + arow);
+                  const uint32_t blo = desc_lo_sw32(w16 + (uint32_t)s * stage16 + (uint32_t)kk * chunk16);
+                  if ((j | kc) == 0) issue_first(alo, blo, two);
+                  else issue_rest(alo, blo, two);
+                }
+                if (elected) tc_commit(bar_empty(s));
+                __syncwarp();
+              }
+            }
+          };
+          auto generic = [&](uint32_t alo, uint32_t blo, bool two, uint32_t acc0) {
+            for (int h = 0; h < (two ? 2 : 1); ++h) {
+              uint32_t ah = alo + (uint32_t)h * kstepA;
+              const uint32_t bh = blo + (uint32_t)h * kstepB;
+              uint32_t tdd = td;
+              for (int i = 0; i < g.m; ++i) {
+                if (elected) tc_mma_f16(tdd, hi | ah, hi | bh, g.idesc, h ? 1u : acc0);
+                ah += 256u;
+                tdd += (uint32_t)g.Np;
+              }
+            }
+          };
+#define AB_RUN(MM, KO)                                                                                            \
+  run_conv([&](uint32_t alo, uint32_t blo, bool two) {                                                            \
+             issue_stage<MM, KO, 1>(elected, td, (uint32_t)g.Np, hi, alo, blo, kstepA, kstepB, g.idesc, two);     \
+           },                                                                                                     \
+           [&](uint32_t alo, uint32_t blo, bool two) {                                                            \
+             issue_stage<MM, KO, 0>(elected, td, (uint32_t)g.Np, hi, alo, blo, kstepA, kstepB, g.idesc, two);     \
+           })
+          if (g.m == 2 && !g.korder) AB_RUN(2, false);
+          else if (g.m == 4 && g.korder) AB_RUN(4, true);
+          else if (g.m == 8 && g.korder) AB_RUN(8, true);
+          else if (g.m == 1 && !g.korder) AB_RUN(1, false);
+          else if (g.m == 16 && g.korder) AB_RUN(16, true);
+          else
+            run_conv([&](uint32_t alo, uint32_t blo, bool two) { generic(alo, blo, two, 0u); },
+                     [&](uint32_t alo, uint32_t blo, bool two) { generic(alo, blo, two, 1u); });
+#undef AB_RUN
+          if (elected) tc_commit(bar_acc(slot));
+          __syncwarp();
+        }
+      }
+    }
+    if (g.dbg != nullptr && elected) {
+      g.dbg[blockIdx.x * DBG_SLOTS + 1] = wait_o;
+      g.dbg[blockIdx.x * DBG_SLOTS + 2] = wait_w;
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+  }
+}
+
+int rb_round_up(int x, int a) { return (x + a - 1) / a * a; }
+
+// halo (one side) of a chain of `npairs` pairs
+int rb_halo(int k, const int* dil, int npairs, int nconv) {
+  const int c = (k - 1) / 2;
+  int h = 0;
+  for (int i = 0; i < npairs; ++i) h += c * (dil[i] + (nconv == 2 ? 1 : 0));
+  return h;
+}
+
+int rb_make_geom(const RbParams& p, RbGeom& g) {
+  if (p.C <= 0 || rb_round_up(p.C, 16) > 128) return fail(AB_ERR_UNSUPPORTED, "rb: C=%d not in [1,128]", p.C);
+  if (p.k <= 0 || !(p.k & 1) || p.k > 31) return fail(AB_ERR_UNSUPPORTED, "rb: need odd k <= 31");
+  if (p.npairs < 1 || p.npairs > AB_RB_MAX_PAIRS || (p.nconv != 1 && p.nconv != 2)) return fail(AB_ERR_ARG, "rb: bad chain");
+  g.Np = rb_round_up(p.C, 16);
+  g.nkc = (g.Np + 31) / 32;
+  g.m = std::min(RB_SLOT_COLS / g.Np, 16);
+  g.R = 128 * g.m;
+  const int c = (p.k - 1) / 2;
+  int dmax = 1;
+  for (int i = 0; i < p.npairs; ++i) {
+    if (p.dil[i] <= 0) return fail(AB_ERR_ARG, "rb: dilation must be positive");
+    dmax = std::max(dmax, p.dil[i]);
+  }
+  g.G = c * dmax;
+  g.RB = rb_round_up(g.R + 2 * g.G, 8);
+  const int H = rb_halo(p.k, p.dil, p.npairs, p.nconv);
+  g.Hlo = rb_round_up(H, 4);
+  g.V = (g.R - g.Hlo - H) / 4 * 4;
+  if (g.V < 32) return fail(AB_ERR_UNSUPPORTED, "rb: halo %d leaves no room in a %d-row tile", H, g.R);
+  g.tiles = (p.T + g.V - 1) / g.V;
+  const int64_t nt = (int64_t)p.B * g.tiles;
+  if (nt > 0x3fffffffll) return fail(AB_ERR_UNSUPPORTED, "rb: too many tiles");
+  g.ntiles = (int)nt;
+  g.nsteps = p.npairs * p.nconv;
+  g.chunk_bytes = (uint32_t)g.Np * 64u;
+  // weight stage = kcs 32-channel chunks of one tap: >= 8 MMAs per stage keeps the issuer's per-stage overhead small
+  static const int kcs_pref = [] { const char* e = getenv("AB_RB_KCS"); return e ? atoi(e) : 0; }();
+  g.kcs = 1;
+  if ((g.nkc % 2) == 0 && g.m * 2 < 8) g.kcs = 2;
+  if (kcs_pref > 0 && (g.nkc % kcs_pref) == 0) g.kcs = kcs_pref;
+  g.stage_bytes = g.chunk_bytes * (uint32_t)g.kcs;
+  const uint32_t buf_bytes = (uint32_t)g.RB * (uint32_t)g.Np * 2u;
+  g.off_buf1 = (buf_bytes + 1023u) & ~1023u;
+  g.off_w = (g.off_buf1 + buf_bytes + 1023u) & ~1023u;
+  const uint32_t tail = (uint32_t)g.nsteps * g.Np * 4u + 8u * (2 * RB_MAX_STAGES + 4) + 32u;
+  if (g.off_w + 2u * g.stage_bytes + tail > RB_SMEM_LIMIT) return fail(AB_ERR_UNSUPPORTED, "rb: C=%d k=%d does not fit shared memory", p.C, p.k);
+  g.nstages = std::min<int>((RB_SMEM_LIMIT - g.off_w - tail) / g.stage_bytes, RB_MAX_STAGES);
+  g.off_bias = g.off_w + (uint32_t)g.nstages * g.stage_bytes;
+  g.off_bar = (g.off_bias + (uint32_t)g.nsteps * g.Np * 4u + 15u) & ~15u;
+  g.smem_bytes = g.off_bar + 8u * (2 * RB_MAX_STAGES + 4) + 16u;
+  const uint32_t fmt = p.precision == AB_PREC_TC_BF16 ? 1u : 0u;
+  g.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(g.Np >> 3) << 17) | ((128u >> 4) << 24);
+  g.korder = g.m >= 4 ? 1 : 0;
+  g.out_scale = 1.0f / p.out_div;
+  g.dbg = nullptr;
+  return AB_OK;
+}
+
+}  // namespace
+
+bool rb_supported(int C, int k) { return C > 0 && rb_round_up(C, 16) <= 128 && (k & 1) && k <= 31; }
+
+size_t rb_scratch_bytes() { return (size_t)148 * 2 * (size_t)(RB_SLOT_COLS * 128) * sizeof(float); }
+
+// Modelled cycles per output row of a chain (SS-mode operand law): used to choose between one fused
+// launch per block and one launch per pair.  Returns 0 when the geometry is not served.
+double rb_cost_per_row(int C, int k, const int* dil, int npairs, int nconv) {
+  if (!rb_supported(C, k)) return 0.0;
+  const int Np = rb_round_up(C, 16), m = std::min(RB_SLOT_COLS / Np, 16), R = 128 * m;
+  const int H = rb_halo(k, dil, npairs, nconv);
+  const int V = (R - rb_round_up(H, 4) - H) / 4 * 4;
+  if (V < 32) return 0.0;
+  const double mma_row = (double)k * (Np / 16.0) * (64.0 + Np / 2.0) / 128.0;      // per conv and computed row
+  const double mma = mma_row * nconv * npairs * (double)R / V;
+  const double hbm = Np * 12.0 / 25.0 * (double)R / V;                              // ~25 B/clk/SM of HBM bandwidth
+  const double epi = (nconv * npairs) * 0.9 * Np / 16.0 * (double)R / V;            // ~0.9 cycles per row and 16 channels
+  return std::max(std::max(mma, hbm), epi);
+}
+
+int launch_rb(const RbParams& p, cudaStream_t s) {
+  if (!p.x || !p.y) return fail(AB_ERR_ARG, "rb: null argument");
+  if (p.B <= 0 || p.T <= 0) return fail(AB_ERR_ARG, "rb: bad shape");
+  if (p.precision != AB_PREC_TC_F16 && p.precision != AB_PREC_TC_BF16) return fail(AB_ERR_ARG, "rb: bad precision");
+  RbGeom g;
+  int rc = rb_make_geom(p, g);
+  if (rc != AB_OK) return rc;
+  for (int i = 0; i < g.nsteps; ++i)
+    if (!p.w[i]) return fail(AB_ERR_ARG, "rb: missing weight image %d", i);
+  if (p.npairs > 1 && !p.scratch) return fail(AB_ERR_ARG, "rb: a fused chain needs the scratch buffer");
+  int dev = 0;
+  AB_CUDA_TRY(cudaGetDevice(&dev));
+  static bool configured[64] = {};
+  if (dev < 64 && !configured[dev]) {
+    AB_CUDA_TRY(cudaFuncSetAttribute(rb_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RB_SMEM_LIMIT));
+    AB_CUDA_TRY(cudaFuncSetAttribute(rb_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RB_SMEM_LIMIT));
+    configured[dev] = true;
+  }
+  static int nsm = 0;
+  if (!nsm) AB_CUDA_TRY(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
+  const int npairs_total = (g.ntiles + 1) / 2;
+  const int grid = std::min(std::min(nsm, 148), npairs_total);
+  // > half of the SM's shared memory: exactly one CTA (all 512 TMEM columns) per SM
+  const uint32_t smem = std::max<uint32_t>(g.smem_bytes, 120u * 1024u);
+  static const bool dbg_on = [] { const char* e = getenv("AB_RB_DEBUG_TIMING"); return e && e[0] == '1'; }();
+  static long long* dbg_buf = nullptr;
+  if (dbg_on) {   // debug only: the one place this file allocates
+    if (!dbg_buf) AB_CUDA_TRY(cudaMalloc(&dbg_buf, sizeof(long long) * 148 * DBG_SLOTS));
+    AB_CUDA_TRY(cudaMemsetAsync(dbg_buf, 0, sizeof(long long) * 148 * DBG_SLOTS, s));
+    g.dbg = dbg_buf;
+  }
+  if (p.precision == AB_PREC_TC_BF16) rb_kernel<1><<<grid, RB_THREADS, smem, s>>>(p, g);
+  else rb_kernel<0><<<grid, RB_THREADS, smem, s>>>(p, g);
+  AB_LAUNCH_CHECK("rb_kernel");
+  if (dbg_on) {
+    AB_CUDA_TRY(cudaStreamSynchronize(s));
+    std::vector<long long> h(148 * DBG_SLOTS);
+    AB_CUDA_TRY(cudaMemcpy(h.data(), dbg_buf, sizeof(long long) * h.size(), cudaMemcpyDeviceToHost));
+    double a[DBG_SLOTS] = {};
+    for (int i = 0; i < grid; ++i)
+      for (int j = 0; j < DBG_SLOTS; ++j) a[j] += (double)h[(size_t)i * DBG_SLOTS + j] / grid;
+    const double ideal = (double)g.m * (g.Np / 2.0) * (g.Np / 16.0) * p.k * g.nsteps * a[5];   // 8192 flop/clk/SM
+    const double law = (double)g.m * (64.0 + g.Np / 2.0) * (g.Np / 16.0) * p.k * g.nsteps * a[5];
+    fprintf(stderr,
+            "[rb_timing] C=%d k=%d d=%d,%d,%d npairs=%d nconv=%d m=%d R=%d V=%d tiles=%d grid=%d stages=%dx%uB | per CTA: "
+            "total %.0f cycles, %.1f tiles | MMA ideal %.0f law %.0f | issuer waits: operand %.0f weights %.0f | "
+            "epilogue waits acc %.0f | producer waits %.0f\n",
+            p.C, p.k, p.dil[0], p.npairs > 1 ? p.dil[1] : 0, p.npairs > 2 ? p.dil[2] : 0, p.npairs, p.nconv, g.m, g.R, g.V,
+            g.ntiles, grid, g.nstages, g.stage_bytes, a[0], a[5], ideal, law, a[1], a[2], a[3], a[4]);
+  }
+  return AB_OK;
+}
+
+}  // namespace ab

@@ -80,6 +80,33 @@ int launch_gc_pack_weight(const float* w_t, void* image, int mode, int cin, int 
                           int precision, cudaStream_t s);
 int launch_gemmconv(const GcParams& p, cudaStream_t s);
 
+
+// Persistent fused ResBlock chain (ab_kernels_rb.cu): npairs x nconv k-tap convs with the residual stream kept
+// on chip / in a thread-private L2-resident scratch, C <= 128.
+//   for p < npairs:  x <- x + conv[p][1](lrelu(conv[p][0](lrelu(x, slope), dil[p]) + b, slope), 1) + b   (nconv == 2)
+//                    x <- x + conv[p][0](lrelu(x, slope), dil[p]) + b                                      (nconv == 1)
+//   y = (x + acc_prev) / out_div ; yimg = cvt(lrelu(y, img_slope))
+constexpr int AB_RB_MAX_PAIRS = 3;
+struct RbParams {
+  const float* x;          // contiguous [B, C, T] fp32 (block input = first residual)
+  const uint16_t* ximg;    // nullable: operand image of lrelu(x, slope), [B][Np/8][T][8]
+  float* y;                // contiguous [B, C, T] fp32
+  const float* acc_prev;   // nullable (may alias y)
+  uint16_t* yimg;          // nullable
+  const void* w[2 * AB_RB_MAX_PAIRS];      // tc weight images, step = pair * nconv + conv
+  const float* bias[2 * AB_RB_MAX_PAIRS];  // nullable entries
+  int dil[AB_RB_MAX_PAIRS];
+  int npairs, nconv;
+  int B, C, T, k;
+  float slope, img_slope, out_div;
+  int precision;
+  float* scratch;          // rb_scratch_bytes() bytes; required when npairs > 1
+};
+bool rb_supported(int C, int k);
+size_t rb_scratch_bytes();
+double rb_cost_per_row(int C, int k, const int* dil, int npairs, int nconv);
+int launch_rb(const RbParams& p, cudaStream_t s);
+
 int tc_max_channels();
 bool tc_conv_supported(int C, int k);
 size_t tc_weight_image_bytes(int cin, int cout, int k);

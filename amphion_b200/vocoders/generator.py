@@ -203,6 +203,10 @@ class NativeGenerator(nn.Module):
             self.last_launches = lib.ab_generator_last_launches(h)
         return wav
 
+    def set_option(self, key: str, value: int):
+        """Execution-plan knob of the C ABI (`ab_generator_set_option`), e.g. ("resblock_fusion", 0..3)."""
+        _capi.check(_capi.lib.ab_generator_set_option(self._ensure_handle(), key.encode(), int(value)), "set_option")
+
     # ---- per-kernel-class device timing (bench.py roofline) ------------------------
     def set_profiling(self, enable: bool):
         _capi.check(_capi.lib.ab_generator_set_profiling(self._ensure_handle(), int(enable)), "set_profiling")

@@ -146,6 +146,11 @@ typedef struct ab_profile_entry {
   double bytes;   /* compulsory fp32 tensor reads+writes of the launch + its weights once */
 } ab_profile_entry;
 int ab_generator_set_profiling(ab_generator* g, int32_t enable);
+/* Execution-plan options (no reference counterpart; tuning / test knobs, results stay within the stated tolerance):
+ *   "resblock_fusion": 0 = one launch per (c1, c2) pair on the per-tile kernel, 1 = persistent kernel with one
+ *   pair per launch, 2 (default) = persistent kernel, a whole ResBlock per launch when the cost model prefers
+ *   it, 3 = always a whole ResBlock per launch.  Returns AB_ERR_ARG for an unknown key / value. */
+int ab_generator_set_option(ab_generator* g, const char* key, int32_t value);
 int ab_generator_get_profile(ab_generator* g, ab_profile_entry* out, int32_t max_entries, int32_t* n_out);
 
 /* ------------------------------------------------------------------------

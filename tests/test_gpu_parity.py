@@ -593,3 +593,53 @@ def test_hifigan_vits_decoder_size_matches_oracle():
     got = model(x.to(DEV), g=cond.to(DEV)).cpu().numpy()
     assert got.shape == (2, 1, 21 * 256)
     assert np.abs(got - want).max() <= 1e-3, np.abs(got - want).max()
+
+
+# ---- persistent fused ResBlock kernel (ab_kernels_rb.cu): execution-plan modes -------------------------------
+def _fusion_outputs(model, mel, modes):
+    outs = {}
+    for mode in modes:
+        model.set_option("resblock_fusion", mode)
+        outs[mode] = model(mel)
+    model.set_option("resblock_fusion", 2)
+    return outs
+
+
+@pytest.mark.parametrize("B,T", [(2, 40), (3, 150), (1, 37)])
+def test_resblock_fusion_modes_agree_on_v1(B, T):
+    """HiFi-GAN V1 (stages of 256/128/64/32 channels): the per-pair kernel (0), the persistent kernel one pair per
+    launch (1), the cost-model plan (2) and whole-block fusion with halo recompute (3) run the same arithmetic in
+    the same order, so they must agree to the last bit; T=150 gives several tiles per sequence and an odd tile
+    count, T=37 a ragged single tile."""
+    model = build_model("hifigan", HP_V1, 80, seed=4321).to(DEV)
+    mel = torch.randn(B, 80, T, generator=torch.Generator().manual_seed(T)).to(DEV)
+    outs = _fusion_outputs(model, mel, (0, 1, 2, 3))
+    for mode in (1, 2, 3):
+        assert torch.isfinite(outs[mode]).all()
+        diff = (outs[mode] - outs[0]).abs().max().item()
+        assert diff == 0.0, (mode, diff)
+
+
+@pytest.mark.parametrize("name", ["hifigan_rb1", "hifigan_rb2"])
+@pytest.mark.parametrize("mode", [0, 1, 3])
+def test_resblock_fusion_modes_match_reference_fixture(name, mode):
+    """ResBlock1 and ResBlock2 (single conv per residual step) fixtures through every plan, incl. bf16."""
+    kind, hp, g, sd, model = golden_model(name)
+    model = model.to(DEV)
+    model.set_option("resblock_fusion", mode)
+    for prec, tol in (("tc_f16", 5e-4), ("tc_bf16", 4e-3)):
+        model.precision = prec
+        wav = model(torch.from_numpy(g["mel"]).to(DEV)).cpu().numpy()
+        assert np.abs(wav - g["wav"]).max() <= tol, (prec, mode, np.abs(wav - g["wav"]).max())
+
+
+def test_resblock_fusion_odd_channels_and_wide_kernel():
+    """Channel counts that are not multiples of 32 (K chunk of 16 left over, generic issue path) and a kernel /
+    dilation set whose fused halo does not fit (falls back to one pair per launch), against the CPU oracle."""
+    hp = dict(resblock="1", upsample_rates=[4, 2], upsample_kernel_sizes=[8, 4], upsample_initial_channel=96,
+              resblock_kernel_sizes=[3, 13], resblock_dilation_sizes=[[1, 2, 4], [1, 7, 9]])
+    model, mel, want = _full_size_case("hifigan", hp, 20, 2, 300, seed=11)
+    for mode in (0, 1, 3):
+        model.set_option("resblock_fusion", mode)
+        got = model(mel.to(DEV)).cpu().numpy()
+        assert np.abs(got - want).max() <= 1e-3, (mode, np.abs(got - want).max())
