@@ -97,6 +97,7 @@ struct ab_generator {
   int hop = 1;
   int launches = 0;
   int rb_mode = 2;          // "resblock_fusion" option; AB_RB in the environment sets the initial value
+  std::vector<cudaEvent_t> tail_events;   // ab_generator_set_tail_events: consumed by the next forward
 
   ConvRef conv_pre, conv_post;
   int cond_w = -1, cond_b = -1;   // HiFiGAN_vits global conditioning (hifigan.py:424-425)
@@ -454,6 +455,16 @@ int ab_generator_last_launches(const ab_generator* g) { return g ? g->launches :
 int ab_generator_set_profiling(ab_generator* g, int32_t enable) {
   if (!g) return fail(AB_ERR_ARG, "set_profiling: null handle");
   g->profiling = enable != 0;
+  return AB_OK;
+}
+
+int ab_generator_set_tail_events(ab_generator* g, void* const* events, int32_t n) {
+  if (!g || n < 0 || (n > 0 && !events)) return fail(AB_ERR_ARG, "set_tail_events: bad argument");
+  g->tail_events.clear();
+  for (int i = 0; i < n; ++i) {
+    if (!events[i]) return fail(AB_ERR_ARG, "set_tail_events: null event %d", i);
+    g->tail_events.push_back(static_cast<cudaEvent_t>(events[i]));
+  }
   return AB_OK;
 }
 
@@ -817,10 +828,25 @@ static int forward_impl(ab_generator* g, const float* dev_mel, int64_t B, int64_
   if (big) {
     rc = snake(g->act_post, xin, ACT, cin, Tn);
     if (rc != AB_OK) return rc;
-    rc = conv(g->conv_post, ACT, sb, sc, 1, dev_wav, Tn, 1.0f, nullptr, nullptr, 1.0f, 1);
-  } else {
-    rc = conv(g->conv_post, xin, sb, sc, 1, dev_wav, Tn, 0.01f, nullptr, nullptr, 1.0f, 1);
+    xin = ACT;
   }
+  // conv_post in contiguous batch chunks, an event after each (ab_generator_set_tail_events): the caller's
+  // final gather of chunk i then runs under conv_post of chunk i+1
+  const int nchunk = g->tail_events.empty() ? 1 : (int)std::min<int64_t>((int64_t)g->tail_events.size(), B);
+  const int64_t Bfull = B;
+  for (int ci = 0; ci < nchunk; ++ci) {
+    const int64_t b0 = Bfull * ci / nchunk, b1 = Bfull * (ci + 1) / nchunk;
+    B = b1 - b0;
+    rc = conv(g->conv_post, xin + b0 * sb, sb, sc, 1, dev_wav + b0 * Tn, Tn, big ? 1.0f : 0.01f, nullptr, nullptr, 1.0f, 1);
+    B = Bfull;
+    if (rc != AB_OK) break;
+    if (!g->tail_events.empty()) {
+      // when there are more events than utterances the surplus events fire with the last chunk
+      const size_t e0 = g->tail_events.size() * (size_t)ci / nchunk, e1 = g->tail_events.size() * (size_t)(ci + 1) / nchunk;
+      for (size_t e = e0; e < e1; ++e) cudaEventRecord(g->tail_events[e], st);
+    }
+  }
+  g->tail_events.clear();
   if (rc != AB_OK) return rc;
   g->launches = launches;
   return AB_OK;

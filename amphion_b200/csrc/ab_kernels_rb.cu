@@ -40,6 +40,7 @@ constexpr uint32_t RB_SMEM_LIMIT = 226 * 1024;      // + 1 KB of static shared m
 
 struct RbGeom {
   int Np, nkc, m, R, G, RB;     // padded channels, 32-channel K chunks, M tiles, rows, guard rows, buffer rows
+  int E;                        // rows of the first conv's own halo that are loaded (c * dil[0])
   int Hlo, V;                   // row of the first valid output, valid outputs per tile
   int tiles, ntiles;            // per sequence, total
   int nsteps;                   // convs per tile
@@ -102,7 +103,7 @@ __global__ void __launch_bounds__(RB_THREADS, 1) rb_kernel(RbParams p, RbGeom g)
       mbar_init(bar_empty(s), 1);
     }
     for (int s = 0; s < 2; ++s) {
-      mbar_init(bar_opnd(s), RB_EPI_THREADS);
+      mbar_init(bar_opnd(s), RB_EPI_WARPS);
       mbar_init(bar_acc(s), 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -142,6 +143,10 @@ __global__ void __launch_bounds__(RB_THREADS, 1) rb_kernel(RbParams p, RbGeom g)
 
   if (warp >= 2) {
     // ===================== epilogue / loader warps =====================
+    // The residual never goes through the epilogue's critical path: x_p (+ the branch sum before the last conv)
+    // is written into the accumulator with tcgen05.st while the slot waits for its next conv, and that conv
+    // accumulates on top of it.  The loads that feed the tcgen05.st are issued at the top of an item, before the
+    // TMEM read and the arithmetic of that item, and the lines were prefetched into L2 when the tile was loaded.
     const int ew = warp - 2;
     const int q4 = warp & 3;        // TMEM lane quarter this warp may access
     const int grp = ew >> 2;        // 0..3: items are dealt round-robin to the four warps of a quarter
@@ -149,19 +154,22 @@ __global__ void __launch_bounds__(RB_THREADS, 1) rb_kernel(RbParams p, RbGeom g)
     const int nch = g.Np >> 4;
     const int c8n = g.Np >> 3;
     const int nitems = g.m * nch;
+    const int last_pair = p.npairs - 1;
     long long wait_acc = 0;
     int ntile_done = 0;
 
-    // tile load: operand buffer rows [0, R) <- lrelu(x)[b, :, T0 - Hlo + row] as 16-bit K-major units
+    // tile load: operand buffer rows [-E, R + E) <- lrelu(x)[b, :, T0 - Hlo + row] as 16-bit K-major units (the
+    // first conv's own halo E = c * dil[0] is loaded, not recomputed)
     auto load_tile = [&](int slot, int tile_id) {
       const int b = tile_id / g.tiles, tl = tile_id - b * g.tiles;
       const int tbase = tl * g.V - g.Hlo;
+      const int rows = g.R + 2 * g.E;
       uint8_t* buf = smem + (uint32_t)slot * g.off_buf1;
       if (p.ximg != nullptr) {
         const uint32_t sb = s0 + (uint32_t)slot * g.off_buf1;
         const uint16_t* xb = p.ximg + (size_t)b * c8n * p.T * 8;
-        for (int u = et; u < c8n * g.R; u += RB_EPI_THREADS) {
-          const int c8 = u / g.R, row = u - c8 * g.R;
+        for (int u = et; u < c8n * rows; u += RB_EPI_THREADS) {
+          const int c8 = u / rows, row = u - c8 * rows - g.E;
           const int t = tbase + row;
           const bool ok = t >= 0 && t < p.T;
           cp_async16(sb + unit_offset(g.RB, c8, row + g.G),
@@ -169,8 +177,8 @@ __global__ void __launch_bounds__(RB_THREADS, 1) rb_kernel(RbParams p, RbGeom g)
         }
       } else {
         const float* xb = p.x + (int64_t)b * p.C * p.T;
-        for (int u = et; u < c8n * g.R; u += RB_EPI_THREADS) {
-          const int c8 = u / g.R, row = u - c8 * g.R;
+        for (int u = et; u < c8n * rows; u += RB_EPI_THREADS) {
+          const int c8 = u / rows, row = u - c8 * rows - g.E;
           const int t = tbase + row;
           const bool ok = t >= 0 && t < p.T;
           float v[8];
@@ -187,12 +195,59 @@ __global__ void __launch_bounds__(RB_THREADS, 1) rb_kernel(RbParams p, RbGeom g)
           *reinterpret_cast<uint4*>(buf + unit_offset(g.RB, c8, row + g.G)) = q;
         }
       }
+      // L2 prefetch of the fp32 rows the accumulator inits will read (x, and the branch sum)
+      const int segs = (g.R + 31) / 32 + 1;
+      const int64_t bCT = (int64_t)b * p.C * p.T;
+      for (int u = et; u < p.C * segs; u += RB_EPI_THREADS) {
+        const int c = u / segs, sgi = u - c * segs;
+        int t = tbase + sgi * 32;
+        t = t < 0 ? 0 : (t >= p.T ? p.T - 1 : t);
+        prefetch_l2(p.x + bCT + (int64_t)c * p.T + t);
+        if (p.acc_prev != nullptr) prefetch_l2(p.acc_prev + bCT + (int64_t)c * p.T + t);
+      }
+    };
+    // 16 fp32 x values of one item (rows of this lane), zero outside [0, T) / beyond C
+    auto load_x16 = [&](float (&d)[16], const float* base, bool inr, int ch) {
+#pragma unroll
+      for (int e = 0; e < 16; ++e) d[e] = (inr && ch * 16 + e < p.C) ? __ldg(base + (int64_t)e * p.T) : 0.f;
+    };
+    auto load_acp16 = [&](float (&d)[16], const float* base, bool inr, int ch) {   // may alias y: plain loads
+#pragma unroll
+      for (int e = 0; e < 16; ++e) d[e] = (inr && ch * 16 + e < p.C) ? base[(int64_t)e * p.T] : 0.f;
+    };
+    // accumulator init of a slot from x (nconv == 1: the first conv accumulates on the residual)
+    auto init_acc_from_x = [&](int slot, int tile_id) {
+      const int b = tile_id / g.tiles, tl = tile_id - b * g.tiles;
+      const int tbase = tl * g.V - g.Hlo;
+      const uint32_t tslot = tmem + (uint32_t)(slot * RB_SLOT_COLS) + ((uint32_t)(q4 * 32) << 16);
+      const int64_t bCT = (int64_t)b * p.C * p.T;
+      for (int n = grp; n < nitems; n += 4) {
+        const int i = n / nch, ch = n - i * nch;
+        const int row = i * 128 + q4 * 32 + lane;
+        const int t = tbase + row;
+        const bool inr = t >= 0 && t < p.T;
+        const int64_t off0 = bCT + (int64_t)(ch * 16) * p.T + t;
+        float res[16];
+        load_x16(res, p.x + off0, inr, ch);
+        if (last_pair == 0 && p.acc_prev != nullptr) {
+          float acp[16];
+          load_acp16(acp, p.acc_prev + off0, inr, ch);
+#pragma unroll
+          for (int e = 0; e < 16; ++e) res[e] += acp[e];
+        }
+        uint32_t r[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) r[e] = __float_as_uint(res[e]);
+        tc_st16(tslot + (uint32_t)(i * g.Np + ch * 16), r);
+      }
+      tc_wait_st();
     };
     auto publish_operand = [&](int slot) {
       cp_async_wait_all();
       fence_proxy_async();
       tc_fence_before();
-      mbar_arrive(bar_opnd(slot));
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_opnd(slot));
     };
 
     uint32_t ph_acc = 0u;   // phase parity of bar_acc per slot (bit s)
@@ -204,11 +259,16 @@ __global__ void __launch_bounds__(RB_THREADS, 1) rb_kernel(RbParams p, RbGeom g)
         cp_async_commit();
         if (two) load_tile(1, 2 * q0 + 1);
         cp_async_commit();
+        if (p.nconv == 1) init_acc_from_x(0, 2 * q0);
         cp_async_wait_group<1>();
         fence_proxy_async();
         tc_fence_before();
-        mbar_arrive(bar_opnd(0));
-        if (two) publish_operand(1);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_opnd(0));
+        if (two) {
+          if (p.nconv == 1) init_acc_from_x(1, 2 * q0 + 1);
+          publish_operand(1);
+        }
       }
     }
     for (int q = blockIdx.x; q < npairs_total; q += gridDim.x) {
@@ -225,6 +285,8 @@ __global__ void __launch_bounds__(RB_THREADS, 1) rb_kernel(RbParams p, RbGeom g)
           const int tbase = tl * g.V - g.Hlo;
           uint8_t* buf = smem + (uint32_t)slot * g.off_buf1;
           const uint32_t tslot = tmem + (uint32_t)(slot * RB_SLOT_COLS) + ((uint32_t)(q4 * 32) << 16);
+          float* scr = p.scratch ? p.scratch + ((size_t)blockIdx.x * 2 + slot) * ((size_t)g.R * g.Np) : nullptr;
+          const int64_t bCT = (int64_t)b * p.C * p.T;
           {
             const long long t0 = g.dbg ? clock64() : 0;
             mbar_wait(bar_acc(slot), (ph_acc >> slot) & 1u, 40 + slot);
@@ -233,14 +295,27 @@ __global__ void __launch_bounds__(RB_THREADS, 1) rb_kernel(RbParams p, RbGeom g)
           ph_acc ^= 1u << slot;
           tc_fence_after();
           if (is_e1) {
-            // ---- intermediate = lrelu(conv1 + b1) -> operand buffer, zero outside [0, T) (conv2's zero padding)
+            // ---- intermediate = lrelu(conv1 + b1) -> operand buffer, zero outside [0, T) (conv2's zero padding);
+            //      accumulator <- x_p (+ branch sum before the last conv): conv2 accumulates on the residual
+            const bool add_acp = pair == last_pair && p.acc_prev != nullptr;
             for (int n = grp; n < nitems; n += 4) {
               const int i = n / nch, ch = n - i * nch;
               const int row = i * 128 + q4 * 32 + lane;
               const int t = tbase + row;
               const bool inr = t >= 0 && t < p.T;
+              const int64_t off0 = bCT + (int64_t)(ch * 16) * p.T + t;
+              float res[16], acp[16];
+              if (pair == 0) {
+                load_x16(res, p.x + off0, inr, ch);
+              } else {
+                const float* sp = scr + (size_t)(ch * 16) * g.R + row;
+#pragma unroll
+                for (int e = 0; e < 16; ++e) res[e] = sp[(size_t)e * g.R];
+              }
+              if (add_acp) load_acp16(acp, p.acc_prev + off0, inr, ch);
               uint32_t r[16];
-              tc_ld16(tslot + (uint32_t)(i * g.Np + ch * 16), r);
+              const uint32_t taddr = tslot + (uint32_t)(i * g.Np + ch * 16);
+              tc_ld16(taddr, r);
               tc_wait_ld();
               float v[16];
 #pragma unroll
@@ -249,78 +324,66 @@ __global__ void __launch_bounds__(RB_THREADS, 1) rb_kernel(RbParams p, RbGeom g)
                 v[e] = inr ? lrelu(a, p.slope) : 0.f;
               }
               store_operand16<BF16>(buf, g.RB, ch, row + g.G, v);
+#pragma unroll
+              for (int e = 0; e < 16; ++e) r[e] = __float_as_uint(add_acp ? res[e] + acp[e] : res[e]);
+              tc_st16(taddr, r);
             }
+            tc_wait_st();
             publish_operand(slot);
           } else if (!final_step) {
-            // ---- x_{p+1} = conv + b + x_p -> scratch (fp32), lrelu(x_{p+1}) -> operand buffer
-            float* scr = p.scratch + ((size_t)blockIdx.x * 2 + slot) * ((size_t)g.R * g.Np);
-            const float* xb = p.x + (int64_t)b * p.C * p.T;
+            // ---- x_{p+1} = acc + b (the accumulator started from x_p).  nconv == 2: -> scratch for the next
+            //      pair's accumulator init; nconv == 1: written straight back as the next conv's start value
+            //      (+ the branch sum before the last conv).  lrelu(x_{p+1}) -> operand buffer.
+            const bool add_acp = p.nconv == 1 && pair + 1 == last_pair && p.acc_prev != nullptr;
             for (int n = grp; n < nitems; n += 4) {
               const int i = n / nch, ch = n - i * nch;
               const int row = i * 128 + q4 * 32 + lane;
               const int t = tbase + row;
               const bool inr = t >= 0 && t < p.T;
-              float* sp = scr + (size_t)(ch * 16) * g.R + row;
-              float res[16];
-              if (pair == 0) {
-                const float* xp = xb + (int64_t)(ch * 16) * p.T + t;
-#pragma unroll
-                for (int e = 0; e < 16; ++e) res[e] = (inr && ch * 16 + e < p.C) ? __ldg(xp + (int64_t)e * p.T) : 0.f;
-              } else {
-#pragma unroll
-                for (int e = 0; e < 16; ++e) res[e] = sp[(size_t)e * g.R];
-              }
+              float acp[16];
+              if (add_acp) load_acp16(acp, p.acc_prev + bCT + (int64_t)(ch * 16) * p.T + t, inr, ch);
               uint32_t r[16];
-              tc_ld16(tslot + (uint32_t)(i * g.Np + ch * 16), r);
+              const uint32_t taddr = tslot + (uint32_t)(i * g.Np + ch * 16);
+              tc_ld16(taddr, r);
               tc_wait_ld();
-              float v[16];
+              float a[16], v[16];
 #pragma unroll
               for (int e = 0; e < 16; ++e) {
-                float a = __uint_as_float(r[e]) + bias_c[ch * 16 + e];
-                a += res[e];
-                sp[(size_t)e * g.R] = a;
-                v[e] = inr ? lrelu(a, p.slope) : 0.f;
+                a[e] = __uint_as_float(r[e]) + bias_c[ch * 16 + e];
+                v[e] = inr ? lrelu(a[e], p.slope) : 0.f;
+              }
+              if (p.nconv == 2) {
+                float* sp = scr + (size_t)(ch * 16) * g.R + row;
+#pragma unroll
+                for (int e = 0; e < 16; ++e) sp[(size_t)e * g.R] = a[e];
+              } else {
+#pragma unroll
+                for (int e = 0; e < 16; ++e) r[e] = __float_as_uint(add_acp ? a[e] + acp[e] : a[e]);
+                tc_st16(taddr, r);
               }
               store_operand16<BF16>(buf, g.RB, ch, row + g.G, v);
             }
+            if (p.nconv == 1) tc_wait_st();
             publish_operand(slot);
           } else {
-            // ---- last conv of the chain: y = ((conv + b) + x_p + branch_sum) / out_div (+ operand image of
-            // lrelu(y, img_slope)); the operand buffer is free, so the next tile's load is issued first
+            // ---- last conv of the chain: y = (acc + b) / out_div (+ operand image of lrelu(y, img_slope)); the
+            // operand buffer is free, so the next tile's load is issued first
             const int next_tile = 2 * qn + slot;
             const bool have_next = qn < npairs_total && next_tile < g.ntiles;
             if (have_next) load_tile(slot, next_tile);
-            const float* scr = p.scratch ? p.scratch + ((size_t)blockIdx.x * 2 + slot) * ((size_t)g.R * g.Np) : nullptr;
-            const int64_t bCT = (int64_t)b * p.C * p.T;
             for (int n = grp; n < nitems; n += 4) {
               const int i = n / nch, ch = n - i * nch;
               const int row = i * 128 + q4 * 32 + lane;
               const int t = tbase + row;
               const bool ok = row >= g.Hlo && row < g.Hlo + g.V && t < p.T;
               const int64_t off0 = bCT + (int64_t)(ch * 16) * p.T + t;
-              float res[16], acp[16];
-              if (pair == 0) {
-#pragma unroll
-                for (int e = 0; e < 16; ++e) res[e] = (ok && ch * 16 + e < p.C) ? __ldg(p.x + off0 + (int64_t)e * p.T) : 0.f;
-              } else {
-                const float* sp = scr + (size_t)(ch * 16) * g.R + row;
-#pragma unroll
-                for (int e = 0; e < 16; ++e) res[e] = sp[(size_t)e * g.R];
-              }
-              if (p.acc_prev != nullptr) {
-#pragma unroll
-                for (int e = 0; e < 16; ++e) acp[e] = (ok && ch * 16 + e < p.C) ? p.acc_prev[off0 + (int64_t)e * p.T] : 0.f;
-              }
               uint32_t r[16];
               tc_ld16(tslot + (uint32_t)(i * g.Np + ch * 16), r);
               tc_wait_ld();
               float v[16];
 #pragma unroll
               for (int e = 0; e < 16; ++e) {
-                float a = __uint_as_float(r[e]) + bias_c[ch * 16 + e];
-                a += res[e];
-                if (p.acc_prev != nullptr) a += acp[e];
-                a *= g.out_scale;
+                const float a = (__uint_as_float(r[e]) + bias_c[ch * 16 + e]) * g.out_scale;
                 v[e] = a;
                 if (ok && ch * 16 + e < p.C) p.y[off0 + (int64_t)e * p.T] = a;
               }
@@ -338,8 +401,12 @@ __global__ void __launch_bounds__(RB_THREADS, 1) rb_kernel(RbParams p, RbGeom g)
               }
             }
             ++ntile_done;
-            if (have_next) publish_operand(slot);
-            else tc_fence_before();
+            if (have_next) {
+              if (p.nconv == 1) init_acc_from_x(slot, next_tile);
+              publish_operand(slot);
+            } else {
+              tc_fence_before();
+            }
           }
         }
       }
@@ -394,6 +461,9 @@ __global__ void __launch_bounds__(RB_THREADS, 1) rb_kernel(RbParams p, RbGeom g)
       for (int step = 0; step < g.nsteps; ++step) {
         const int pair = step / p.nconv;
         const int dil = (p.nconv == 2 && (step & 1)) ? 1 : dil_s[pair];
+        // conv1 of a pair starts from zero; every conv that closes a residual step accumulates on x_p, which the
+        // epilogue warps wrote into the accumulator
+        const bool zero_init = p.nconv == 2 && (step & 1) == 0;
         for (int slot = 0; slot < nact; ++slot) {
           {
             const long long t0 = g.dbg ? clock64() : 0;
@@ -419,7 +489,7 @@ __global__ void __launch_bounds__(RB_THREADS, 1) rb_kernel(RbParams p, RbGeom g)
                   const bool two = nks_total - kc * 2 >= 2;
                   const uint32_t alo = desc_lo_sw32(a16 + (uint32_t)(kc * 2) * kstepA + arow);
                   const uint32_t blo = desc_lo_sw32(w16 + (uint32_t)s * stage16 + (uint32_t)kk * chunk16);
-                  if ((j | kc) == 0) issue_first(alo, blo, two);
+                  if (zero_init && (j | kc) == 0) issue_first(alo, blo, two);
                   else issue_rest(alo, blo, two);
                 }
                 if (elected) tc_commit(bar_empty(s));
@@ -499,7 +569,8 @@ int rb_make_geom(const RbParams& p, RbGeom& g) {
   }
   g.G = c * dmax;
   g.RB = rb_round_up(g.R + 2 * g.G, 8);
-  const int H = rb_halo(p.k, p.dil, p.npairs, p.nconv);
+  g.E = c * p.dil[0];
+  const int H = rb_halo(p.k, p.dil, p.npairs, p.nconv) - g.E;   // rows lost on each side: every conv but the first
   g.Hlo = rb_round_up(H, 4);
   g.V = (g.R - g.Hlo - H) / 4 * 4;
   if (g.V < 32) return fail(AB_ERR_UNSUPPORTED, "rb: halo %d leaves no room in a %d-row tile", H, g.R);
@@ -543,7 +614,7 @@ size_t rb_scratch_bytes() { return (size_t)148 * 2 * (size_t)(RB_SLOT_COLS * 128
 double rb_cost_per_row(int C, int k, const int* dil, int npairs, int nconv) {
   if (!rb_supported(C, k)) return 0.0;
   const int Np = rb_round_up(C, 16), m = std::min(RB_SLOT_COLS / Np, 16), R = 128 * m;
-  const int H = rb_halo(k, dil, npairs, nconv);
+  const int H = rb_halo(k, dil, npairs, nconv) - (k - 1) / 2 * dil[0];
   const int V = (R - rb_round_up(H, 4) - H) / 4 * 4;
   if (V < 32) return 0.0;
   const double mma_row = (double)k * (Np / 16.0) * (64.0 + Np / 2.0) / 128.0;      // per conv and computed row

@@ -1,10 +1,16 @@
 """Batch sharding across the GPUs of one box: the utterance
 batch is split contiguously over ranks, every rank runs the identical single-GPU
-pipeline, and ONE collective — an all-gather of the wav shards over
-NCCL/NVLink — assembles the result in global utterance order.  The reference has
-no equivalent (each accelerate rank writes its own files and mis-indexes the
-uids, models/vocoders/vocoder_inference.py:360)."""
+pipeline, and ONE exchange — a gather of the wav shards to the destination rank
+over NCCL/NVLink (grouped send/recv) — assembles the result in global utterance
+order.  Only the destination receives data; the other ranks send their shard and
+return ``None``.  The exchange is issued per batch chunk on a side stream while
+the last layer of the next chunk is still computing (``tail_events`` of the
+generator), so all but the last chunk's transfer hides under compute.  The
+reference has no equivalent (each accelerate rank writes its own files and
+mis-indexes the uids, models/vocoders/vocoder_inference.py:360)."""
 from __future__ import annotations
+
+import inspect
 
 import torch
 import torch.distributed as dist
@@ -17,38 +23,132 @@ def shard_bounds(n_items: int, world_size: int, rank: int):
     return start, start + base + (1 if rank < extra else 0)
 
 
-def sharded_vocoder_forward(model, mels, group=None):
-    """mels: the GLOBAL batch [B, n_mel, T] (every rank holds it or at least its
-    own slice filled in).  Returns wav [B, 1, T*hop] on every rank."""
+def _chunk_bounds(n: int, chunks: int, i: int):
+    """Chunk i of n items, the split `ab_generator_set_tail_events` uses: [n*i/chunks, n*(i+1)/chunks)."""
+    return n * i // chunks, n * (i + 1) // chunks
+
+
+def _supports(fn, name):
+    try:
+        return name in inspect.signature(fn).parameters
+    except (TypeError, ValueError):
+        return False
+
+
+def gather_shards(local, n_items, world_size, rank, group=None, dst=0, out=None, chunk=None):
+    """Gather ragged shards (sizes differ by at most one, possibly empty) to ``dst`` in global order.
+
+    ``local``: this rank's shard [n_local, ...] (``None`` or empty when it has no items).  On ``dst`` the result
+    [n_items, ...] is returned (``out`` if given — the destination's own shard may already sit in it); other ranks
+    return ``None``.  ``chunk=(i, n)`` restricts the exchange to chunk i of n of every rank's shard.
+    Every rank decides from (n_items, world_size) alone, so ranks with no items never block the others."""
+    lo, hi = shard_bounds(n_items, world_size, rank)
+    ops = []
+    if rank == dst:
+        if out is None:
+            if local is None:
+                raise ValueError("gather_shards: the destination needs `out` when it holds no items")
+            out = torch.empty((n_items,) + tuple(local.shape[1:]), device=local.device, dtype=local.dtype)
+        for r in range(world_size):
+            rlo, rhi = shard_bounds(n_items, world_size, r)
+            if chunk is not None:
+                a, b = _chunk_bounds(rhi - rlo, chunk[1], chunk[0])
+                rlo, rhi = rlo + a, rlo + b
+            if rhi <= rlo:
+                continue
+            if r == dst:
+                if local is not None and out[rlo:rhi].data_ptr() != local[rlo - lo: rhi - lo].data_ptr():
+                    out[rlo:rhi].copy_(local[rlo - lo: rhi - lo])
+            else:
+                ops.append(dist.P2POp(dist.irecv, out[rlo:rhi], _global_rank(group, r), group=group))
+    elif hi > lo:
+        a, b = (0, hi - lo) if chunk is None else _chunk_bounds(hi - lo, chunk[1], chunk[0])
+        if b > a:
+            ops.append(dist.P2POp(dist.isend, local[a:b].contiguous(), _global_rank(group, dst), group=group))
+    works = dist.batch_isend_irecv(ops) if ops else []
+    return (out if rank == dst else None), works
+
+
+def _global_rank(group, group_rank):
+    return group_rank if group is None else dist.get_global_rank(group, group_rank)
+
+
+def sharded_vocoder_forward(model, mels, group=None, dst=0, chunks=4):
+    """mels: the GLOBAL batch [B, n_mel, T] (every rank holds it or at least its own slice filled in).
+    Returns wav [B, 1, T*hop] on rank ``dst`` and ``None`` elsewhere (ranks without items just skip).
+
+    The generator writes the destination's own shard straight into the gathered tensor; on CUDA the transfer of
+    chunk i overlaps the last layer of chunk i+1 (side stream + the generator's ``tail_events``)."""
     ws = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     B = mels.shape[0]
     lo, hi = shard_bounds(B, ws, rank)
-    local = model(mels[lo:hi]) if hi > lo else None
     if ws == 1:
-        return local
-    return gather_shards(local, B, ws, rank, group, like=mels, model=model)
-
-
-def gather_shards(local, n_items, world_size, rank, group=None, like=None, model=None):
-    """All-gather ragged shards (sizes differ by at most one) into global order."""
-    base, extra = divmod(n_items, world_size)
-    cap = base + (1 if extra else 0)
+        return model(mels)
+    fwd = model.forward if hasattr(model, "forward") else model
+    cuda = mels.is_cuda
+    use_events = cuda and _supports(fwd, "tail_events") and chunks > 1
+    use_out = _supports(fwd, "out")
+    out = None
+    local = None
+    events = [torch.cuda.Event() for _ in range(chunks)] if use_events else None
+    if rank == dst:
+        # shape of one utterance's result: from this rank's forward when it has items, else from a 1-item probe
+        if hi > lo:
+            if use_out:
+                hop = _hop_of(model)
+                if hop is not None:
+                    out = torch.empty((B, 1, mels.shape[-1] * hop), device=mels.device, dtype=torch.float32)
+                    kw = dict(out=out[lo:hi])
+                    if use_events:
+                        kw["tail_events"] = events
+                    local = model(mels[lo:hi], **kw)
+            if local is None:
+                local = model(mels[lo:hi], **({"tail_events": events} if use_events else {}))
+        else:
+            hop = _hop_of(model)
+            if hop is None:
+                raise ValueError("sharded forward: the destination rank needs at least one item (or a model with cfg)")
+            out = torch.empty((B, 1, mels.shape[-1] * hop), device=mels.device, dtype=torch.float32)
+    elif hi > lo:
+        local = model(mels[lo:hi], **({"tail_events": events} if use_events else {}))
+    if not use_events:
+        res, works = gather_shards(local, B, ws, rank, group, dst, out=out)
+        for w in works:
+            w.wait()
+        return res
+    # chunked exchange on a side stream: chunk i is sent / received as soon as its event fired
+    main = torch.cuda.current_stream(mels.device)
+    side = _side_stream(mels.device)
+    res, all_works = out, []
+    with torch.cuda.stream(side):
+        for i in range(chunks):
+            if hi > lo:
+                side.wait_event(events[i])
+            elif i == 0:
+                side.wait_stream(main)
+            res, works = gather_shards(local, B, ws, rank, group, dst, out=res if rank == dst else None, chunk=(i, chunks))
+            all_works += works
+        for w in all_works:
+            w.wait()
+    main.wait_stream(side)
     if local is not None:
-        tail = local.shape[1:]
-        dev, dt = local.device, local.dtype
-    else:  # this rank got no items: shape from a peer via the padded gather
-        raise ValueError("sharded forward needs at least one item per rank")
-    padded = local
-    if local.shape[0] < cap:
-        padded = torch.zeros((cap,) + tuple(tail), device=dev, dtype=dt)
-        padded[: local.shape[0]] = local
-    out = torch.empty((world_size * cap,) + tuple(tail), device=dev, dtype=dt)
-    dist.all_gather_into_tensor(out, padded.contiguous(), group=group)
-    if extra == 0:
-        return out
-    pieces = []
-    for r in range(world_size):
-        lo, hi = shard_bounds(n_items, world_size, r)
-        pieces.append(out[r * cap: r * cap + (hi - lo)])
-    return torch.cat(pieces, 0)
+        local.record_stream(side)
+    return res if rank == dst else None
+
+
+_side_streams = {}
+
+
+def _side_stream(device):
+    key = str(device)
+    if key not in _side_streams:
+        _side_streams[key] = torch.cuda.Stream(device=device)
+    return _side_streams[key]
+
+
+def _hop_of(model):
+    try:
+        return int(model.cfg.preprocess.hop_size)
+    except AttributeError:
+        return None

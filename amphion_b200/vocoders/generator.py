@@ -166,11 +166,15 @@ class NativeGenerator(nn.Module):
         del keep  # stream-ordered: the caching allocator keeps the blocks alive until the copies ran
 
     # ---- forward ---------------------------------------------------------------
-    def forward(self, x):
-        """mel [B, n_mel, T] (any strides) -> wav [B, 1, T*hop], fp32, same device."""
-        return self._forward_native(x)
+    def forward(self, x, out=None, tail_events=None):
+        """mel [B, n_mel, T] (any strides) -> wav [B, 1, T*hop], fp32, same device.
 
-    def _forward_native(self, x, g=None):
+        ``out`` (optional, beyond the reference signature): a contiguous fp32 [B, 1, T*hop] tensor to write into
+        (e.g. a slice of a gathered batch).  ``tail_events``: a list of ``torch.cuda.Event``; the last layer runs in
+        ``len(tail_events)`` batch chunks and event i is recorded when utterances [B*i/n, B*(i+1)/n) are complete."""
+        return self._forward_native(x, out=out, tail_events=tail_events)
+
+    def _forward_native(self, x, g=None, out=None, tail_events=None):
         """``g`` [B, gin_channels] (HiFiGAN_vits conditioning) or None."""
         _capi.require_cuda(x, f"{type(self).__name__}.forward")
         if x.dim() != 3 or x.shape[1] != int(self.cfg.preprocess.n_mel):
@@ -191,7 +195,18 @@ class NativeGenerator(nn.Module):
                 self._workspace = None
                 self._workspace = torch.empty(need + 256, dtype=torch.uint8, device=x.device)
             wbase = (self._workspace.data_ptr() + 255) // 256 * 256
-            wav = torch.empty(B, 1, T * hop, dtype=torch.float32, device=x.device)
+            if out is None:
+                wav = torch.empty(B, 1, T * hop, dtype=torch.float32, device=x.device)
+            else:
+                if (tuple(out.shape) != (B, 1, T * hop) or out.dtype != torch.float32 or out.device != x.device
+                        or not out.is_contiguous()):
+                    raise ValueError(f"out must be a contiguous fp32 [{B}, 1, {T * hop}] tensor on {x.device}")
+                wav = out
+            if tail_events:
+                for ev in tail_events:
+                    ev.record()   # creates the underlying cudaEvent_t (torch creates it lazily); re-recorded below
+                arr = (C.c_void_p * len(tail_events))(*[C.c_void_p(ev.cuda_event) for ev in tail_events])
+                _capi.check(lib.ab_generator_set_tail_events(h, arr, len(tail_events)), "ab_generator_set_tail_events")
             strides = _capi.shape_array(x.stride())
             if g is None:
                 _capi.check(lib.ab_generator_forward(h, _capi.ptr(x), B, T, strides, _capi.ptr(wav), C.c_void_p(wbase),

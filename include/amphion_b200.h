@@ -151,6 +151,11 @@ int ab_generator_set_profiling(ab_generator* g, int32_t enable);
  *   pair per launch, 2 (default) = persistent kernel, a whole ResBlock per launch when the cost model prefers
  *   it, 3 = always a whole ResBlock per launch.  Returns AB_ERR_ARG for an unknown key / value. */
 int ab_generator_set_option(ab_generator* g, const char* key, int32_t value);
+/* Final-gather hook for the batch-sharded multi-GPU path (no reference counterpart): the NEXT
+ * ab_generator_forward[_cond] runs conv_post (hifigan.py:216-217) in n contiguous batch chunks
+ * [B*i/n, B*(i+1)/n) and records events[i] (cudaEvent_t, caller-owned) on `stream` after chunk i, so the caller
+ * can start sending chunk i while chunk i+1 is computed.  One-shot: cleared by that forward.  n = 0 clears. */
+int ab_generator_set_tail_events(ab_generator* g, void* const* events, int32_t n);
 int ab_generator_get_profile(ab_generator* g, ab_profile_entry* out, int32_t max_entries, int32_t* n_out);
 
 /* ------------------------------------------------------------------------

@@ -1,7 +1,10 @@
-"""CPU (gloo, world_size 2/3) coverage of the N>1 host logic: contiguous utterance sharding and the final
-all-gather in global utterance order, including ragged shard sizes."""
+"""CPU (gloo, world_size 2/3) coverage of the N>1 host logic: contiguous utterance sharding and the final gather
+to the destination rank in global utterance order — ragged shard sizes, fewer utterances than ranks (ranks
+without items must not block the others), a non-zero destination, the chunked exchange and the write-in-place
+path of a model that accepts ``out=``."""
 import os
 import socket
+from types import SimpleNamespace as NS
 
 import pytest
 import torch
@@ -33,28 +36,59 @@ def _fake_vocoder(mel):  # stand-in with the generator's contract: [B, n_mel, T]
     return (mel.sum(1, keepdim=True) * 0.01).repeat_interleave(4, dim=-1)
 
 
-def _worker(rank, world, port, n_items, out_dir):
+class _FakeModel:
+    """Same contract plus the generator's ``out=`` extension and ``cfg.preprocess.hop_size``."""
+    cfg = NS(preprocess=NS(hop_size=4))
+
+    def forward(self, mel, out=None):
+        y = _fake_vocoder(mel)
+        if out is None:
+            return y
+        out.copy_(y)
+        return out
+
+    __call__ = forward
+
+
+def _worker(rank, world, port, n_items, dst, out_dir):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         g = torch.Generator().manual_seed(0)
         mels = torch.randn(n_items, 5, 6, generator=g)          # every rank holds the global batch
-        wav = sharded_vocoder_forward(_fake_vocoder, mels)
-        torch.save(wav, os.path.join(out_dir, f"wav{rank}.pt"))
+        for tag, model in (("fn", _fake_vocoder), ("obj", _FakeModel())):
+            if tag == "fn" and shard_bounds(n_items, world, dst)[0] == shard_bounds(n_items, world, dst)[1]:
+                continue   # a bare function gives an item-less destination no way to size the result
+            wav = sharded_vocoder_forward(model, mels, dst=dst)
+            assert (wav is not None) == (rank == dst)
+            if rank == dst:
+                torch.save(wav, os.path.join(out_dir, f"wav_{tag}.pt"))
+        # the chunked exchange, chunk by chunk (what the CUDA path does behind the generator's tail events)
         lo, hi = shard_bounds(n_items, world, rank)
-        again = gather_shards(_fake_vocoder(mels[lo:hi]), n_items, world, rank)
-        assert torch.equal(again, wav)
+        local = _fake_vocoder(mels[lo:hi]) if hi > lo else None
+        out = torch.full((n_items, 1, 24), float("nan")) if rank == dst else None
+        for i in range(3):
+            res, works = gather_shards(local, n_items, world, rank, dst=dst, out=out, chunk=(i, 3))
+            for w in works:
+                w.wait()
+        if rank == dst:
+            torch.save(out, os.path.join(out_dir, "wav_chunked.pt"))
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,n_items", [(2, 6), (2, 7), (3, 8)])
-def test_sharded_forward_gathers_in_global_order(tmp_path, world, n_items):
+@pytest.mark.parametrize("world,n_items,dst", [(2, 6, 0), (2, 7, 1), (3, 8, 0), (3, 2, 0), (3, 2, 2), (2, 1, 0)])
+def test_sharded_forward_gathers_to_the_destination_in_global_order(tmp_path, world, n_items, dst):
     port = _free_port()
-    mp.spawn(_worker, args=(world, port, n_items, str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, port, n_items, dst, str(tmp_path)), nprocs=world, join=True)
     g = torch.Generator().manual_seed(0)
     want = _fake_vocoder(torch.randn(n_items, 5, 6, generator=g))
-    for r in range(world):
-        got = torch.load(os.path.join(tmp_path, f"wav{r}.pt"))
-        assert got.shape == want.shape
-        assert torch.equal(got, want)          # same result on every rank, global utterance order
+    seen = 0
+    for tag in ("fn", "obj", "chunked"):
+        f = os.path.join(tmp_path, f"wav_{tag}.pt")
+        if not os.path.exists(f):
+            continue
+        got = torch.load(f)
+        assert got.shape == want.shape and torch.equal(got, want), tag   # global utterance order, no padding rows
+        seen += 1
+    assert seen >= 2

@@ -607,17 +607,19 @@ def _fusion_outputs(model, mel, modes):
 
 @pytest.mark.parametrize("B,T", [(2, 40), (3, 150), (1, 37)])
 def test_resblock_fusion_modes_agree_on_v1(B, T):
-    """HiFi-GAN V1 (stages of 256/128/64/32 channels): the per-pair kernel (0), the persistent kernel one pair per
-    launch (1), the cost-model plan (2) and whole-block fusion with halo recompute (3) run the same arithmetic in
-    the same order, so they must agree to the last bit; T=150 gives several tiles per sequence and an odd tile
-    count, T=37 a ragged single tile."""
+    """HiFi-GAN V1 (stages of 256/128/64/32 channels).  The persistent kernel one pair per launch (1), the
+    cost-model plan (2) and whole-block fusion with halo recompute (3) run the same arithmetic in the same order
+    and must agree to the last bit (recomputed halo rows == the rows another tile owns).  The per-pair kernel (0)
+    adds the residual after the convolution instead of accumulating on top of it: fp32 summation order only.
+    T=150 gives several tiles per sequence and an odd tile count, T=37 a ragged single tile."""
     model = build_model("hifigan", HP_V1, 80, seed=4321).to(DEV)
     mel = torch.randn(B, 80, T, generator=torch.Generator().manual_seed(T)).to(DEV)
     outs = _fusion_outputs(model, mel, (0, 1, 2, 3))
     for mode in (1, 2, 3):
         assert torch.isfinite(outs[mode]).all()
-        diff = (outs[mode] - outs[0]).abs().max().item()
-        assert diff == 0.0, (mode, diff)
+    assert torch.equal(outs[1], outs[3]) and torch.equal(outs[2], outs[3])
+    diff = (outs[3] - outs[0]).abs().max().item()
+    assert diff <= 5e-6, diff
 
 
 @pytest.mark.parametrize("name", ["hifigan_rb1", "hifigan_rb2"])
