@@ -19,6 +19,7 @@
 #include <stdlib.h>
 
 #include <algorithm>
+#include <type_traits>
 #include <vector>
 
 #include "ab_tc.cuh"
@@ -57,6 +58,14 @@ struct RbGeom {
 constexpr int DBG_SLOTS = 8;   // 0 total, 1 mma wait operand, 2 mma wait weights, 3 epi wait acc, 4 producer wait, 5 tiles
 
 // ---- epilogue pieces (one item = 32 rows x 16 channels of one M tile) ---------------------------------------
+__device__ __forceinline__ void load_bias16(float (&bv)[16], const float* b) {   // 64-byte aligned shared memory
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const float4 f = *reinterpret_cast<const float4*>(b + 4 * q);
+    bv[4 * q] = f.x; bv[4 * q + 1] = f.y; bv[4 * q + 2] = f.z; bv[4 * q + 3] = f.w;
+  }
+}
+
 template <int BF16>
 __device__ __forceinline__ void store_operand16(uint8_t* buf, int RBrows, int ch, int brow, const float (&v)[16]) {
 #pragma unroll
@@ -294,39 +303,72 @@ __global__ void __launch_bounds__(RB_THREADS, 1) rb_kernel(RbParams p, RbGeom g)
           }
           ph_acc ^= 1u << slot;
           tc_fence_after();
+          // thread-private scratch of this slot: 16 contiguous floats per (item, lane) -> 4 x 16-byte accesses
+          float* scr_lane = scr ? scr + ((size_t)q4 * 32 + lane) * 16 : nullptr;
+          const size_t scr_item = (size_t)4 * 32 * 16;
           if (is_e1) {
             // ---- intermediate = lrelu(conv1 + b1) -> operand buffer, zero outside [0, T) (conv2's zero padding);
-            //      accumulator <- x_p (+ branch sum before the last conv): conv2 accumulates on the residual
+            //      accumulator <- x_p (+ branch sum before the last conv): conv2 accumulates on the residual.
+            //      The residual of the NEXT item is requested before this item is processed.
             const bool add_acp = pair == last_pair && p.acc_prev != nullptr;
-            for (int n = grp; n < nitems; n += 4) {
+            auto load_res = [&](float (&res)[16], int n) {
+              if (pair == 0) {
+                const int i = n / nch, ch = n - i * nch;
+                const int t = tbase + i * 128 + q4 * 32 + lane;
+                load_x16(res, p.x + bCT + (int64_t)(ch * 16) * p.T + t, t >= 0 && t < p.T, ch);
+              } else {
+                const float4* sp = reinterpret_cast<const float4*>(scr_lane + (size_t)n * scr_item);
+#pragma unroll
+                for (int qd = 0; qd < 4; ++qd) {
+                  const float4 f = sp[qd];
+                  res[4 * qd] = f.x; res[4 * qd + 1] = f.y; res[4 * qd + 2] = f.z; res[4 * qd + 3] = f.w;
+                }
+              }
+            };
+            auto process = [&](int n, float (&res)[16], auto with_acp) {
               const int i = n / nch, ch = n - i * nch;
               const int row = i * 128 + q4 * 32 + lane;
               const int t = tbase + row;
               const bool inr = t >= 0 && t < p.T;
-              const int64_t off0 = bCT + (int64_t)(ch * 16) * p.T + t;
-              float res[16], acp[16];
-              if (pair == 0) {
-                load_x16(res, p.x + off0, inr, ch);
-              } else {
-                const float* sp = scr + (size_t)(ch * 16) * g.R + row;
-#pragma unroll
-                for (int e = 0; e < 16; ++e) res[e] = sp[(size_t)e * g.R];
-              }
-              if (add_acp) load_acp16(acp, p.acc_prev + off0, inr, ch);
+              float acp[16];
+              if (with_acp.value) load_acp16(acp, p.acc_prev + bCT + (int64_t)(ch * 16) * p.T + t, inr, ch);
               uint32_t r[16];
               const uint32_t taddr = tslot + (uint32_t)(i * g.Np + ch * 16);
               tc_ld16(taddr, r);
+              float bv[16];
+              load_bias16(bv, bias_c + ch * 16);
               tc_wait_ld();
               float v[16];
 #pragma unroll
               for (int e = 0; e < 16; ++e) {
-                const float a = __uint_as_float(r[e]) + bias_c[ch * 16 + e];
+                const float a = __uint_as_float(r[e]) + bv[e];
                 v[e] = inr ? lrelu(a, p.slope) : 0.f;
               }
               store_operand16<BF16>(buf, g.RB, ch, row + g.G, v);
 #pragma unroll
-              for (int e = 0; e < 16; ++e) r[e] = __float_as_uint(add_acp ? res[e] + acp[e] : res[e]);
+              for (int e = 0; e < 16; ++e) r[e] = __float_as_uint(with_acp.value ? res[e] + acp[e] : res[e]);
               tc_st16(taddr, r);
+            };
+            if (add_acp) {   // last pair of a later branch: x_p and the branch sum, no look-ahead (register budget)
+              for (int n = grp; n < nitems; n += 4) {
+                float res[16];
+                load_res(res, n);
+                process(n, res, std::true_type{});
+              }
+            } else {
+              float res0[16], res1[16];
+              int n = grp;
+              if (n < nitems) load_res(res0, n);
+              while (n < nitems) {
+                const int n1 = n + 4, n2 = n + 8;
+                if (n1 < nitems) load_res(res1, n1);
+                process(n, res0, std::false_type{});
+                if (n1 < nitems) {
+                  if (n2 < nitems) load_res(res0, n2);
+                  process(n1, res1, std::false_type{});
+                }
+                n = n2;
+              }
             }
             tc_wait_st();
             publish_operand(slot);
@@ -345,17 +387,19 @@ __global__ void __launch_bounds__(RB_THREADS, 1) rb_kernel(RbParams p, RbGeom g)
               uint32_t r[16];
               const uint32_t taddr = tslot + (uint32_t)(i * g.Np + ch * 16);
               tc_ld16(taddr, r);
+              float bv[16];
+              load_bias16(bv, bias_c + ch * 16);
               tc_wait_ld();
               float a[16], v[16];
 #pragma unroll
               for (int e = 0; e < 16; ++e) {
-                a[e] = __uint_as_float(r[e]) + bias_c[ch * 16 + e];
+                a[e] = __uint_as_float(r[e]) + bv[e];
                 v[e] = inr ? lrelu(a[e], p.slope) : 0.f;
               }
               if (p.nconv == 2) {
-                float* sp = scr + (size_t)(ch * 16) * g.R + row;
+                float4* sp = reinterpret_cast<float4*>(scr_lane + (size_t)n * scr_item);
 #pragma unroll
-                for (int e = 0; e < 16; ++e) sp[(size_t)e * g.R] = a[e];
+                for (int qd = 0; qd < 4; ++qd) sp[qd] = make_float4(a[4 * qd], a[4 * qd + 1], a[4 * qd + 2], a[4 * qd + 3]);
               } else {
 #pragma unroll
                 for (int e = 0; e < 16; ++e) r[e] = __float_as_uint(add_acp ? a[e] + acp[e] : a[e]);
@@ -379,11 +423,13 @@ __global__ void __launch_bounds__(RB_THREADS, 1) rb_kernel(RbParams p, RbGeom g)
               const int64_t off0 = bCT + (int64_t)(ch * 16) * p.T + t;
               uint32_t r[16];
               tc_ld16(tslot + (uint32_t)(i * g.Np + ch * 16), r);
+              float bv[16];
+              load_bias16(bv, bias_c + ch * 16);
               tc_wait_ld();
               float v[16];
 #pragma unroll
               for (int e = 0; e < 16; ++e) {
-                const float a = (__uint_as_float(r[e]) + bias_c[ch * 16 + e]) * g.out_scale;
+                const float a = (__uint_as_float(r[e]) + bv[e]) * g.out_scale;
                 v[e] = a;
                 if (ok && ch * 16 + e < p.C) p.y[off0 + (int64_t)e * p.T] = a;
               }
@@ -455,6 +501,10 @@ __global__ void __launch_bounds__(RB_THREADS, 1) rb_kernel(RbParams p, RbGeom g)
     const int c = (p.k - 1) >> 1;
     uint32_t ph_opnd = 0u;
     int it = 0;
+    uint32_t next_ready = 0u;     // the weight stage `it` was already seen full by the previous stage's poll
+    int total_stages = 0;         // weight stages this CTA will consume (no poll beyond the last one)
+    for (int q = blockIdx.x; q < npairs_total; q += gridDim.x) total_stages += (2 * q + 1 < g.ntiles) ? 2 : 1;
+    total_stages *= g.nsteps * p.k * (g.nkc / g.kcs);
     long long wait_o = 0, wait_w = 0;
     for (int q = blockIdx.x; q < npairs_total; q += gridDim.x) {
       const int nact = (2 * q + 1 < g.ntiles) ? 2 : 1;
@@ -479,30 +529,40 @@ __global__ void __launch_bounds__(RB_THREADS, 1) rb_kernel(RbParams p, RbGeom g)
               const uint32_t arow = (uint32_t)(g.G + (j - c) * dil) * 2u;
               for (int kg = 0; kg < groups; ++kg, ++it) {
                 const int s = it % g.nstages;
-                const uint32_t ph = (uint32_t)(it / g.nstages) & 1u;
-                const long long t0 = g.dbg ? clock64() : 0;
-                mbar_wait(bar_full(s), ph, 31);
-                if (g.dbg) wait_w += clock64() - t0;
+                if (!next_ready) {
+                  const uint32_t ph = (uint32_t)(it / g.nstages) & 1u;
+                  const long long t0 = g.dbg ? clock64() : 0;
+                  mbar_wait(bar_full(s), ph, 31);
+                  if (g.dbg) wait_w += clock64() - t0;
+                }
+                next_ready = 0u;
                 tc_fence_after();
+                // the next stage's barrier is tested between the last MMAs of this stage (issue_stage's poll point)
+                const int sn = (it + 1) % g.nstages;
+                const uint32_t phn = (uint32_t)((it + 1) / g.nstages) & 1u;
+                const bool can_poll = it + 1 < total_stages;
+                auto poll = [&] { if (can_poll) next_ready = mbar_try_wait(bar_full(sn), phn); };
                 for (int kk = 0; kk < g.kcs; ++kk) {
                   const int kc = kg * g.kcs + kk;
                   const bool two = nks_total - kc * 2 >= 2;
                   const uint32_t alo = desc_lo_sw32(a16 + (uint32_t)(kc * 2) * kstepA + arow);
                   const uint32_t blo = desc_lo_sw32(w16 + (uint32_t)s * stage16 + (uint32_t)kk * chunk16);
-                  if (zero_init && (j | kc) == 0) issue_first(alo, blo, two);
-                  else issue_rest(alo, blo, two);
+                  const bool last = kk == g.kcs - 1;
+                  if (zero_init && (j | kc) == 0) issue_first(alo, blo, two, poll, last);
+                  else issue_rest(alo, blo, two, poll, last);
                 }
                 if (elected) tc_commit(bar_empty(s));
                 __syncwarp();
               }
             }
           };
-          auto generic = [&](uint32_t alo, uint32_t blo, bool two, uint32_t acc0) {
+          auto generic = [&](uint32_t alo, uint32_t blo, bool two, uint32_t acc0, auto& poll, bool last) {
             for (int h = 0; h < (two ? 2 : 1); ++h) {
               uint32_t ah = alo + (uint32_t)h * kstepA;
               const uint32_t bh = blo + (uint32_t)h * kstepB;
               uint32_t tdd = td;
               for (int i = 0; i < g.m; ++i) {
+                if (last && h == (two ? 1 : 0) && i == g.m - 1) poll();
                 if (elected) tc_mma_f16(tdd, hi | ah, hi | bh, g.idesc, h ? 1u : acc0);
                 ah += 256u;
                 tdd += (uint32_t)g.Np;
@@ -510,11 +570,13 @@ __global__ void __launch_bounds__(RB_THREADS, 1) rb_kernel(RbParams p, RbGeom g)
             }
           };
 #define AB_RUN(MM, KO)                                                                                            \
-  run_conv([&](uint32_t alo, uint32_t blo, bool two) {                                                            \
-             issue_stage<MM, KO, 1>(elected, td, (uint32_t)g.Np, hi, alo, blo, kstepA, kstepB, g.idesc, two);     \
+  run_conv([&](uint32_t alo, uint32_t blo, bool two, auto& poll, bool last) {                                     \
+             if (last) issue_stage<MM, KO, 1>(elected, td, (uint32_t)g.Np, hi, alo, blo, kstepA, kstepB, g.idesc, two, poll); \
+             else issue_stage<MM, KO, 1>(elected, td, (uint32_t)g.Np, hi, alo, blo, kstepA, kstepB, g.idesc, two); \
            },                                                                                                     \
-           [&](uint32_t alo, uint32_t blo, bool two) {                                                            \
-             issue_stage<MM, KO, 0>(elected, td, (uint32_t)g.Np, hi, alo, blo, kstepA, kstepB, g.idesc, two);     \
+           [&](uint32_t alo, uint32_t blo, bool two, auto& poll, bool last) {                                     \
+             if (last) issue_stage<MM, KO, 0>(elected, td, (uint32_t)g.Np, hi, alo, blo, kstepA, kstepB, g.idesc, two, poll); \
+             else issue_stage<MM, KO, 0>(elected, td, (uint32_t)g.Np, hi, alo, blo, kstepA, kstepB, g.idesc, two); \
            })
           if (g.m == 2 && !g.korder) AB_RUN(2, false);
           else if (g.m == 4 && g.korder) AB_RUN(4, true);
@@ -522,8 +584,8 @@ __global__ void __launch_bounds__(RB_THREADS, 1) rb_kernel(RbParams p, RbGeom g)
           else if (g.m == 1 && !g.korder) AB_RUN(1, false);
           else if (g.m == 16 && g.korder) AB_RUN(16, true);
           else
-            run_conv([&](uint32_t alo, uint32_t blo, bool two) { generic(alo, blo, two, 0u); },
-                     [&](uint32_t alo, uint32_t blo, bool two) { generic(alo, blo, two, 1u); });
+            run_conv([&](uint32_t alo, uint32_t blo, bool two, auto& poll, bool last) { generic(alo, blo, two, 0u, poll, last); },
+                     [&](uint32_t alo, uint32_t blo, bool two, auto& poll, bool last) { generic(alo, blo, two, 1u, poll, last); });
 #undef AB_RUN
           if (elected) tc_commit(bar_acc(slot));
           __syncwarp();

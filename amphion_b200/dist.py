@@ -81,59 +81,76 @@ def sharded_vocoder_forward(model, mels, group=None, dst=0, chunks=4):
     chunk i overlaps the last layer of chunk i+1 (side stream + the generator's ``tail_events``)."""
     ws = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
-    B = mels.shape[0]
-    lo, hi = shard_bounds(B, ws, rank)
     if ws == 1:
         return model(mels)
+    lo, hi = shard_bounds(mels.shape[0], ws, rank)
+    return _sharded_forward(model, mels[lo:hi], mels.shape[0], rank, ws, group, dst, chunks)
+
+
+def sharded_vocoder_inference(cfg, model, mels_local, n_global, group=None, dst=0, device=None, chunks=4):
+    """The multi-GPU form of ``vocoder_inference`` (models/vocoders/gan/gan_vocoder_inference.py:11-38): every
+    rank passes ITS shard of the batch (``shard_bounds(n_global, world, rank)``, host or device, any strides), runs
+    the generator on it and the wav shards are gathered to ``dst``, which returns the reference's result type —
+    a detached CPU tensor [n_global, T*hop] in global utterance order; the other ranks return ``None``."""
+    ws = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    model.eval()
+    with torch.no_grad():
+        if device is None:
+            device = next(model.parameters()).device
+        mels_local = mels_local.to(device, non_blocking=True)
+        if ws == 1:
+            return model(mels_local).squeeze(1).detach().cpu()
+        wav = _sharded_forward(model, mels_local, n_global, rank, ws, group, dst, chunks)
+        return wav.squeeze(1).detach().cpu() if rank == dst else None
+
+
+def _sharded_forward(model, mel_local, B, rank, ws, group, dst, chunks):
+    lo, hi = shard_bounds(B, ws, rank)
+    if mel_local.shape[0] != hi - lo:
+        raise ValueError(f"rank {rank} holds {mel_local.shape[0]} utterances, its shard of {B} has {hi - lo}")
     fwd = model.forward if hasattr(model, "forward") else model
-    cuda = mels.is_cuda
-    use_events = cuda and _supports(fwd, "tail_events") and chunks > 1
+    use_events = mel_local.is_cuda and _supports(fwd, "tail_events") and chunks > 1
     use_out = _supports(fwd, "out")
-    out = None
-    local = None
+    out = local = None
     events = [torch.cuda.Event() for _ in range(chunks)] if use_events else None
+    kw = {"tail_events": events} if use_events else {}
     if rank == dst:
-        # shape of one utterance's result: from this rank's forward when it has items, else from a 1-item probe
+        hop = _hop_of(model)
+        if hop is not None:
+            out = torch.empty((B, 1, mel_local.shape[-1] * hop), device=mel_local.device, dtype=torch.float32)
         if hi > lo:
-            if use_out:
-                hop = _hop_of(model)
-                if hop is not None:
-                    out = torch.empty((B, 1, mels.shape[-1] * hop), device=mels.device, dtype=torch.float32)
-                    kw = dict(out=out[lo:hi])
-                    if use_events:
-                        kw["tail_events"] = events
-                    local = model(mels[lo:hi], **kw)
-            if local is None:
-                local = model(mels[lo:hi], **({"tail_events": events} if use_events else {}))
-        else:
-            hop = _hop_of(model)
-            if hop is None:
-                raise ValueError("sharded forward: the destination rank needs at least one item (or a model with cfg)")
-            out = torch.empty((B, 1, mels.shape[-1] * hop), device=mels.device, dtype=torch.float32)
+            if out is not None and use_out:
+                local = model(mel_local, out=out[lo:hi], **kw)
+            else:
+                local = model(mel_local, **kw)
+        elif out is None:
+            raise ValueError("sharded forward: a destination rank without items needs a model with cfg.preprocess.hop_size")
     elif hi > lo:
-        local = model(mels[lo:hi], **({"tail_events": events} if use_events else {}))
+        local = model(mel_local, **kw)
     if not use_events:
         res, works = gather_shards(local, B, ws, rank, group, dst, out=out)
         for w in works:
             w.wait()
         return res
     # chunked exchange on a side stream: chunk i is sent / received as soon as its event fired
-    main = torch.cuda.current_stream(mels.device)
-    side = _side_stream(mels.device)
+    main = torch.cuda.current_stream(mel_local.device)
+    side = _side_stream(mel_local.device)
     res, all_works = out, []
     with torch.cuda.stream(side):
+        if hi <= lo:
+            side.wait_stream(main)
         for i in range(chunks):
             if hi > lo:
                 side.wait_event(events[i])
-            elif i == 0:
-                side.wait_stream(main)
             res, works = gather_shards(local, B, ws, rank, group, dst, out=res if rank == dst else None, chunk=(i, chunks))
             all_works += works
         for w in all_works:
             w.wait()
     main.wait_stream(side)
-    if local is not None:
-        local.record_stream(side)
+    for t in (local, out):
+        if t is not None:
+            t.record_stream(side)
     return res if rank == dst else None
 
 
