@@ -28,6 +28,18 @@ int fail(int code, const char* fmt, ...);
       return ::ab::fail(AB_ERR_CUDA, "launch of %s failed: %s", what, cudaGetErrorString(_e)); \
   } while (0)
 
+// cudaFuncSetAttribute is per device: `flags` (one static array per call site) remembers which devices were set up
+struct DeviceOnce {
+  bool done[64] = {};
+  bool need() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;
+    if (done[dev]) return false;
+    done[dev] = true;
+    return true;
+  }
+};
+
 static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 

@@ -255,12 +255,10 @@ int launch_conv1d_fp32(const ConvParams& p, cudaStream_t s) {
   if (p.Cout <= 4) {
     const size_t smem = sizeof(float) * ((size_t)PCI * (PT + halo) + (size_t)p.Cin * p.k * p.Cout);
     if (smem > 200 * 1024) return fail(AB_ERR_UNSUPPORTED, "conv1d(few-out): filter too large for smem");
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
+    static DeviceOnce configured;
+    if (smem > 48 * 1024 && configured.need())
       AB_CUDA_TRY(cudaFuncSetAttribute(conv1d_fewout_fp32_kernel,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      configured = 200 * 1024;
-    }
     dim3 grid((unsigned)ceil_div(p.T, PT), 1, (unsigned)p.B);
     conv1d_fewout_fp32_kernel<<<grid, NT, smem, s>>>(p);
     AB_LAUNCH_CHECK("conv1d_fewout_fp32_kernel");
@@ -269,11 +267,10 @@ int launch_conv1d_fp32(const ConvParams& p, cudaStream_t s) {
   const size_t smem = sizeof(float) * ((size_t)CI_T * (TT + halo) + (size_t)CI_T * p.k * CO_T);
   if (smem > 200 * 1024)
     return fail(AB_ERR_UNSUPPORTED, "conv1d: k=%d dilation=%d needs %zu B of shared memory", p.k, p.d, smem);
-  static bool configured = false;
-  if (smem > 48 * 1024 && !configured) {
+  static DeviceOnce configured;
+  if (smem > 48 * 1024 && configured.need()) {
     AB_CUDA_TRY(cudaFuncSetAttribute(conv1d_fp32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      200 * 1024));
-    configured = true;
   }
   if (ceil_div(p.Cout, CO_T) > 65535) return fail(AB_ERR_UNSUPPORTED, "conv1d: too many channels");
   dim3 grid((unsigned)ceil_div(p.T, TT), (unsigned)ceil_div(p.Cout, CO_T), (unsigned)p.B);
@@ -382,11 +379,10 @@ int launch_conv_transpose1d_fp32(const ConvTParams& p, cudaStream_t s) {
   const int XW = TT / p.u + 2 + M;
   const size_t smem = sizeof(float) * ((size_t)CI_T * XW + (size_t)CI_T * p.k * CO_T);
   if (smem > 200 * 1024) return fail(AB_ERR_UNSUPPORTED, "conv_transpose1d: kernel %d too large", p.k);
-  static bool configured = false;
-  if (smem > 48 * 1024 && !configured) {
+  static DeviceOnce configured;
+  if (smem > 48 * 1024 && configured.need()) {
     AB_CUDA_TRY(cudaFuncSetAttribute(convT_fp32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      200 * 1024));
-    configured = true;
   }
   const int64_t Tout = (int64_t)p.Tin * p.u;
   dim3 grid((unsigned)ceil_div(Tout, TT), (unsigned)ceil_div(p.Cout, CO_T), (unsigned)p.B);

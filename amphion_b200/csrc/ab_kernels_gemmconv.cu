@@ -809,10 +809,9 @@ int launch_gemmconv_stream(const GsParams& p, cudaStream_t s) {
   const uint32_t fmt = p.precision == AB_PREC_TC_BF16 ? 1u : 0u;
   g.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(g.Nb >> 3) << 17) | ((128u >> 4) << 24);
   g.out_scale = 1.0f / p.out_div;
-  static bool configured = false;
-  if (!configured) {
+  static DeviceOnce configured;
+  if (configured.need()) {
     AB_CUDA_TRY(cudaFuncSetAttribute(gemmconv_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GC_SMEM_LIMIT));
-    configured = true;
   }
   const int64_t grid = (int64_t)p.B * g.tiles;
   if (grid > 0x7fffffffll) return fail(AB_ERR_UNSUPPORTED, "gemmconv(stream): grid too large");
@@ -857,10 +856,9 @@ int launch_gemmconv(const GcParams& p, cudaStream_t s) {
   if (rc != AB_OK) return rc;
   if (p.yimg != nullptr && !(p.mode == 1 && g.grouped && (p.Cout % 16) == 0))
     return fail(AB_ERR_UNSUPPORTED, "gemmconv: cannot emit an operand image for this layer");
-  static bool configured = false;
-  if (!configured) {
+  static DeviceOnce configured;
+  if (configured.need()) {
     AB_CUDA_TRY(cudaFuncSetAttribute(gemmconv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GC_SMEM_LIMIT));
-    configured = true;
   }
   const int64_t grid = (int64_t)p.B * g.tiles;
   if (grid > 0x7fffffffll) return fail(AB_ERR_UNSUPPORTED, "gemmconv: grid too large");

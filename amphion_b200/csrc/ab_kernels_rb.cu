@@ -698,11 +698,10 @@ int launch_rb(const RbParams& p, cudaStream_t s) {
   if (p.npairs > 1 && !p.scratch) return fail(AB_ERR_ARG, "rb: a fused chain needs the scratch buffer");
   int dev = 0;
   AB_CUDA_TRY(cudaGetDevice(&dev));
-  static bool configured[64] = {};
-  if (dev < 64 && !configured[dev]) {
+  static DeviceOnce configured;
+  if (configured.need()) {
     AB_CUDA_TRY(cudaFuncSetAttribute(rb_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RB_SMEM_LIMIT));
     AB_CUDA_TRY(cudaFuncSetAttribute(rb_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RB_SMEM_LIMIT));
-    configured[dev] = true;
   }
   static int nsm = 0;
   if (!nsm) AB_CUDA_TRY(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));

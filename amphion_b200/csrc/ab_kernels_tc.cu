@@ -639,8 +639,8 @@ int launch_tc_conv(const TcConvParams& p, cudaStream_t s) {
   TcGeom g;
   int rc = make_geom(p, g);
   if (rc != AB_OK) return rc;
-  static bool configured = false;
-  if (!configured) {
+  static DeviceOnce configured;
+  if (configured.need()) {
     AB_CUDA_TRY(cudaFuncSetAttribute(tc_conv_kernel<8, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_LIMIT));
     AB_CUDA_TRY(cudaFuncSetAttribute(tc_conv_kernel<8, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_LIMIT));
     AB_CUDA_TRY(cudaFuncSetAttribute(tc_conv_kernel<4, 2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
@@ -649,7 +649,6 @@ int launch_tc_conv(const TcConvParams& p, cudaStream_t s) {
     AB_CUDA_TRY(cudaFuncSetAttribute(tc_conv_kernel<8, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_LIMIT));
     AB_CUDA_TRY(cudaFuncSetAttribute(tc_conv_kernel<4, 3, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 74 * 1024));
     AB_CUDA_TRY(cudaFuncSetAttribute(tc_conv_kernel<4, 3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 74 * 1024));
-    configured = true;
   }
   const int64_t grid = (int64_t)p.B * g.tiles;
   if (grid > 0x7fffffffll) return fail(AB_ERR_UNSUPPORTED, "tc_conv: grid too large");

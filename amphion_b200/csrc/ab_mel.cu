@@ -7,7 +7,9 @@
 // so the complex spectrum is bit-identical to torch.stft's on the same device.
 #include <cufft.h>
 
+#include <algorithm>
 #include <map>
+#include <vector>
 
 #include "ab_common.cuh"
 
@@ -16,8 +18,9 @@ using namespace ab;
 struct ab_mel {
   ab_mel_config cfg;
   int bins;
-  std::map<int64_t, cufftHandle> plans;   // batch (B*F) -> plan
+  std::map<int64_t, cufftHandle> plans;   // batch (B*F) -> plan; bounded LRU (variable-length corpora)
   std::map<int64_t, size_t> plan_ws;
+  std::vector<int64_t> plan_lru;          // most recently used last
 };
 
 namespace {
@@ -138,11 +141,24 @@ const char* cufft_err(cufftResult r) {
   } while (0)
 
 int get_plan(ab_mel* m, int64_t batch, cufftHandle* plan, size_t* ws) {
+  constexpr size_t kMaxPlans = 8;
+  auto touch = [&](int64_t b) {
+    auto& l = m->plan_lru;
+    l.erase(std::remove(l.begin(), l.end(), b), l.end());
+    l.push_back(b);
+  };
   auto it = m->plans.find(batch);
   if (it != m->plans.end()) {
     *plan = it->second;
     *ws = m->plan_ws[batch];
+    touch(batch);
     return AB_OK;
+  }
+  while (m->plans.size() >= kMaxPlans && !m->plan_lru.empty()) {   // evict the least recently used plan
+    const int64_t old = m->plan_lru.front();
+    m->plan_lru.erase(m->plan_lru.begin());
+    auto ev = m->plans.find(old);
+    if (ev != m->plans.end()) { cufftDestroy(ev->second); m->plans.erase(ev); m->plan_ws.erase(old); }
   }
   if (batch > 0x7fffffffll) return fail(AB_ERR_UNSUPPORTED, "mel: too many frames");
   cufftHandle h;
@@ -153,6 +169,7 @@ int get_plan(ab_mel* m, int64_t batch, cufftHandle* plan, size_t* ws) {
   AB_CUFFT_TRY(cufftMakePlanMany(h, 1, n, nullptr, 1, 0, nullptr, 1, 0, CUFFT_R2C, (int)batch, &sz));
   m->plans[batch] = h;
   m->plan_ws[batch] = sz;
+  touch(batch);
   *plan = h;
   *ws = sz;
   return AB_OK;
@@ -244,11 +261,9 @@ int ab_mel_forward(ab_mel* m, const float* dev_wav, int64_t B, int64_t T, const 
   }
   const size_t smem = (size_t)m->bins * (FT + 1) * sizeof(float);
   if (smem > 200 * 1024) return fail(AB_ERR_UNSUPPORTED, "mel_forward: n_fft=%d too large", m->cfg.n_fft);
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && configured < smem) {
+  static DeviceOnce configured;
+  if (smem > 48 * 1024 && configured.need())
     AB_CUDA_TRY(cudaFuncSetAttribute(mag_mel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    configured = 200 * 1024;
-  }
   dim3 grid((unsigned)ceil_div(L.F, FT), (unsigned)B);
   mag_mel_kernel<<<grid, 256, smem, st>>>(spec, dev_mel_basis, span, dev_mag, dev_mel, dev_energy, (int)L.F,
                                           m->bins, m->cfg.n_mel, m->cfg.eps, m->cfg.clamp);

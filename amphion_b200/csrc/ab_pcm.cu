@@ -48,7 +48,12 @@ __global__ void pcm_quant_kernel(const float* __restrict__ w, int64_t row_stride
   const int b = blockIdx.y;
   const int64_t n = lengths ? min(lengths[b], T) : T;
   float ratio = 1.0f;
-  if (peak_bits != nullptr) ratio = volume_peak / __uint_as_float(peak_bits[b]);   // IEEE division, as numpy's
+  if (peak_bits != nullptr) {
+    const float peak = __uint_as_float(peak_bits[b]);
+    // all-zero utterance: the reference divides by zero there (0 * inf = NaN samples, utils/io.py:60-62);
+    // a silent waveform stays silent instead
+    ratio = peak > 0.f ? volume_peak / peak : 1.0f;   // IEEE division, as numpy's
+  }
   const float* row = w + (int64_t)b * row_stride;
   int16_t* orow = out + (int64_t)b * out_stride;
   // pairs of samples -> one 32-bit store (out rows are 4-byte aligned: out_stride is even, checked on the host)

@@ -69,7 +69,8 @@ def native_stft_mel(y, n_fft, hop, win, window, basis, pad, eps, want_mag=False,
     y = y.contiguous().float()
     B, T = y.shape
     n_mel = int(basis.shape[0]) if (want_mel and basis is not None) else 0
-    key = (n_fft, hop, win, n_mel, pad, float(eps), float(clamp))
+    # cuFFT plans belong to a device: one handle per (configuration, device)
+    key = (n_fft, hop, win, n_mel, pad, float(eps), float(clamp), str(y.device))
     if key not in _handles:
         h = C.c_void_p()
         cfg = _capi.MelConfig(n_fft, hop, win, n_mel, pad, eps, clamp)

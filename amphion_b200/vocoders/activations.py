@@ -111,8 +111,9 @@ class Activation1d(nn.Module):
         fu = self.upsample.filter.reshape(-1).float().contiguous()
         fd = self.downsample.lowpass.filter.reshape(-1).float().contiguous()
         B, Cn, T = x.shape
-        _capi.check(_capi.lib.ab_activation1d_forward(
-            _capi.ptr(x), _capi.ptr(y), B, Cn, T, _capi.ptr(alpha), _capi.ptr(beta),
-            int(bool(self.act.alpha_logscale)), _capi.ptr(fu), _capi.ptr(fd), _capi.stream_ptr()),
-            "ab_activation1d_forward")
+        with torch.cuda.device(x.device):   # the launch and the stream belong to x's device
+            _capi.check(_capi.lib.ab_activation1d_forward(
+                _capi.ptr(x), _capi.ptr(y), B, Cn, T, _capi.ptr(alpha), _capi.ptr(beta),
+                int(bool(self.act.alpha_logscale)), _capi.ptr(fu), _capi.ptr(fd), _capi.stream_ptr()),
+                "ab_activation1d_forward")
         return y

@@ -234,6 +234,38 @@ class NativeGenerator(nn.Module):
         return {arr[i].name.decode(): dict(launches=arr[i].launches, ms=arr[i].ms, flops=arr[i].flops,
                                            bytes=arr[i].bytes) for i in range(n.value)}
 
+    # ---- native state is derived: never copied / pickled, rebuilt on the next forward ---------------
+    def invalidate(self):
+        """Drop the packed weight arena so the next forward re-reads the parameters.  Needed after edits that do
+        not bump a tensor's version counter (``p.data.copy_()``, ``m.weight.data.normal_()``); ``load_state_dict``,
+        ``.to()`` / ``.cuda()`` and ``remove_weight_norm`` call it themselves."""
+        self._arena_key = None
+
+    def load_state_dict(self, *args, **kwargs):
+        out = super().load_state_dict(*args, **kwargs)
+        self.invalidate()
+        return out
+
+    def _apply(self, fn, *args, **kwargs):
+        out = super()._apply(fn, *args, **kwargs)
+        self.invalidate()
+        return out
+
+    def __getstate__(self):
+        state = self.__dict__.copy()
+        for k in ("_handle", "_arena", "_arena_key", "_workspace"):   # ctypes handle / device scratch: not state
+            state[k] = None
+        return state
+
+    def __deepcopy__(self, memo):
+        import copy
+        cls = self.__class__
+        new = cls.__new__(cls)
+        memo[id(self)] = new
+        for k, v in self.__getstate__().items():
+            setattr(new, k, copy.deepcopy(v, memo))
+        return new
+
     def __del__(self):
         try:
             if self._handle is not None:

@@ -19,7 +19,9 @@ def save_audio_float(waveform, fs, add_silence=False, turn_up=False, volume_peak
     """-> float32 [1, T'] exactly as handed to torchaudio.save (:70-76)."""
     waveform = np.asarray(waveform, np.float32)
     if turn_up:  # :59-62 (numpy 2 scalar promotion: the ratio is float32)
-        ratio = np.float32(volume_peak) / max(waveform.max(), abs(waveform.min()))
+        peak = max(waveform.max(), abs(waveform.min()))
+        # an all-zero waveform makes the reference divide by zero (NaN samples); the product keeps it silent
+        ratio = np.float32(volume_peak) / peak if peak > 0 else np.float32(1.0)
         waveform = waveform * ratio
     if add_silence:  # :64-68
         silence = np.zeros((fs // 20,), dtype=waveform.dtype)

@@ -645,3 +645,90 @@ def test_resblock_fusion_odd_channels_and_wide_kernel():
         model.set_option("resblock_fusion", mode)
         got = model(mel.to(DEV)).cpu().numpy()
         assert np.abs(got - want).max() <= 1e-3, (mode, np.abs(got - want).max())
+
+
+# ---- parity where 16-bit operands can bite -------------------------------------------------------
+def _trained_like(model, seed):
+    """Give a random-init model the dynamic range of a trained checkpoint without changing its fp32 function much:
+    every (c1, c2) pair of a ResBlock gets c1 scaled by s and c2 by 1/s, s = 10^U(-1.5, 1.5) (leaky_relu is
+    positively homogeneous, so only the intermediate's magnitude moves: 0.03x .. 30x), the weight-norm gains carry
+    the scale (weight_g spanning three decades), and ~1 % of the direction entries are 10x outliers."""
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for name, mod in model.named_modules():
+            if hasattr(mod, "convs1") and hasattr(mod, "convs2"):
+                for c1, c2 in zip(mod.convs1, mod.convs2):
+                    s = float(10.0 ** (torch.rand((), generator=g) * 3.0 - 1.5))
+                    c1.weight_g.mul_(s)
+                    c1.bias.mul_(s)
+                    c2.weight_g.div_(s)
+        for n, p in model.named_parameters():
+            if n.endswith("weight_v"):
+                mask = torch.rand(p.shape, generator=g) < 0.01
+                p[mask] *= 10.0
+    if hasattr(model, "invalidate"):
+        model.invalidate()
+    return model
+
+
+@pytest.mark.parametrize("kind,hp,n_mel,B,T,seed", [("hifigan", HP_V1, 80, 2, 40, 21), ("bigvgan", HP_BIGVGAN_BASE, 100, 1, 24, 22)])
+@pytest.mark.parametrize("stress", ["logmel_input", "trained_like_weights", "both"])
+def test_tensor_core_path_holds_1e3_under_trained_like_dynamic_range(kind, hp, n_mel, B, T, seed, stress):
+    """Full-width V1 / BigVGAN-base on the default tensor-core path (fp16 operands, fp32 accumulate) against the
+    fp32 CPU oracle with (i) mel ~ U(-11.5, 2), the log-mel range of utils/mel.py:11, and (ii) weight-norm
+    gains spanning three decades plus outlier weights.  Bar: 1e-3 max-abs (north star)."""
+    model = build_model(kind, hp, n_mel, seed=seed)
+    if kind == "bigvgan":
+        randomize_snake(model, seed + 1, hp["snake_logscale"])
+    if stress in ("trained_like_weights", "both"):
+        _trained_like(model, seed + 2)
+    gm = torch.Generator().manual_seed(seed + 3)
+    mel = torch.rand(B, n_mel, T, generator=gm) * 13.5 - 11.5 if stress != "trained_like_weights" else torch.randn(B, n_mel, T, generator=gm)
+    want = og.generator_forward(kind, sd_numpy(model), hp, mel.numpy())
+    model = model.to(DEV)
+    model.precision = "tc_f16"
+    got = model(mel.to(DEV)).cpu().numpy()
+    assert np.isfinite(got).all()
+    err = np.abs(got - want).max()
+    print(f"max|tc_f16 - oracle| {kind} {stress}: {err:.3e} (|wav| max {np.abs(want).max():.3f})")
+    assert err <= 1e-3, (stress, err)
+
+
+def _full_size_consistency(kind, hp, n_mel, B, T, seed, win_lo):
+    """Full BASELINE size on the default precision, tied to oracle-checked sizes through size-independent
+    properties (the CPU oracle cannot afford the full batch): batch independence, right-edge locality and an
+    oracle-checked interior window."""
+    hop = int(np.prod(hp["upsample_rates"]))
+    model = build_model(kind, hp, n_mel, seed=seed)
+    if kind == "bigvgan":
+        randomize_snake(model, seed + 1, hp["snake_logscale"])
+    sd = sd_numpy(model)
+    model = model.to(DEV)
+    mel = torch.randn(B, n_mel, T, generator=torch.Generator().manual_seed(seed + 2)).to(DEV)
+    wav = model(mel)
+    assert wav.shape == (B, 1, T * hop) and torch.isfinite(wav).all() and wav.abs().max() <= 1.0
+    for b in (0, B - 1):
+        assert torch.equal(model(mel[b:b + 1])[0], wav[b])                        # batch independence
+    prefix = model(mel[1:2, :, :256])
+    far = (256 - 48) * hop
+    assert torch.equal(prefix[..., :far], wav[1:2, :, :far])                      # right-edge locality
+    lo, hi = win_lo, win_lo + 72                                                  # 72-frame window, interior 24 frames
+    want = og.generator_forward(kind, sd, hp, mel[B // 2: B // 2 + 1, :, lo:hi].cpu().numpy())
+    got = wav[B // 2: B // 2 + 1, :, lo * hop: hi * hop].cpu().numpy()
+    mid = slice(24 * hop, 48 * hop)
+    err = np.abs(got[..., mid] - want[..., mid]).max()
+    print(f"full-size {kind} B={B} T={T}: interior max|cuda - oracle| = {err:.3e}")
+    assert err <= 1e-3, err
+
+
+def test_config3_full_size_is_consistent_with_checked_sizes():
+    """BASELINE config 3: BigVGAN-base 24 kHz, batch 32, 100 x 1024 mel."""
+    _full_size_consistency("bigvgan", HP_BIGVGAN_BASE, 100, 32, 1024, seed=303, win_lo=480)
+
+
+def test_config5_shard_full_size_is_consistent_with_checked_sizes():
+    """BASELINE config 5, one GPU's shard: BigVGAN-large 24 kHz (1536 ch, six stages), batch 32, 100 x 2048 mel."""
+    hp = dict(resblock="1", upsample_rates=[4, 4, 2, 2, 2, 2], upsample_kernel_sizes=[8, 8, 4, 4, 4, 4],
+              upsample_initial_channel=1536, resblock_kernel_sizes=[3, 7, 11],
+              resblock_dilation_sizes=[[1, 3, 5]] * 3, activation="snakebeta", snake_logscale=True)
+    _full_size_consistency("bigvgan", hp, 100, 32, 2048, seed=505, win_lo=1000)

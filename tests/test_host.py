@@ -222,3 +222,59 @@ def test_f0_padding_and_argument_checks_run_before_any_device_work():
         vits_g(torch.zeros(2, 24, 4), g=torch.zeros(2, 7, 1))   # wrong gin
     with pytest.raises(NotImplementedError):
         vits_g(torch.zeros(2, 24, 4), g=torch.zeros(2, 10, 4))  # time-varying conditioning
+
+
+def test_checkpoint_resolution_follows_the_reference_layout(tmp_path):
+    """models/vocoders/vocoder_inference.py:443-451: an experiment directory is searched under checkpoint/ for the
+    highest epoch (names with "audio" skipped); accelerate writes pytorch_model.bin or model.safetensors; a directory
+    that is one epoch-*_step-* checkpoint, or a plain file, is taken as is."""
+    import torch
+    from safetensors.torch import save_file
+    from amphion_b200.vocoders.vocoder_inference import _read_state_dict, resolve_checkpoint
+    exp = tmp_path / "exp"
+    for name, fname in (("epoch-0002_step-0000200_loss-0.9", "pytorch_model.bin"),
+                        ("epoch-0011_step-0001100_loss-0.5", "model.safetensors"),
+                        ("epoch-0007_step-0000700_loss-0.7", "pytorch_model.bin"),
+                        ("epoch-0099_audio", "pytorch_model.bin")):
+        d = exp / "checkpoint" / name
+        d.mkdir(parents=True)
+        sd = {"conv_pre.bias": torch.full((3,), float(name.split("-")[1][:4]))}
+        if fname.endswith(".bin"):
+            torch.save(sd, d / fname)
+        else:
+            save_file(sd, str(d / fname))
+    best = resolve_checkpoint(str(exp))
+    assert best.endswith("epoch-0011_step-0001100_loss-0.5/model.safetensors")
+    assert float(_read_state_dict(best)["conv_pre.bias"][0]) == 11.0
+    one = str(exp / "checkpoint" / "epoch-0007_step-0000700_loss-0.7")
+    assert resolve_checkpoint(one) == os.path.join(one, "pytorch_model.bin")
+    pt = tmp_path / "legacy.pt"
+    torch.save({"generator_state_dict": {"module.conv_pre.bias": torch.zeros(3)}}, pt)
+    assert resolve_checkpoint(str(pt)) == str(pt)
+    assert list(_read_state_dict(str(pt))) == ["module.conv_pre.bias"]
+    with pytest.raises(FileNotFoundError):
+        resolve_checkpoint(str(tmp_path))
+
+
+def test_native_state_is_not_copied_or_pickled(tmp_path):
+    """The ctypes handle / packed arena are derived state: deepcopy and torch.save of a model work (also after the
+    handle exists) and the copy starts without native state; in-place `.data` edits need `invalidate()`."""
+    import copy
+    import torch
+    kind, hp, n_mel = GOLDEN_MODELS["hifigan_rb1"]
+    m = build_model(kind, hp, n_mel, seed=3)
+    m.remove_weight_norm()                   # torch cannot deepcopy the derived .weight of old-style weight_norm
+    m._ensure_handle()                       # what a first forward leaves behind (no GPU needed for the handle)
+    m._arena_key = ("fake",)
+    c = copy.deepcopy(m)
+    assert c._handle is None and c._arena_key is None and m._handle is not None
+    assert all(torch.equal(a, b) for a, b in zip(m.state_dict().values(), c.state_dict().values()))
+    torch.save(m, tmp_path / "m.pt")
+    r = torch.load(tmp_path / "m.pt", weights_only=False)
+    assert r._handle is None and list(r.state_dict()) == list(m.state_dict())
+    m._arena_key = ("fake",)
+    m.load_state_dict(c.state_dict())
+    assert m._arena_key is None              # load_state_dict invalidates the packed weights
+    m._arena_key = ("fake",)
+    m.invalidate()
+    assert m._arena_key is None
