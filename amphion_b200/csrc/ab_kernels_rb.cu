@@ -45,7 +45,9 @@ struct RbGeom {
   int Hlo, V;                   // row of the first valid output, valid outputs per tile
   int tiles, ntiles;            // per sequence, total
   int nsteps;                   // convs per tile
-  int kcs;                      // 32-channel chunks per weight stage
+  int cps;                      // weight chunks (tap, 32 channels) per stage, in image order (tap-major)
+  int poll;                     // debug: test the next stage's barrier between the MMAs of a stage
+  int skip;                     // debug timing experiments (AB_RB_DEBUG_SKIP bitmask), results are wrong
   int nstages;
   uint32_t stage_bytes, chunk_bytes;
   uint32_t off_buf1, off_w, off_bias, off_bar, smem_bytes;
@@ -216,14 +218,25 @@ __global__ void __launch_bounds__(RB_THREADS, 1) rb_kernel(RbParams p, RbGeom g)
       }
     };
     // 16 fp32 x values of one item (rows of this lane), zero outside [0, T) / beyond C
+    const bool sk_ld = g.skip & 1, sk_st = g.skip & 2, sk_tm = g.skip & 4, sk_sm = g.skip & 8;   // debug timing only
     auto load_x16 = [&](float (&d)[16], const float* base, bool inr, int ch) {
+      if (sk_ld) inr = false;
 #pragma unroll
       for (int e = 0; e < 16; ++e) d[e] = (inr && ch * 16 + e < p.C) ? __ldg(base + (int64_t)e * p.T) : 0.f;
     };
     auto load_acp16 = [&](float (&d)[16], const float* base, bool inr, int ch) {   // may alias y: plain loads
+      if (sk_ld) inr = false;
 #pragma unroll
       for (int e = 0; e < 16; ++e) d[e] = (inr && ch * 16 + e < p.C) ? base[(int64_t)e * p.T] : 0.f;
     };
+    auto tld16 = [&](uint32_t taddr, uint32_t (&r)[16]) {
+      if (!sk_tm) tc_ld16(taddr, r);
+      else {
+#pragma unroll
+        for (int e = 0; e < 16; ++e) r[e] = 0u;
+      }
+    };
+    auto tst16 = [&](uint32_t taddr, const uint32_t (&r)[16]) { if (!sk_tm) tc_st16(taddr, r); };
     // accumulator init of a slot from x (nconv == 1: the first conv accumulates on the residual)
     auto init_acc_from_x = [&](int slot, int tile_id) {
       const int b = tile_id / g.tiles, tl = tile_id - b * g.tiles;
@@ -247,7 +260,7 @@ __global__ void __launch_bounds__(RB_THREADS, 1) rb_kernel(RbParams p, RbGeom g)
         uint32_t r[16];
 #pragma unroll
         for (int e = 0; e < 16; ++e) r[e] = __float_as_uint(res[e]);
-        tc_st16(tslot + (uint32_t)(i * g.Np + ch * 16), r);
+        tst16(tslot + (uint32_t)(i * g.Np + ch * 16), r);
       }
       tc_wait_st();
     };
@@ -320,7 +333,7 @@ __global__ void __launch_bounds__(RB_THREADS, 1) rb_kernel(RbParams p, RbGeom g)
                 const float4* sp = reinterpret_cast<const float4*>(scr_lane + (size_t)n * scr_item);
 #pragma unroll
                 for (int qd = 0; qd < 4; ++qd) {
-                  const float4 f = sp[qd];
+                  const float4 f = sk_ld ? make_float4(0.f, 0.f, 0.f, 0.f) : sp[qd];
                   res[4 * qd] = f.x; res[4 * qd + 1] = f.y; res[4 * qd + 2] = f.z; res[4 * qd + 3] = f.w;
                 }
               }
@@ -334,7 +347,7 @@ __global__ void __launch_bounds__(RB_THREADS, 1) rb_kernel(RbParams p, RbGeom g)
               if (with_acp.value) load_acp16(acp, p.acc_prev + bCT + (int64_t)(ch * 16) * p.T + t, inr, ch);
               uint32_t r[16];
               const uint32_t taddr = tslot + (uint32_t)(i * g.Np + ch * 16);
-              tc_ld16(taddr, r);
+              tld16(taddr, r);
               float bv[16];
               load_bias16(bv, bias_c + ch * 16);
               tc_wait_ld();
@@ -344,10 +357,10 @@ __global__ void __launch_bounds__(RB_THREADS, 1) rb_kernel(RbParams p, RbGeom g)
                 const float a = __uint_as_float(r[e]) + bv[e];
                 v[e] = inr ? lrelu(a, p.slope) : 0.f;
               }
-              store_operand16<BF16>(buf, g.RB, ch, row + g.G, v);
+              if (!sk_sm) store_operand16<BF16>(buf, g.RB, ch, row + g.G, v);
 #pragma unroll
               for (int e = 0; e < 16; ++e) r[e] = __float_as_uint(with_acp.value ? res[e] + acp[e] : res[e]);
-              tc_st16(taddr, r);
+              tst16(taddr, r);
             };
             if (add_acp) {   // last pair of a later branch: x_p and the branch sum, no look-ahead (register budget)
               for (int n = grp; n < nitems; n += 4) {
@@ -386,7 +399,7 @@ __global__ void __launch_bounds__(RB_THREADS, 1) rb_kernel(RbParams p, RbGeom g)
               if (add_acp) load_acp16(acp, p.acc_prev + bCT + (int64_t)(ch * 16) * p.T + t, inr, ch);
               uint32_t r[16];
               const uint32_t taddr = tslot + (uint32_t)(i * g.Np + ch * 16);
-              tc_ld16(taddr, r);
+              tld16(taddr, r);
               float bv[16];
               load_bias16(bv, bias_c + ch * 16);
               tc_wait_ld();
@@ -399,13 +412,14 @@ __global__ void __launch_bounds__(RB_THREADS, 1) rb_kernel(RbParams p, RbGeom g)
               if (p.nconv == 2) {
                 float4* sp = reinterpret_cast<float4*>(scr_lane + (size_t)n * scr_item);
 #pragma unroll
-                for (int qd = 0; qd < 4; ++qd) sp[qd] = make_float4(a[4 * qd], a[4 * qd + 1], a[4 * qd + 2], a[4 * qd + 3]);
+                for (int qd = 0; qd < 4; ++qd)
+                  if (!sk_st) sp[qd] = make_float4(a[4 * qd], a[4 * qd + 1], a[4 * qd + 2], a[4 * qd + 3]);
               } else {
 #pragma unroll
                 for (int e = 0; e < 16; ++e) r[e] = __float_as_uint(add_acp ? a[e] + acp[e] : a[e]);
-                tc_st16(taddr, r);
+                tst16(taddr, r);
               }
-              store_operand16<BF16>(buf, g.RB, ch, row + g.G, v);
+              if (!sk_sm) store_operand16<BF16>(buf, g.RB, ch, row + g.G, v);
             }
             if (p.nconv == 1) tc_wait_st();
             publish_operand(slot);
@@ -422,7 +436,7 @@ __global__ void __launch_bounds__(RB_THREADS, 1) rb_kernel(RbParams p, RbGeom g)
               const bool ok = row >= g.Hlo && row < g.Hlo + g.V && t < p.T;
               const int64_t off0 = bCT + (int64_t)(ch * 16) * p.T + t;
               uint32_t r[16];
-              tc_ld16(tslot + (uint32_t)(i * g.Np + ch * 16), r);
+              tld16(tslot + (uint32_t)(i * g.Np + ch * 16), r);
               float bv[16];
               load_bias16(bv, bias_c + ch * 16);
               tc_wait_ld();
@@ -431,9 +445,9 @@ __global__ void __launch_bounds__(RB_THREADS, 1) rb_kernel(RbParams p, RbGeom g)
               for (int e = 0; e < 16; ++e) {
                 const float a = (__uint_as_float(r[e]) + bv[e]) * g.out_scale;
                 v[e] = a;
-                if (ok && ch * 16 + e < p.C) p.y[off0 + (int64_t)e * p.T] = a;
+                if (ok && ch * 16 + e < p.C && !sk_st) p.y[off0 + (int64_t)e * p.T] = a;
               }
-              if (p.yimg != nullptr && ok) {
+              if (p.yimg != nullptr && ok && !sk_st) {
                 uint16_t* yi = p.yimg + (((size_t)b * c8n + (size_t)ch * 2) * p.T + (size_t)t) * 8;
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
@@ -465,8 +479,8 @@ __global__ void __launch_bounds__(RB_THREADS, 1) rb_kernel(RbParams p, RbGeom g)
   } else if (warp == 0) {
     // ===================== weight producer =====================
     if (lane == 0) {
-      const int groups = g.nkc / g.kcs;          // weight stages per tap
-      const int per_conv = p.k * groups;
+      const int nchunks = p.k * g.nkc;                        // chunks per conv, image order
+      const int per_conv = (nchunks + g.cps - 1) / g.cps;     // stages per conv (the last one may be short)
       int it = 0;
       long long wait_e = 0;
       for (int q = blockIdx.x; q < npairs_total; q += gridDim.x) {
@@ -480,9 +494,9 @@ __global__ void __launch_bounds__(RB_THREADS, 1) rb_kernel(RbParams p, RbGeom g)
               const long long t0 = g.dbg ? clock64() : 0;
               mbar_wait(bar_empty(s), ph ^ 1u, 20);
               if (g.dbg) wait_e += clock64() - t0;
-              mbar_arrive_expect_tx(bar_full(s), g.stage_bytes);
-              bulk_g2s(s0 + g.off_w + (uint32_t)s * g.stage_bytes, wsrc + (size_t)l * g.stage_bytes, g.stage_bytes,
-                       bar_full(s));
+              const uint32_t bytes = (uint32_t)min(g.cps, nchunks - l * g.cps) * g.chunk_bytes;
+              mbar_arrive_expect_tx(bar_full(s), bytes);
+              bulk_g2s(s0 + g.off_w + (uint32_t)s * g.stage_bytes, wsrc + (size_t)l * g.stage_bytes, bytes, bar_full(s));
             }
           }
         }
@@ -497,14 +511,14 @@ __global__ void __launch_bounds__(RB_THREADS, 1) rb_kernel(RbParams p, RbGeom g)
     const uint32_t kstepA = 2u * (uint32_t)g.RB;
     const uint32_t kstepB = 2u * (uint32_t)g.Np;
     const uint32_t w16 = (s0 + g.off_w) >> 4, stage16 = g.stage_bytes >> 4, chunk16 = g.chunk_bytes >> 4;
-    const int groups = g.nkc / g.kcs;
+    const int nchunks = p.k * g.nkc;
     const int c = (p.k - 1) >> 1;
     uint32_t ph_opnd = 0u;
     int it = 0;
     uint32_t next_ready = 0u;     // the weight stage `it` was already seen full by the previous stage's poll
     int total_stages = 0;         // weight stages this CTA will consume (no poll beyond the last one)
     for (int q = blockIdx.x; q < npairs_total; q += gridDim.x) total_stages += (2 * q + 1 < g.ntiles) ? 2 : 1;
-    total_stages *= g.nsteps * p.k * (g.nkc / g.kcs);
+    total_stages *= g.nsteps * ((p.k * g.nkc + g.cps - 1) / g.cps);
     long long wait_o = 0, wait_w = 0;
     for (int q = blockIdx.x; q < npairs_total; q += gridDim.x) {
       const int nact = (2 * q + 1 < g.ntiles) ? 2 : 1;
@@ -525,35 +539,35 @@ __global__ void __launch_bounds__(RB_THREADS, 1) rb_kernel(RbParams p, RbGeom g)
           const uint32_t a16 = (s0 + (uint32_t)slot * g.off_buf1) >> 4;
           const uint32_t td = tmem + (uint32_t)(slot * RB_SLOT_COLS);
           auto run_conv = [&](auto issue_first, auto issue_rest) {
-            for (int j = 0; j < p.k; ++j) {
-              const uint32_t arow = (uint32_t)(g.G + (j - c) * dil) * 2u;
-              for (int kg = 0; kg < groups; ++kg, ++it) {
-                const int s = it % g.nstages;
-                if (!next_ready) {
-                  const uint32_t ph = (uint32_t)(it / g.nstages) & 1u;
-                  const long long t0 = g.dbg ? clock64() : 0;
-                  mbar_wait(bar_full(s), ph, 31);
-                  if (g.dbg) wait_w += clock64() - t0;
-                }
-                next_ready = 0u;
-                tc_fence_after();
-                // the next stage's barrier is tested between the last MMAs of this stage (issue_stage's poll point)
-                const int sn = (it + 1) % g.nstages;
-                const uint32_t phn = (uint32_t)((it + 1) / g.nstages) & 1u;
-                const bool can_poll = it + 1 < total_stages;
-                auto poll = [&] { if (can_poll) next_ready = mbar_try_wait(bar_full(sn), phn); };
-                for (int kk = 0; kk < g.kcs; ++kk) {
-                  const int kc = kg * g.kcs + kk;
-                  const bool two = nks_total - kc * 2 >= 2;
-                  const uint32_t alo = desc_lo_sw32(a16 + (uint32_t)(kc * 2) * kstepA + arow);
-                  const uint32_t blo = desc_lo_sw32(w16 + (uint32_t)s * stage16 + (uint32_t)kk * chunk16);
-                  const bool last = kk == g.kcs - 1;
-                  if (zero_init && (j | kc) == 0) issue_first(alo, blo, two, poll, last);
-                  else issue_rest(alo, blo, two, poll, last);
-                }
-                if (elected) tc_commit(bar_empty(s));
-                __syncwarp();
+            int j = 0, kc = 0;                       // chunk cursor: tap, 32-channel K chunk
+            uint32_t arow = (uint32_t)(g.G - c * dil) * 2u;
+            for (int q0 = 0; q0 < nchunks; q0 += g.cps, ++it) {
+              const int s = it % g.nstages;
+              if (!next_ready) {
+                const uint32_t ph = (uint32_t)(it / g.nstages) & 1u;
+                const long long t0 = g.dbg ? clock64() : 0;
+                mbar_wait(bar_full(s), ph, 31);
+                if (g.dbg) wait_w += clock64() - t0;
               }
+              next_ready = 0u;
+              tc_fence_after();
+              const int sn = (it + 1) % g.nstages;
+              const uint32_t phn = (uint32_t)((it + 1) / g.nstages) & 1u;
+              const bool can_poll = g.poll && it + 1 < total_stages;
+              auto poll = [&] { if (can_poll) next_ready = mbar_try_wait(bar_full(sn), phn); };
+              const int nq = min(g.cps, nchunks - q0);
+              uint32_t blo = desc_lo_sw32(w16 + (uint32_t)s * stage16);
+              for (int kk = 0; kk < nq; ++kk) {
+                const bool two = nks_total - kc * 2 >= 2;
+                const uint32_t alo = desc_lo_sw32(a16 + (uint32_t)(kc * 2) * kstepA + arow);
+                const bool last = kk == nq - 1;
+                if (zero_init && (q0 | kk) == 0) issue_first(alo, blo, two, poll, last);
+                else issue_rest(alo, blo, two, poll, last);
+                blo += chunk16;
+                if (++kc == g.nkc) { kc = 0; ++j; arow += (uint32_t)dil * 2u; }
+              }
+              if (elected) tc_commit(bar_empty(s));
+              __syncwarp();
             }
           };
           auto generic = [&](uint32_t alo, uint32_t blo, bool two, uint32_t acc0, auto& poll, bool last) {
@@ -571,11 +585,11 @@ __global__ void __launch_bounds__(RB_THREADS, 1) rb_kernel(RbParams p, RbGeom g)
           };
 #define AB_RUN(MM, KO)                                                                                            \
   run_conv([&](uint32_t alo, uint32_t blo, bool two, auto& poll, bool last) {                                     \
-             if (last) issue_stage<MM, KO, 1>(elected, td, (uint32_t)g.Np, hi, alo, blo, kstepA, kstepB, g.idesc, two, poll); \
+             if (last && g.poll) issue_stage<MM, KO, 1>(elected, td, (uint32_t)g.Np, hi, alo, blo, kstepA, kstepB, g.idesc, two, poll); \
              else issue_stage<MM, KO, 1>(elected, td, (uint32_t)g.Np, hi, alo, blo, kstepA, kstepB, g.idesc, two); \
            },                                                                                                     \
            [&](uint32_t alo, uint32_t blo, bool two, auto& poll, bool last) {                                     \
-             if (last) issue_stage<MM, KO, 0>(elected, td, (uint32_t)g.Np, hi, alo, blo, kstepA, kstepB, g.idesc, two, poll); \
+             if (last && g.poll) issue_stage<MM, KO, 0>(elected, td, (uint32_t)g.Np, hi, alo, blo, kstepA, kstepB, g.idesc, two, poll); \
              else issue_stage<MM, KO, 0>(elected, td, (uint32_t)g.Np, hi, alo, blo, kstepA, kstepB, g.idesc, two); \
            })
           if (g.m == 2 && !g.korder) AB_RUN(2, false);
@@ -642,16 +656,22 @@ int rb_make_geom(const RbParams& p, RbGeom& g) {
   g.ntiles = (int)nt;
   g.nsteps = p.npairs * p.nconv;
   g.chunk_bytes = (uint32_t)g.Np * 64u;
-  // weight stage = kcs 32-channel chunks of one tap: >= 8 MMAs per stage keeps the issuer's per-stage overhead small
-  static const int kcs_pref = [] { const char* e = getenv("AB_RB_KCS"); return e ? atoi(e) : 0; }();
-  g.kcs = 1;
-  if ((g.nkc % 2) == 0 && g.m * 2 < 8) g.kcs = 2;
-  if (kcs_pref > 0 && (g.nkc % kcs_pref) == 0) g.kcs = kcs_pref;
-  g.stage_bytes = g.chunk_bytes * (uint32_t)g.kcs;
+  // weight stage = cps consecutive chunks of the image (a chunk = one tap x 32 channels): the issuer pays one
+  // barrier test per stage (~85 cycles even when the stage is already there), so a stage carries up to 32 MMAs
+  static const int cps_pref = [] { const char* e = getenv("AB_RB_CPS"); return e ? atoi(e) : 0; }();
+  const int mma_per_chunk = g.m * 2;
+  g.cps = std::max(1, (32 + mma_per_chunk - 1) / mma_per_chunk);
+  if (cps_pref > 0) g.cps = cps_pref;
+  g.cps = std::min(g.cps, p.k * g.nkc);
   const uint32_t buf_bytes = (uint32_t)g.RB * (uint32_t)g.Np * 2u;
   g.off_buf1 = (buf_bytes + 1023u) & ~1023u;
   g.off_w = (g.off_buf1 + buf_bytes + 1023u) & ~1023u;
   const uint32_t tail = (uint32_t)g.nsteps * g.Np * 4u + 8u * (2 * RB_MAX_STAGES + 4) + 32u;
+  g.stage_bytes = g.chunk_bytes * (uint32_t)g.cps;
+  while (g.cps > 1 && g.off_w + 3u * g.stage_bytes + tail > RB_SMEM_LIMIT) {   // keep at least three stages in the ring
+    --g.cps;
+    g.stage_bytes = g.chunk_bytes * (uint32_t)g.cps;
+  }
   if (g.off_w + 2u * g.stage_bytes + tail > RB_SMEM_LIMIT) return fail(AB_ERR_UNSUPPORTED, "rb: C=%d k=%d does not fit shared memory", p.C, p.k);
   g.nstages = std::min<int>((RB_SMEM_LIMIT - g.off_w - tail) / g.stage_bytes, RB_MAX_STAGES);
   g.off_bias = g.off_w + (uint32_t)g.nstages * g.stage_bytes;
@@ -662,6 +682,10 @@ int rb_make_geom(const RbParams& p, RbGeom& g) {
   g.korder = g.m >= 4 ? 1 : 0;
   g.out_scale = 1.0f / p.out_div;
   g.dbg = nullptr;
+  static const int poll = [] { const char* e = getenv("AB_RB_POLL"); return e ? atoi(e) : 0; }();
+  static const int skip = [] { const char* e = getenv("AB_RB_DEBUG_SKIP"); return e ? atoi(e) : 0; }();
+  g.poll = poll;
+  g.skip = skip;
   return AB_OK;
 }
 
@@ -733,7 +757,7 @@ int launch_rb(const RbParams& p, cudaStream_t s) {
             "total %.0f cycles, %.1f tiles | MMA ideal %.0f law %.0f | issuer waits: operand %.0f weights %.0f | "
             "epilogue waits acc %.0f | producer waits %.0f\n",
             p.C, p.k, p.dil[0], p.npairs > 1 ? p.dil[1] : 0, p.npairs > 2 ? p.dil[2] : 0, p.npairs, p.nconv, g.m, g.R, g.V,
-            g.ntiles, grid, g.nstages, g.stage_bytes, a[0], a[5], ideal, law, a[1], a[2], a[3], a[4]);
+            g.ntiles, grid, g.nstages, g.stage_bytes, g.cps, a[0], a[5], ideal, law, a[1], a[2], a[3], a[4]);
   }
   return AB_OK;
 }
