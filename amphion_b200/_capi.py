@@ -88,6 +88,7 @@ SIGNATURES = {
     "ab_mel_num_frames": (C.c_int64, [_P, C.c_int64]),
     "ab_mel_workspace_bytes": (C.c_size_t, [_P, C.c_int64, C.c_int64]),
     "ab_mel_forward": (C.c_int, [_P, _P, C.c_int64, C.c_int64, _P, _P, _P, _P, _P, _P, C.c_size_t, _P]),
+    "ab_mel_forward_fused": (C.c_int, [_P, _P, C.c_int64, C.c_int64, _P, _P, _P, _P, _P, C.c_size_t, _P]),
     "ab_pcm16_workspace_bytes": (C.c_size_t, [C.c_int64]),
     "ab_pcm16_forward": (C.c_int, [_P, C.c_int64, C.c_int64, C.c_int64, _P, C.c_int32, C.c_float, C.c_int64, _P, C.c_int64,
                                    _P, C.c_size_t, _P]),

@@ -61,8 +61,12 @@ def _warn_range(y):
 
 
 def native_stft_mel(y, n_fft, hop, win, window, basis, pad, eps, want_mag=False, want_mel=True,
-                    want_energy=False, clamp=1e-5):
-    """y [B, T] CUDA fp32 -> (magnitude [B,bins,F] | None, mel [B,n_mel,F] | None, energy [B,F] | None)."""
+                    want_energy=False, clamp=1e-5, fused=False):
+    """y [B, T] CUDA fp32 -> (magnitude [B,bins,F] | None, mel [B,n_mel,F] | None, energy [B,F] | None).
+
+    ``fused=True`` asks for the one-kernel front end (own FFT, n_fft = 1024, no magnitude output): the wav is read
+    once and only mel / energy are written.  The default is the cuFFT pipeline, whose spectrum is bit-identical to
+    ``torch.stft`` on the same device."""
     _capi.require_cuda(y, "mel front end")
     if y.dim() != 2:
         raise ValueError("expected audio of shape [B, T]")
@@ -82,7 +86,8 @@ def native_stft_mel(y, n_fft, hop, win, window, basis, pad, eps, want_mag=False,
     if F <= 0:
         raise ValueError(f"audio of {T} samples is too short for n_fft={n_fft}, pad={pad}")
     with torch.cuda.device(y.device):
-        need = lib.ab_mel_workspace_bytes(h, B, T)
+        fused = bool(fused) and n_fft == 1024 and not want_mag and 0 < n_mel <= 128
+        need = 4096 if fused else lib.ab_mel_workspace_bytes(h, B, T)
         ws = _workspaces.get(str(y.device))
         if ws is None or ws.numel() < need + 256:
             ws = torch.empty(need + 256, dtype=torch.uint8, device=y.device)
@@ -94,9 +99,14 @@ def native_stft_mel(y, n_fft, hop, win, window, basis, pad, eps, want_mag=False,
         en = torch.empty(B, F, device=y.device) if want_energy else None
         window = window.to(device=y.device, dtype=torch.float32).contiguous()
         bt = basis.to(device=y.device, dtype=torch.float32).contiguous() if n_mel else None
-        _capi.check(lib.ab_mel_forward(h, _capi.ptr(y), B, T, _capi.ptr(window), _capi.ptr(bt), _capi.ptr(mag),
-                                       _capi.ptr(mel), _capi.ptr(en), C.c_void_p(wbase), need, _capi.stream_ptr()),
-                    "ab_mel_forward")
+        if fused:
+            _capi.check(lib.ab_mel_forward_fused(h, _capi.ptr(y), B, T, _capi.ptr(window), _capi.ptr(bt), _capi.ptr(mel),
+                                                 _capi.ptr(en), C.c_void_p(wbase), need, _capi.stream_ptr()),
+                        "ab_mel_forward_fused")
+        else:
+            _capi.check(lib.ab_mel_forward(h, _capi.ptr(y), B, T, _capi.ptr(window), _capi.ptr(bt), _capi.ptr(mag),
+                                           _capi.ptr(mel), _capi.ptr(en), C.c_void_p(wbase), need, _capi.stream_ptr()),
+                        "ab_mel_forward")
     return mag, mel, en
 
 

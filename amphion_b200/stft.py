@@ -4,6 +4,8 @@ the STFT as a dense convolution with a windowed DFT matrix on the GPU
 (:167-172); here the same transform is the cuFFT-driven native pipeline."""
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import mel as _mel
@@ -65,6 +67,9 @@ class TacotronSTFT(torch.nn.Module):
         assert torch.max(y.data) <= 1
         yc = y if y.is_cuda else y.cuda()   # the reference hard-codes .cuda() (:168)
         s = self.stft_fn
+        # one fused kernel (own FFT) when n_fft = 1024; AMPHION_B200_MEL=cufft keeps the cuFFT pipeline.  The
+        # reference computes this spectrum with a conv-DFT (:152-181), so there is no FFT backend to be identical to.
+        fused = os.environ.get("AMPHION_B200_MEL", "fused") != "cufft"
         _, mel, energy = _mel.native_stft_mel(yc, s.filter_length, s.hop_length, s.win_length, s.fft_window,
-                                              self.mel_basis, s.filter_length // 2, 0.0, want_energy=True)
+                                              self.mel_basis, s.filter_length // 2, 0.0, want_energy=True, fused=fused)
         return mel.cpu(), energy.cpu()

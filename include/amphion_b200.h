@@ -224,6 +224,14 @@ int ab_mel_forward(ab_mel* m, const float* dev_wav, int64_t batch, int64_t sampl
                    const float* dev_window, const float* dev_mel_basis, float* dev_magnitude,
                    float* dev_mel, float* dev_energy, void* dev_workspace, size_t workspace_bytes,
                    void* stream);
+/* Same mel / energy outputs from ONE kernel for n_fft = 1024 (the 22.05 / 24 kHz configs): frame, window, an in-kernel
+ * 512-point complex FFT of the even/odd-packed frame, real-FFT post-processing, |.|, mel filterbank, log — the wav is
+ * the only HBM read and mel / energy the only writes (utils/stft.py:259-278, utils/mel.py:145-169).  fp32 with an own
+ * FFT: agrees with ab_mel_forward to ~1e-6 in the log-mel, NOT bit for bit (use ab_mel_forward where the spectrum
+ * must equal torch.stft's).  AB_ERR_UNSUPPORTED for other n_fft / n_mel > 128.  Workspace: >= 1 KB, 256-byte aligned. */
+int ab_mel_forward_fused(ab_mel* m, const float* dev_wav, int64_t batch, int64_t samples,
+                         const float* dev_window, const float* dev_mel_basis, float* dev_mel, float* dev_energy,
+                         void* dev_workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------
  * Waveform -> 16-bit PCM: the arithmetic of save_audio (utils/io.py:49-76) on the device, applied to a

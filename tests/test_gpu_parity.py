@@ -732,3 +732,29 @@ def test_config5_shard_full_size_is_consistent_with_checked_sizes():
               upsample_initial_channel=1536, resblock_kernel_sizes=[3, 7, 11],
               resblock_dilation_sizes=[[1, 3, 5]] * 3, activation="snakebeta", snake_logscale=True)
     _full_size_consistency("bigvgan", hp, 100, 32, 2048, seed=505, win_lo=1000)
+
+
+def test_fused_mel_kernel_matches_the_cufft_pipeline_and_the_oracle():
+    """ab_mel_forward_fused (frame -> window -> own 1024-point FFT -> |.| -> mel -> log in one kernel): log-mel
+    within 1e-5 of the cuFFT pipeline (whose spectrum is bit-identical to torch.stft), energy within 2e-6 relative,
+    on ragged lengths (partial frame groups, reflect padding at both ends), the three parameterisations of
+    SURVEY Q8 (eps 0 / 1e-9 / 1e-6; pad n_fft/2 and (n_fft-hop)/2; win < n_fft) and 24 kHz / 100 mels."""
+    from amphion_b200 import mel
+    cases = [  # B, T, hop, win, n_mel, sr, fmax, pad, eps
+        (3, 22050, 256, 1024, 80, 22050, 8000, 512, 0.0),        # TacotronSTFT (config 4 parameters)
+        (2, 9000, 256, 1024, 80, 22050, 8000, 384, 1e-9),        # extract_mel_features
+        (1, 4097, 240, 960, 100, 24000, 12000, 392, 1e-6),       # mel_spectrogram_torch, BigVGAN 24 kHz, win < n_fft
+        (5, 1300, 256, 1024, 128, 22050, None, 512, 0.0),        # fewer frames than a group of 8, 128 mels
+    ]
+    for B, T, hop, win, n_mel, sr, fmax, pad, eps in cases:
+        g = torch.Generator().manual_seed(T)
+        y = ((torch.rand(B, T, generator=g) * 2 - 1) * 0.9).to(DEV)
+        window = torch.hann_window(win).to(DEV)
+        basis = mel.librosa_mel_fn(sr, 1024, n_mel, 0, fmax).to(DEV)
+        _, m0, e0 = mel.native_stft_mel(y, 1024, hop, win, window, basis, pad, eps, want_energy=True)
+        _, m1, e1 = mel.native_stft_mel(y, 1024, hop, win, window, basis, pad, eps, want_energy=True, fused=True)
+        assert m1.shape == m0.shape and e1.shape == e0.shape
+        assert (m1 - m0).abs().max() <= 1e-5, ((B, T), float((m1 - m0).abs().max()))
+        assert ((e1 - e0).abs() / e0.abs().clamp_min(1e-3)).max() <= 2e-6
+    want, _ = om.tacotron_mel(y[:1, :1300].cpu().numpy()[:, :1300], basis.cpu().numpy(), 1024, 256, 1024)
+    np.testing.assert_allclose(m1[:1].cpu().numpy(), want, atol=3e-4)      # CPU oracle (conv-DFT restatement)
