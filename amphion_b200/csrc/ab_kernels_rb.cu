@@ -167,6 +167,7 @@ __global__ void __launch_bounds__(RB_THREADS, 1) rb_kernel(RbParams p, RbGeom g)
     const int nch = g.Np >> 4;
     const int c8n = g.Np >> 3;
     const int nitems = g.m * nch;
+    const int grp_i0 = grp / nch, grp_ch0 = grp - grp_i0 * nch;   // the only division of the item cursor
     const int last_pair = p.npairs - 1;
     long long wait_acc = 0;
     int ntile_done = 0;
@@ -334,38 +335,53 @@ __global__ void __launch_bounds__(RB_THREADS, 1) rb_kernel(RbParams p, RbGeom g)
           tc_fence_after();
           // thread-private scratch of this slot: 16 contiguous floats per (item, lane) -> 4 x 16-byte accesses
           float* scr_lane = scr ? scr + ((size_t)q4 * 32 + lane) * 16 : nullptr;
-          const size_t scr_item = (size_t)4 * 32 * 16;
+          constexpr size_t scr_item = (size_t)4 * 32 * 16;
+          // item cursor without divisions: item n = (M tile i, 16-channel chunk ch), n = grp, grp + G, ...
+          struct Cur { int n, i, ch; };
+          auto cur_first = [&]() { Cur c; c.n = grp; c.i = grp_i0; c.ch = grp_ch0; return c; };
+          auto cur_next = [&](Cur& c) {
+            c.n += RB_EPI_GROUPS;
+            c.ch += RB_EPI_GROUPS;
+            while (c.ch >= nch) { c.ch -= nch; ++c.i; }
+          };
+          const int rowl = q4 * 32 + lane;            // row of this lane inside an M tile
+          const int tl0 = tbase + rowl;               // its time
+          // operand-buffer byte offset of (row, 16-channel chunk): unit (2 ch) at off, unit (2 ch + 1) at off ^ 16
+          const uint32_t chunk_stride = (uint32_t)g.RB * 32u;
+          auto opnd_off = [&](int i, int ch) {
+            const uint32_t brow = (uint32_t)(i * 128 + rowl + g.G);
+            return (uint32_t)ch * chunk_stride + brow * 32u + (((brow >> 2) & 1u) << 4);
+          };
+          auto store_opnd = [&](uint32_t off, const float (&v)[16]) {
+            if (sk_sm) return;
+            uint4 q0, q1;
+            q0.x = pack2t<BF16>(v[0], v[1]); q0.y = pack2t<BF16>(v[2], v[3]);
+            q0.z = pack2t<BF16>(v[4], v[5]); q0.w = pack2t<BF16>(v[6], v[7]);
+            q1.x = pack2t<BF16>(v[8], v[9]); q1.y = pack2t<BF16>(v[10], v[11]);
+            q1.z = pack2t<BF16>(v[12], v[13]); q1.w = pack2t<BF16>(v[14], v[15]);
+            *reinterpret_cast<uint4*>(buf + off) = q0;
+            *reinterpret_cast<uint4*>(buf + (off ^ 16u)) = q1;
+          };
+          auto load_scr = [&](float (&res)[16], int n) {
+            const float4* sp = reinterpret_cast<const float4*>(scr_lane + (size_t)n * scr_item);
+#pragma unroll
+            for (int qd = 0; qd < 4; ++qd) {
+              const float4 f = sk_ld ? make_float4(0.f, 0.f, 0.f, 0.f) : sp[qd];
+              res[4 * qd] = f.x; res[4 * qd + 1] = f.y; res[4 * qd + 2] = f.z; res[4 * qd + 3] = f.w;
+            }
+          };
           if (is_e1) {
             // ---- intermediate = lrelu(conv1 + b1) -> operand buffer, zero outside [0, T) (conv2's zero padding);
             //      accumulator <- x_p (+ branch sum before the last conv): conv2 accumulates on the residual.
-            //      The residual of the NEXT item is requested before this item is processed.
             const bool add_acp = pair == last_pair && p.acc_prev != nullptr;
-            auto load_res = [&](float (&res)[16], int n) {
-              if (pair == 0) {
-                const int i = n / nch, ch = n - i * nch;
-                const int t = tbase + i * 128 + q4 * 32 + lane;
-                load_x16(res, p.x + bCT + (int64_t)(ch * 16) * p.T + t, t >= 0 && t < p.T, ch);
-              } else {
-                const float4* sp = reinterpret_cast<const float4*>(scr_lane + (size_t)n * scr_item);
-#pragma unroll
-                for (int qd = 0; qd < 4; ++qd) {
-                  const float4 f = sk_ld ? make_float4(0.f, 0.f, 0.f, 0.f) : sp[qd];
-                  res[4 * qd] = f.x; res[4 * qd + 1] = f.y; res[4 * qd + 2] = f.z; res[4 * qd + 3] = f.w;
-                }
-              }
-            };
-            auto process = [&](int n, float (&res)[16], auto with_acp) {
-              const int i = n / nch, ch = n - i * nch;
-              const int row = i * 128 + q4 * 32 + lane;
-              const int t = tbase + row;
-              const bool inr = t >= 0 && t < p.T;
-              float acp[16];
-              if (with_acp.value) load_acp16(acp, p.acc_prev + bCT + (int64_t)(ch * 16) * p.T + t, inr, ch);
+            // TMEM -> bias, lrelu, mask, pack -> operand buffer; then the accumulator is overwritten with `res`
+            auto e1_item = [&](const Cur& c, const float (&res)[16]) {
+              const bool inr = (unsigned)(tl0 + c.i * 128) < (unsigned)p.T;
               uint32_t r[16];
-              const uint32_t taddr = tslot + (uint32_t)(i * g.Np + ch * 16);
+              const uint32_t taddr = tslot + (uint32_t)(c.i * g.Np + c.ch * 16);
               tld16(taddr, r);
               float bv[16];
-              load_bias16(bv, bias_c + ch * 16);
+              load_bias16(bv, bias_c + c.ch * 16);
               tc_wait_ld();
               float v[16];
 #pragma unroll
@@ -373,30 +389,42 @@ __global__ void __launch_bounds__(RB_THREADS, 1) rb_kernel(RbParams p, RbGeom g)
                 const float a = __uint_as_float(r[e]) + bv[e];
                 v[e] = inr ? lrelu(a, p.slope) : 0.f;
               }
-              if (!sk_sm) store_operand16<BF16>(buf, g.RB, ch, row + g.G, v);
+              store_opnd(opnd_off(c.i, c.ch), v);
 #pragma unroll
-              for (int e = 0; e < 16; ++e) r[e] = __float_as_uint(with_acp.value ? res[e] + acp[e] : res[e]);
+              for (int e = 0; e < 16; ++e) r[e] = __float_as_uint(res[e]);
               tst16(taddr, r);
             };
-            if (add_acp) {   // last pair of a later branch: x_p and the branch sum, no look-ahead (register budget)
-              for (int n = grp; n < nitems; n += RB_EPI_GROUPS) {
-                float res[16];
-                load_res(res, n);
-                process(n, res, std::true_type{});
+            if (pair > 0 && !add_acp) {
+              // residual from the scratch: the next item's 64 bytes are requested before this item is processed
+              float res0[16], res1[16];
+              Cur c0 = cur_first();
+              if (c0.n < nitems) load_scr(res0, c0.n);
+              while (c0.n < nitems) {
+                Cur c1 = c0;
+                cur_next(c1);
+                if (c1.n < nitems) load_scr(res1, c1.n);
+                e1_item(c0, res0);
+                if (c1.n >= nitems) break;
+                c0 = c1;
+                cur_next(c0);
+                if (c0.n < nitems) load_scr(res0, c0.n);
+                e1_item(c1, res1);
               }
             } else {
-              float res0[16], res1[16];
-              int n = grp;
-              if (n < nitems) load_res(res0, n);
-              while (n < nitems) {
-                const int n1 = n + RB_EPI_GROUPS, n2 = n + 2 * RB_EPI_GROUPS;
-                if (n1 < nitems) load_res(res1, n1);
-                process(n, res0, std::false_type{});
-                if (n1 < nitems) {
-                  if (n2 < nitems) load_res(res0, n2);
-                  process(n1, res1, std::false_type{});
+              for (Cur c = cur_first(); c.n < nitems; cur_next(c)) {
+                const int t = tl0 + c.i * 128;
+                const bool inr = (unsigned)t < (unsigned)p.T;
+                const int64_t off0 = bCT + (int64_t)(c.ch * 16) * p.T + t;
+                float res[16];
+                if (pair == 0) load_x16(res, p.x + off0, inr, c.ch);
+                else load_scr(res, c.n);
+                if (add_acp) {
+                  float acp[16];
+                  load_acp16(acp, p.acc_prev + off0, inr, c.ch);
+#pragma unroll
+                  for (int e = 0; e < 16; ++e) res[e] += acp[e];
                 }
-                n = n2;
+                e1_item(c, res);
               }
             }
             tc_wait_st();
@@ -406,18 +434,16 @@ __global__ void __launch_bounds__(RB_THREADS, 1) rb_kernel(RbParams p, RbGeom g)
             //      pair's accumulator init; nconv == 1: written straight back as the next conv's start value
             //      (+ the branch sum before the last conv).  lrelu(x_{p+1}) -> operand buffer.
             const bool add_acp = p.nconv == 1 && pair + 1 == last_pair && p.acc_prev != nullptr;
-            for (int n = grp; n < nitems; n += RB_EPI_GROUPS) {
-              const int i = n / nch, ch = n - i * nch;
-              const int row = i * 128 + q4 * 32 + lane;
-              const int t = tbase + row;
-              const bool inr = t >= 0 && t < p.T;
+            for (Cur c = cur_first(); c.n < nitems; cur_next(c)) {
+              const int t = tl0 + c.i * 128;
+              const bool inr = (unsigned)t < (unsigned)p.T;
               float acp[16];
-              if (add_acp) load_acp16(acp, p.acc_prev + bCT + (int64_t)(ch * 16) * p.T + t, inr, ch);
+              if (add_acp) load_acp16(acp, p.acc_prev + bCT + (int64_t)(c.ch * 16) * p.T + t, inr, c.ch);
               uint32_t r[16];
-              const uint32_t taddr = tslot + (uint32_t)(i * g.Np + ch * 16);
+              const uint32_t taddr = tslot + (uint32_t)(c.i * g.Np + c.ch * 16);
               tld16(taddr, r);
               float bv[16];
-              load_bias16(bv, bias_c + ch * 16);
+              load_bias16(bv, bias_c + c.ch * 16);
               tc_wait_ld();
               float a[16], v[16];
 #pragma unroll
@@ -426,7 +452,7 @@ __global__ void __launch_bounds__(RB_THREADS, 1) rb_kernel(RbParams p, RbGeom g)
                 v[e] = inr ? lrelu(a[e], p.slope) : 0.f;
               }
               if (p.nconv == 2) {
-                float4* sp = reinterpret_cast<float4*>(scr_lane + (size_t)n * scr_item);
+                float4* sp = reinterpret_cast<float4*>(scr_lane + (size_t)c.n * scr_item);
 #pragma unroll
                 for (int qd = 0; qd < 4; ++qd)
                   if (!sk_st) sp[qd] = make_float4(a[4 * qd], a[4 * qd + 1], a[4 * qd + 2], a[4 * qd + 3]);
@@ -435,7 +461,7 @@ __global__ void __launch_bounds__(RB_THREADS, 1) rb_kernel(RbParams p, RbGeom g)
                 for (int e = 0; e < 16; ++e) r[e] = __float_as_uint(add_acp ? a[e] + acp[e] : a[e]);
                 tst16(taddr, r);
               }
-              if (!sk_sm) store_operand16<BF16>(buf, g.RB, ch, row + g.G, v);
+              store_opnd(opnd_off(c.i, c.ch), v);
             }
             if (p.nconv == 1) tc_wait_st();
             publish_operand(slot);
@@ -445,41 +471,40 @@ __global__ void __launch_bounds__(RB_THREADS, 1) rb_kernel(RbParams p, RbGeom g)
             const int next_tile = 2 * qn + slot;
             const bool have_next = qn < npairs_total && next_tile < g.ntiles;
             if (have_next) load_tile(slot, next_tile);
-            for (int n = grp; n < nitems; n += RB_EPI_GROUPS) {
-              const int i = n / nch, ch = n - i * nch;
-              const int row = i * 128 + q4 * 32 + lane;
+            for (Cur c = cur_first(); c.n < nitems; cur_next(c)) {
+              const int row = c.i * 128 + rowl;
               const int t = tbase + row;
               const bool ok = row >= g.Hlo && row < g.Hlo + g.V && t < p.T;
-              const int64_t off0 = bCT + (int64_t)(ch * 16) * p.T + t;
+              const int64_t off0 = bCT + (int64_t)(c.ch * 16) * p.T + t;
               uint32_t r[16];
-              tld16(tslot + (uint32_t)(i * g.Np + ch * 16), r);
+              tld16(tslot + (uint32_t)(c.i * g.Np + c.ch * 16), r);
               float bv[16];
-              load_bias16(bv, bias_c + ch * 16);
+              load_bias16(bv, bias_c + c.ch * 16);
               tc_wait_ld();
               float v[16];
 #pragma unroll
               for (int e = 0; e < 16; ++e) v[e] = (__uint_as_float(r[e]) + bv[e]) * g.out_scale;
               if (ok && !sk_st) {
                 float* q = p.y + off0;
-                if (cfull || ch * 16 + 16 <= p.C) {
+                if (cfull || c.ch * 16 + 16 <= p.C) {
 #pragma unroll
                   for (int e = 0; e < 16; ++e) { *q = v[e]; q += p.T; }
                 } else {
 #pragma unroll
                   for (int e = 0; e < 16; ++e)
-                    if (ch * 16 + e < p.C) q[(int64_t)e * p.T] = v[e];
+                    if (c.ch * 16 + e < p.C) q[(int64_t)e * p.T] = v[e];
                 }
-              }
-              if (p.yimg != nullptr && ok && !sk_st) {
-                uint16_t* yi = p.yimg + (((size_t)b * c8n + (size_t)ch * 2) * p.T + (size_t)t) * 8;
+                if (p.yimg != nullptr) {
+                  uint16_t* yi = p.yimg + (((size_t)b * c8n + (size_t)c.ch * 2) * p.T + (size_t)t) * 8;
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                  uint4 qv;
-                  qv.x = pack2t<BF16>(lrelu(v[8 * h + 0], p.img_slope), lrelu(v[8 * h + 1], p.img_slope));
-                  qv.y = pack2t<BF16>(lrelu(v[8 * h + 2], p.img_slope), lrelu(v[8 * h + 3], p.img_slope));
-                  qv.z = pack2t<BF16>(lrelu(v[8 * h + 4], p.img_slope), lrelu(v[8 * h + 5], p.img_slope));
-                  qv.w = pack2t<BF16>(lrelu(v[8 * h + 6], p.img_slope), lrelu(v[8 * h + 7], p.img_slope));
-                  *reinterpret_cast<uint4*>(yi + (size_t)h * p.T * 8) = qv;
+                  for (int h = 0; h < 2; ++h) {
+                    uint4 qv;
+                    qv.x = pack2t<BF16>(lrelu(v[8 * h + 0], p.img_slope), lrelu(v[8 * h + 1], p.img_slope));
+                    qv.y = pack2t<BF16>(lrelu(v[8 * h + 2], p.img_slope), lrelu(v[8 * h + 3], p.img_slope));
+                    qv.z = pack2t<BF16>(lrelu(v[8 * h + 4], p.img_slope), lrelu(v[8 * h + 5], p.img_slope));
+                    qv.w = pack2t<BF16>(lrelu(v[8 * h + 6], p.img_slope), lrelu(v[8 * h + 7], p.img_slope));
+                    *reinterpret_cast<uint4*>(yi + (size_t)h * p.T * 8) = qv;
+                  }
                 }
               }
             }
@@ -761,7 +786,7 @@ int launch_rb(const RbParams& p, cudaStream_t s) {
     const double ideal = (double)g.m * (g.Np / 2.0) * (g.Np / 16.0) * p.k * g.nsteps * a[5];   // 8192 flop/clk/SM
     const double law = (double)g.m * (64.0 + g.Np / 2.0) * (g.Np / 16.0) * p.k * g.nsteps * a[5];
     fprintf(stderr,
-            "[rb_timing] C=%d k=%d d=%d,%d,%d npairs=%d nconv=%d m=%d R=%d V=%d tiles=%d grid=%d stages=%dx%uB | per CTA: "
+            "[rb_timing] C=%d k=%d d=%d,%d,%d npairs=%d nconv=%d m=%d R=%d V=%d tiles=%d grid=%d stages=%dx%uB (%d chunks) | per CTA: "
             "total %.0f cycles, %.1f tiles | MMA ideal %.0f law %.0f | issuer waits: operand %.0f weights %.0f | "
             "epilogue waits acc %.0f | producer waits %.0f\n",
             p.C, p.k, p.dil[0], p.npairs > 1 ? p.dil[1] : 0, p.npairs > 2 ? p.dil[2] : 0, p.npairs, p.nconv, g.m, g.R, g.V,

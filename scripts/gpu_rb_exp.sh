@@ -12,11 +12,8 @@ run() {  # label, env...
 }
 {
 run base
-run cps2 AB_RB_CPS=2
-run cps4 AB_RB_CPS=4
-run cps8 AB_RB_CPS=8
 run skip_all AB_RB_DEBUG_SKIP=15
 } | tee gpurun_out/rb_exp.txt
-echo "=== tests"; timeout 600 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -p no:cacheprovider -k "fusion or fixture" 2>&1 | tail -3
+echo "=== tests"; timeout 900 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -p no:cacheprovider -k "fusion or fixture or mel" 2>&1 | tail -3
 echo "=== bench per plan"
-for MODE in 0 2; do echo "AB_RB=$MODE"; AB_RB=$MODE timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-also 2>>gpurun_out/bench.err | tee gpurun_out/bench_rb$MODE.json | cut -c1-200; done
+for MODE in 0 1 2 3; do echo "AB_RB=$MODE"; AB_RB=$MODE timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-also 2>>gpurun_out/bench.err | tee gpurun_out/bench_rb$MODE.json | cut -c1-200; done
