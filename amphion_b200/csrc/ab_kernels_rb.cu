@@ -728,19 +728,21 @@ bool rb_supported(int C, int k) { return C > 0 && rb_round_up(C, 16) <= 128 && (
 
 size_t rb_scratch_bytes() { return (size_t)148 * 2 * (size_t)(RB_SLOT_COLS * 128) * sizeof(float); }
 
-// Modelled cycles per output row of a chain (SS-mode operand law): used to choose between one fused
-// launch per block and one launch per pair.  Returns 0 when the geometry is not served.
+// Modelled cycles per output row of a chain, calibrated on B200 (profiles/r2_rb_timing.txt): per tile the tensor
+// pipe needs k * (Np/16) * m MMAs of ~(48 + 0.3 Np) cycles per conv, the epilogue warps ~8 k cycles per phase of a
+// full 32 K-element tile (one pair per launch: ~26.5 k, bound by the HBM round trip of x / y / images), and the two
+// overlap imperfectly: t = max + 0.35 min.  Used to choose between one fused launch per block and one launch per
+// pair.  Returns 0 when the geometry is not served.
 double rb_cost_per_row(int C, int k, const int* dil, int npairs, int nconv) {
   if (!rb_supported(C, k)) return 0.0;
   const int Np = rb_round_up(C, 16), m = std::min(RB_SLOT_COLS / Np, 16), R = 128 * m;
   const int H = rb_halo(k, dil, npairs, nconv) - (k - 1) / 2 * dil[0];
   const int V = (R - rb_round_up(H, 4) - H) / 4 * 4;
   if (V < 32) return 0.0;
-  const double mma_row = (double)k * (Np / 16.0) * (64.0 + Np / 2.0) / 128.0;      // per conv and computed row
-  const double mma = mma_row * nconv * npairs * (double)R / V;
-  const double hbm = Np * 12.0 / 25.0 * (double)R / V;                              // ~25 B/clk/SM of HBM bandwidth
-  const double epi = (nconv * npairs) * 0.9 * Np / 16.0 * (double)R / V;            // ~0.9 cycles per row and 16 channels
-  return std::max(std::max(mma, hbm), epi);
+  const double fill = (double)(m * Np) / RB_SLOT_COLS;                       // tile elements / 32768
+  const double mma = (double)nconv * npairs * k * (Np / 16.0) * m * (48.0 + 0.3 * Np);
+  const double epi = fill * (npairs == 1 ? (nconv == 2 ? 26500.0 : 22000.0) : 8000.0 * (nconv * npairs + 1));
+  return (std::max(mma, epi) + 0.35 * std::min(mma, epi)) / V;
 }
 
 int launch_rb(const RbParams& p, cudaStream_t s) {
