@@ -3,12 +3,12 @@
 from .bigvgan import BigVGAN
 from .hifigan import HiFiGAN, HiFiGAN_vits
 from .nsfhifigan import NSFHiFiGAN
-from .gan_vocoder_inference import synthesis_audios, vocoder_inference
+from .gan_vocoder_inference import synthesis_audios, synthesize_to_files, vocoder_inference
 
 # same shape as the reference's registries: generator name -> class / functions
 _vocoders = {"hifigan": HiFiGAN, "bigvgan": BigVGAN, "nsfhifigan": NSFHiFiGAN}
 _vocoder_forward_funcs = {"hifigan": vocoder_inference, "bigvgan": vocoder_inference, "nsfhifigan": vocoder_inference}
 _vocoder_infer_funcs = {"hifigan": synthesis_audios, "bigvgan": synthesis_audios, "nsfhifigan": synthesis_audios}
 
-__all__ = ["HiFiGAN", "HiFiGAN_vits", "BigVGAN", "NSFHiFiGAN", "vocoder_inference", "synthesis_audios", "_vocoders",
+__all__ = ["HiFiGAN", "HiFiGAN_vits", "BigVGAN", "NSFHiFiGAN", "vocoder_inference", "synthesis_audios", "synthesize_to_files", "_vocoders",
            "_vocoder_forward_funcs", "_vocoder_infer_funcs"]

@@ -758,3 +758,35 @@ def test_fused_mel_kernel_matches_the_cufft_pipeline_and_the_oracle():
         assert ((e1 - e0).abs() / e0.abs().clamp_min(1e-3)).max() <= 2e-6
     want, _ = om.tacotron_mel(y[:1, :1300].cpu().numpy()[:, :1300], basis.cpu().numpy(), 1024, 256, 1024)
     np.testing.assert_allclose(m1[:1].cpu().numpy(), want, atol=3e-4)      # CPU oracle (conv-DFT restatement)
+
+
+def test_bucketed_synthesis_and_generate_to_files(tmp_path):
+    """length bucketing (opt-in) and the fused generate + trim + PCM16 + save loop.  Every
+    utterance's samples away from its last receptive field equal the unbucketed result; an utterance grouped with
+    the same neighbours is bit-identical; the files hold exactly the PCM16 of the returned audio."""
+    import wave
+    from oracle import io as oio
+    from amphion_b200.vocoders import synthesis_audios, synthesize_to_files
+    kind, hp, g0, sd, model = golden_model("hifigan_rb1")
+    model = model.to(DEV)
+    cfg = model.cfg
+    cfg.preprocess.sample_rate = 16000
+    hop = cfg.preprocess.hop_size
+    gen = torch.Generator().manual_seed(9)
+    lens = [31, 9, 40, 12, 33, 10]
+    mels = [torch.randn(g0["mel"].shape[1], n, generator=gen) for n in lens]
+    plain = synthesis_audios(cfg, model, mels, batch_size=2)
+    buck = synthesis_audios(cfg, model, mels, batch_size=2, bucket=True)
+    assert [a.shape[0] for a in buck] == [n * hop for n in lens]                 # input order, trimmed lengths
+    rf = 20 * hop                                                                # > receptive field of the model
+    for a, b, n in zip(plain, buck, lens):
+        keep = max(n * hop - rf, 0)
+        assert torch.equal(a[:keep], b[:keep])
+    paths = [str(tmp_path / f"u{i}.wav") for i in range(len(mels))]
+    synthesize_to_files(cfg, model, mels, paths, batch_size=2, bucket=True, turn_up=True)
+    for p, a in zip(paths, buck):
+        with wave.open(p) as f:
+            assert (f.getnchannels(), f.getsampwidth(), f.getframerate()) == (1, 2, 16000)
+            got = np.frombuffer(f.readframes(f.getnframes()), "<i2")
+        want = oio.pcm16(oio.save_audio_float(a.numpy(), 16000, turn_up=True))[0]
+        assert got.shape == want.shape and np.abs(got.astype(np.int32) - want.astype(np.int32)).max() <= 1
