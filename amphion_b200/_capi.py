@@ -74,6 +74,7 @@ SIGNATURES = {
     "ab_generator_last_launches": (C.c_int, [_P]),
     "ab_generator_set_profiling": (C.c_int, [_P, C.c_int32]),
     "ab_generator_set_option": (C.c_int, [_P, C.c_char_p, C.c_int32]),
+    "ab_generator_output_samples": (C.c_int64, [_P, C.c_int64, C.c_int64]),
     "ab_generator_set_tail_events": (C.c_int, [_P, C.POINTER(C.c_void_p), C.c_int32]),
     "ab_generator_get_profile": (C.c_int, [_P, C.POINTER(ProfileEntry), C.c_int32, C.POINTER(C.c_int32)]),
     "ab_activation1d_forward": (C.c_int, [_P, _P, C.c_int64, C.c_int64, C.c_int64, _P, _P, C.c_int32, _P, _P, _P]),

@@ -98,6 +98,7 @@ struct ab_generator {
   int launches = 0;
   int rb_mode = 2;          // "resblock_fusion" option; AB_RB in the environment sets the initial value
   std::vector<cudaEvent_t> tail_events;   // ab_generator_set_tail_events: consumed by the next forward
+  int64_t source_frames = 0;              // NSF-HiFiGAN: frames of the f0 track of the next forward (0 = covers the mel)
 
   ConvRef conv_pre, conv_post;
   int cond_w = -1, cond_b = -1;   // HiFiGAN_vits global conditioning (hifigan.py:424-425)
@@ -199,16 +200,6 @@ int validate_config(const ab_generator_config& c) {
   if (c.gin_channels < 0 || c.gin_channels > 65536) return fail(AB_ERR_ARG, "config: gin_channels %d out of range", c.gin_channels);
   if ((c.gin_channels > 0 || c.conv_post_no_bias) && c.kind != AB_GEN_HIFIGAN)
     return fail(AB_ERR_ARG, "config: gin_channels / conv_post_no_bias belong to the HiFi-GAN kind (HiFiGAN_vits)");
-  if (c.kind == AB_GEN_NSFHIFIGAN) {
-    // noise_convs[i]: Conv1d(1, C, 2s, stride s, padding s/2) with s = prod(rates[i+1:]) (nsfhifigan.py:223-236);
-    // for odd s > 1 its output is one sample short and the reference truncates the stage (:264-266)
-    for (int i = 0; i + 1 < c.num_upsamples; ++i) {
-      int64_t sf = 1;
-      for (int j = i + 1; j < c.num_upsamples; ++j) sf *= c.upsample_rates[j];
-      if (sf > 1 && (sf & 1))
-        return fail(AB_ERR_UNSUPPORTED, "config: NSF-HiFiGAN stage %d: odd source stride %lld truncates the stage", i, (long long)sf);
-    }
-  }
   return AB_OK;
 }
 
@@ -444,6 +435,19 @@ size_t stage_max_elems(const ab_generator* g, int64_t B, int64_t T) {
 }
 }  // namespace
 
+// NSF-HiFiGAN: length of stage i's output after `length = min(x.shape[-1], x_source.shape[-1])` (nsfhifigan.py:264-268).
+// noise_convs[i] = Conv1d(1, C, 2s, stride s, padding s/2), s = prod(rates[i+1:]) (:223-236; kernel 1 for the last stage),
+// applied to a source of source_frames * prod(rates) samples; Tn = length of the stage's transposed-conv output.
+static int64_t nsf_stage_length(const ab_generator* g, int stage, int64_t Tn, int64_t source_frames) {
+  if (g->cfg.kind != AB_GEN_NSFHIFIGAN || source_frames <= 0) return Tn;
+  int64_t upp = 1, sfac = 1;
+  for (int j = 0; j < g->cfg.num_upsamples; ++j) upp *= g->cfg.upsample_rates[j];
+  for (int j = stage + 1; j < g->cfg.num_upsamples; ++j) sfac *= g->cfg.upsample_rates[j];
+  const int64_t src = source_frames * upp;
+  const int64_t xs = stage + 1 < g->cfg.num_upsamples ? (src + 2 * (sfac / 2) - 2 * sfac) / sfac + 1 : src;
+  return std::max<int64_t>(std::min(Tn, xs), 0);
+}
+
 size_t ab_generator_workspace_bytes(const ab_generator* g, int64_t B, int64_t T) {
   if (!g || B <= 0 || T <= 0) return 0;
   return NBUF * align_up(stage_max_elems(g, B, T) * sizeof(float), 256) +
@@ -468,8 +472,21 @@ int ab_generator_set_tail_events(ab_generator* g, void* const* events, int32_t n
   return AB_OK;
 }
 
+int64_t ab_generator_output_samples(const ab_generator* g, int64_t frames, int64_t source_frames) {
+  if (!g || frames <= 0) return 0;
+  int64_t Tn = frames;
+  for (int i = 0; i < g->cfg.num_upsamples; ++i) Tn = nsf_stage_length(g, i, Tn * g->cfg.upsample_rates[i], source_frames);
+  return Tn;
+}
+
 int ab_generator_set_option(ab_generator* g, const char* key, int32_t value) {
   if (!g || !key) return fail(AB_ERR_ARG, "set_option: null argument");
+  if (strcmp(key, "nsf_source_frames") == 0) {   // one-shot: consumed by the next forward
+    if (value < 0) return fail(AB_ERR_ARG, "set_option: nsf_source_frames must be >= 0");
+    if (value > 0 && g->cfg.kind != AB_GEN_NSFHIFIGAN) return fail(AB_ERR_ARG, "set_option: nsf_source_frames belongs to NSF-HiFiGAN");
+    g->source_frames = value;
+    return AB_OK;
+  }
   if (strcmp(key, "resblock_fusion") == 0) {
     if (value < 0 || value > 3) return fail(AB_ERR_ARG, "set_option: resblock_fusion must be 0..3 (got %d)", value);
     g->rb_mode = value;
@@ -501,6 +518,7 @@ int ab_generator_get_profile(ab_generator* g, ab_profile_entry* out, int32_t max
   *n_out = 5;
   return AB_OK;
 }
+
 
 static int forward_impl(ab_generator* g, const float* dev_mel, int64_t B, int64_t T, const int64_t mel_strides[3],
                         const float* dev_g, int64_t g_batch_stride, float* dev_wav, void* dev_workspace,
@@ -713,6 +731,20 @@ static int forward_impl(ab_generator* g, const float* dev_mel, int64_t B, int64_
     if (rc != AB_OK) return rc;
     Tn *= sg.u;
     const int C = sg.ch;
+    {
+      // NSF-HiFiGAN with a source shorter than this stage (short f0, odd source stride): the reference truncates x
+      // to the source length before the ResBlocks (nsfhifigan.py:264-268).  Compact the rows; the operand image
+      // (laid out for the untruncated length) is dropped for this stage.
+      const int64_t Lt = nsf_stage_length(g, (int)i, Tn, g->source_frames);
+      if (Lt < Tn) {
+        if (Lt <= 0) return fail(AB_ERR_ARG, "forward: the f0 track leaves no samples in stage %d", (int)i);
+        AB_CUDA_TRY(cudaMemcpy2DAsync(TMP, (size_t)Lt * sizeof(float), U, (size_t)Tn * sizeof(float), (size_t)Lt * sizeof(float),
+                                      (size_t)B * C, cudaMemcpyDeviceToDevice, st));
+        std::swap(U, TMP);
+        u_img = nullptr;
+        Tn = (int)Lt;
+      }
+    }
     float* Rout = R[cur_r ^ 1];
     const int64_t sb = (int64_t)C * Tn, sc = Tn;
     const bool use_tc = tc && tc_conv_supported(C, sg.blocks[0].k);
@@ -847,6 +879,7 @@ static int forward_impl(ab_generator* g, const float* dev_mel, int64_t B, int64_
     }
   }
   g->tail_events.clear();
+  g->source_frames = 0;
   if (rc != AB_OK) return rc;
   g->launches = launches;
   return AB_OK;

@@ -174,7 +174,7 @@ class NativeGenerator(nn.Module):
         ``len(tail_events)`` batch chunks and event i is recorded when utterances [B*i/n, B*(i+1)/n) are complete."""
         return self._forward_native(x, out=out, tail_events=tail_events)
 
-    def _forward_native(self, x, g=None, out=None, tail_events=None):
+    def _forward_native(self, x, g=None, out=None, tail_events=None, out_samples=None):
         """``g`` [B, gin_channels] (HiFiGAN_vits conditioning) or None."""
         _capi.require_cuda(x, f"{type(self).__name__}.forward")
         if x.dim() != 3 or x.shape[1] != int(self.cfg.preprocess.n_mel):
@@ -195,12 +195,13 @@ class NativeGenerator(nn.Module):
                 self._workspace = None
                 self._workspace = torch.empty(need + 256, dtype=torch.uint8, device=x.device)
             wbase = (self._workspace.data_ptr() + 255) // 256 * 256
+            n_out = T * hop if out_samples is None else int(out_samples)
             if out is None:
-                wav = torch.empty(B, 1, T * hop, dtype=torch.float32, device=x.device)
+                wav = torch.empty(B, 1, n_out, dtype=torch.float32, device=x.device)
             else:
-                if (tuple(out.shape) != (B, 1, T * hop) or out.dtype != torch.float32 or out.device != x.device
+                if (tuple(out.shape) != (B, 1, n_out) or out.dtype != torch.float32 or out.device != x.device
                         or not out.is_contiguous()):
-                    raise ValueError(f"out must be a contiguous fp32 [{B}, 1, {T * hop}] tensor on {x.device}")
+                    raise ValueError(f"out must be a contiguous fp32 [{B}, 1, {n_out}] tensor on {x.device}")
                 wav = out
             if tail_events:
                 for ev in tail_events:

@@ -21,6 +21,7 @@ import torch
 from torch import nn
 from torch.nn.utils import remove_weight_norm, weight_norm
 
+from .. import _capi
 from .generator import ConvBlock, NativeGenerator, init_weights
 
 
@@ -76,18 +77,24 @@ class NSFHiFiGAN(NativeGenerator):
         self.upp = int(np.prod(rates))
 
     def forward(self, x, f0):
-        """mel [B, n_mel, T], f0 [B, T_f0] -> wav [B, 1, T*hop].  ``f0`` only has to cover the mel
-        (T_f0 >= T): a shorter f0 makes the reference truncate every stage to the source length
-        (:264-268), which this path does not implement."""
+        """mel [B, n_mel, T], f0 [B, T_f0] -> wav [B, 1, n].  The harmonic source only contributes its LENGTH
+        (``x_source = x[:, :, :length]``, :269): when it covers every stage, n = T*hop; when the f0 track is shorter
+        than the mel or a source stride is odd, each stage is truncated to the source length as in the reference
+        (:264-268) and n = ``ab_generator_output_samples(T, T_f0)``."""
         if f0 is None:
             raise TypeError("NSFHiFiGAN.forward() missing 1 required positional argument: 'f0'")
         if f0.dim() != 2 or f0.shape[0] != x.shape[0]:
             raise ValueError(f"expected f0 of shape [B, T_f0] with B={x.shape[0]}, got {tuple(f0.shape)}")
-        if f0.shape[1] < x.shape[2]:
-            raise NotImplementedError(
-                f"amphion_b200: f0 has {f0.shape[1]} frames but the mel has {x.shape[2]}; the reference would "
-                "truncate every stage to the source length (nsfhifigan.py:264-268), which is not on this path")
-        return super().forward(x)
+        T, Tf = int(x.shape[2]), int(f0.shape[1])
+        n = int(_capi.lib.ab_generator_output_samples(self._ensure_handle(), T, Tf))
+        if n == T * self.upp:
+            return super().forward(x)
+        if n <= 0:
+            raise ValueError(f"the f0 track ({Tf} frames) leaves no samples")
+        # the C ABI writes T*hop-sample rows when no truncation happens and n-sample rows otherwise
+        out = torch.empty(x.shape[0], 1, n, dtype=torch.float32, device=x.device)
+        self.set_option("nsf_source_frames", Tf)
+        return self._forward_native(x, out=out, out_samples=n)
 
     def remove_weight_norm(self):
         print("Removing weight norm...")

@@ -149,8 +149,15 @@ int ab_generator_set_profiling(ab_generator* g, int32_t enable);
 /* Execution-plan options (no reference counterpart; tuning / test knobs, results stay within the stated tolerance):
  *   "resblock_fusion": 0 = one launch per (c1, c2) pair on the per-tile kernel, 1 = persistent kernel with one
  *   pair per launch, 2 (default) = persistent kernel, a whole ResBlock per launch when the cost model prefers
- *   it, 3 = always a whole ResBlock per launch.  Returns AB_ERR_ARG for an unknown key / value. */
+ *   it, 3 = always a whole ResBlock per launch.
+ *   "nsf_source_frames" (NSF-HiFiGAN, one-shot, consumed by the next forward): frames of the f0 track when it does
+ *   not cover the mel; every stage is then truncated to the harmonic source's length as the reference does
+ *   (nsfhifigan.py:264-268) and the output holds ab_generator_output_samples() samples per utterance.
+ *   Returns AB_ERR_ARG for an unknown key / value. */
 int ab_generator_set_option(ab_generator* g, const char* key, int32_t value);
+/* samples per utterance of the forward of `frames` mel frames (frames * hop, or less for NSF-HiFiGAN when the f0 track
+ * of `source_frames` frames is shorter than the mel or a source stride is odd; source_frames = 0: covers the mel) */
+int64_t ab_generator_output_samples(const ab_generator* g, int64_t frames, int64_t source_frames);
 /* Final-gather hook for the batch-sharded multi-GPU path (no reference counterpart): the NEXT
  * ab_generator_forward[_cond] runs conv_post (hifigan.py:216-217) in n contiguous batch chunks
  * [B*i/n, B*(i+1)/n) and records events[i] (cudaEvent_t, caller-owned) on `stream` after chunk i, so the caller

@@ -323,10 +323,17 @@ def test_nsfhifigan_matches_reference_fixture():
     model.precision = "fp32"
     longer = model(mel, torch.cat([f0, f0[:, :4]], dim=1))          # f0 longer than the mel: nothing is truncated
     np.testing.assert_allclose(longer.cpu().numpy(), g["wav_long_f0"], atol=2e-5)
-    with pytest.raises(NotImplementedError):                          # shorter: the reference truncates each stage
-        model(mel, f0[:, :11])
     with pytest.raises(ValueError):
         model(mel, f0[:1])
+    # f0 shorter than the mel: the reference truncates every stage to the source length (:264-268)
+    sdn = {k: v for k, v in sd.items()}
+    for prec, tol in (("fp32", 2e-5), ("tc_f16", 5e-4)):
+        model.precision = prec
+        short = model(mel, f0[:, :11])
+        want = og.generator_forward(kind, sdn, hp, g["mel"], f0=g["f0"][:, :11])
+        assert short.shape == want.shape and short.shape[-1] < g["wav"].shape[-1]
+        assert np.abs(short.cpu().numpy() - want).max() <= tol, (prec, np.abs(short.cpu().numpy() - want).max())
+    model.precision = "fp32"
     # f0-aware plumbing (gan_vocoder_inference.py:36, :76-95)
     mels = [torch.from_numpy(g[f"pl_mel{i}"]) for i in range(3)]
     f0s = [torch.from_numpy(g[f"pl_f0{i}"]) for i in range(3)]
@@ -790,3 +797,20 @@ def test_bucketed_synthesis_and_generate_to_files(tmp_path):
             got = np.frombuffer(f.readframes(f.getnframes()), "<i2")
         want = oio.pcm16(oio.save_audio_float(a.numpy(), 16000, turn_up=True))[0]
         assert got.shape == want.shape and np.abs(got.astype(np.int32) - want.astype(np.int32)).max() <= 1
+
+
+def test_nsfhifigan_odd_source_stride_truncates_like_the_reference():
+    """rates [4, 3, 3]: noise_convs with an odd stride give a source one sample short, so the reference cuts the
+    stage (nsfhifigan.py:264-268) and everything after it; CUDA path against the CPU oracle's restatement."""
+    hp = dict(resblock="1", harmonic_num=8, upsample_rates=[4, 3, 3], upsample_kernel_sizes=[8, 5, 5],
+              upsample_initial_channel=128, resblock_kernel_sizes=[3, 7], resblock_dilation_sizes=[[1, 3, 5]] * 2)
+    model = build_model("nsfhifigan", hp, 20, seed=8)
+    gm = torch.Generator().manual_seed(2)
+    mel, f0 = torch.randn(2, 20, 30, generator=gm), torch.rand(2, 30, generator=gm) * 300 + 80
+    want = og.generator_forward("nsfhifigan", sd_numpy(model), hp, mel.numpy(), f0=f0.numpy())
+    model = model.to(DEV)
+    for prec, tol in (("fp32", 5e-5), ("tc_f16", 1e-3)):
+        model.precision = prec
+        got = model(mel.to(DEV), f0.to(DEV)).cpu().numpy()
+        assert got.shape == want.shape and got.shape[-1] < 30 * 36
+        assert np.abs(got - want).max() <= tol, (prec, np.abs(got - want).max())

@@ -85,10 +85,18 @@ def test_nsfhifigan_module_matches_reference_layout():
     # the reference's ResBlock2 cannot be constructed (nsfhifigan.py:111): same TypeError here
     with pytest.raises(TypeError):
         build_model(kind, dict(hp, resblock="2"), n_mel)
-    # odd source stride (rates [..., 3, 3]) truncates the stage in the reference: refused by the C ABI
-    bad = build_model(kind, dict(hp, upsample_rates=[4, 3, 3], upsample_kernel_sizes=[8, 5, 5]), n_mel)
-    with pytest.raises(RuntimeError, match="odd source stride"):
-        bad._ensure_handle()
+    # stage lengths when the harmonic source is shorter than a stage (short f0 / odd source stride):
+    # `length = min(x.shape[-1], x_source.shape[-1])` (nsfhifigan.py:264-268), restated by the C ABI
+    hop = int(np.prod(hp["upsample_rates"]))
+    assert _capi.lib.ab_generator_output_samples(h, 10, 0) == 10 * hop
+    assert _capi.lib.ab_generator_output_samples(h, 10, 12) == 10 * hop     # f0 longer than the mel: nothing cut
+    assert _capi.lib.ab_generator_output_samples(h, 10, 7) == 7 * hop       # every stage cut to the source length
+    odd = build_model(kind, dict(hp, upsample_rates=[4, 3, 3], upsample_kernel_sizes=[8, 5, 5]), n_mel)
+    ho = odd._ensure_handle()
+    T, src = 5, 5 * 36
+    l0 = min(T * 4, (src + 2 * (9 // 2) - 18) // 9 + 1)      # stage 0: s = 9
+    l1 = min(l0 * 3, (src + 2 * (3 // 2) - 6) // 3 + 1)       # stage 1: s = 3
+    assert _capi.lib.ab_generator_output_samples(ho, T, T) == min(l1 * 3, src) < T * 36
     with pytest.raises(RuntimeError, match="CUDA"):      # no CPU fallback
         model(torch.zeros(1, n_mel, 4), torch.zeros(1, 4))
 
@@ -212,8 +220,8 @@ def test_f0_padding_and_argument_checks_run_before_any_device_work():
         model(mel, None)
     with pytest.raises(ValueError):
         model(mel, torch.zeros(3, 6))                       # batch mismatch
-    with pytest.raises(NotImplementedError):
-        model(mel, torch.zeros(2, 4))                       # source shorter than the mel (nsfhifigan.py:264-268)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        model(mel, torch.zeros(2, 4))                       # a shorter source is computed (stage truncation), on CUDA only
     vits = HiFiGAN_vits(**GOLDEN_VITS["b"])                  # gin_channels == 0
     with pytest.raises(AttributeError):
         vits(torch.zeros(1, 12, 4), g=torch.zeros(1, 3, 1))
