@@ -814,3 +814,17 @@ def test_nsfhifigan_odd_source_stride_truncates_like_the_reference():
         got = model(mel.to(DEV), f0.to(DEV)).cpu().numpy()
         assert got.shape == want.shape and got.shape[-1] < 30 * 36
         assert np.abs(got - want).max() <= tol, (prec, np.abs(got - want).max())
+
+
+@pytest.mark.parametrize("n_in,tag", [(256, "JETS: HiFiGAN(hifi_cfg) with n_mel = attention_dim (models/tts/jets/jets.py:454-458)"),
+                                      (192, "VITS-SVC: self.dec = HiFiGAN(temp_cfg) with n_mel = inter_channels (models/svc/vits/vits.py:131-139)")])
+def test_in_model_generators_of_jets_and_vits_svc_are_the_registry_class(n_in, tag):
+    """The end-to-end TTS / SVC models build their waveform decoder from the vocoder registry class with the
+    model's hidden width as `n_mel` — the same native class, fed a [B, hidden, T] latent instead of a mel."""
+    hp = dict(HP_V1, upsample_initial_channel=256)
+    model, z, want = _full_size_case("hifigan", hp, n_in, 2, 33, seed=n_in)
+    for prec, tol in (("fp32", 5e-5), ("tc_f16", 1e-3)):
+        model.precision = prec
+        got = model(z.to(DEV)).cpu().numpy()
+        assert got.shape == (2, 1, 33 * 256)
+        assert np.abs(got - want).max() <= tol, (tag, prec, np.abs(got - want).max())
