@@ -223,7 +223,7 @@ int ab_generator_create(const ab_generator_config* cfg, ab_generator** out) {
   if (rc != AB_OK) return rc;
   ab_generator* g = new ab_generator();
   g->cfg = *cfg;
-  if (const char* e = getenv("AB_RB")) g->rb_mode = std::min(std::max(atoi(e), 0), 3);
+  if (const char* e = getenv("AB_RB")) g->rb_mode = std::min(std::max(atoi(e), 0), 4);
   const bool big = cfg->kind == AB_GEN_BIGVGAN;
   const bool has_beta = cfg->activation == AB_ACT_SNAKEBETA;
   const int c0 = cfg->upsample_initial_channel;
@@ -488,7 +488,7 @@ int ab_generator_set_option(ab_generator* g, const char* key, int32_t value) {
     return AB_OK;
   }
   if (strcmp(key, "resblock_fusion") == 0) {
-    if (value < 0 || value > 3) return fail(AB_ERR_ARG, "set_option: resblock_fusion must be 0..3 (got %d)", value);
+    if (value < 0 || value > 4) return fail(AB_ERR_ARG, "set_option: resblock_fusion must be 0..4 (got %d)", value);
     g->rb_mode = value;
     return AB_OK;
   }
@@ -629,7 +629,7 @@ static int forward_impl(ab_generator* g, const float* dev_mel, int64_t B, int64_
 
   // a chain of `np` (c1[, c2]) pairs of one ResBlock on the persistent fused kernel (ab_kernels_rb.cu)
   auto rb_chain = [&](const BlockRef& blk, int p0, int np, const float* x, const uint16_t* ximg, float* y, int C, int Tn,
-                      const float* acc_prev, float out_div, uint16_t* yimg) -> int {
+                      const float* acc_prev, float out_div, uint16_t* yimg, int split = 0) -> int {
     RbParams rp;
     memset(&rp, 0, sizeof(rp));
     const bool pair = !blk.c2.empty();
@@ -647,6 +647,7 @@ static int forward_impl(ab_generator* g, const float* dev_mel, int64_t B, int64_
     rp.B = (int)B; rp.C = C; rp.T = Tn; rp.k = blk.k;
     rp.slope = 0.1f; rp.img_slope = 0.1f; rp.out_div = out_div; rp.precision = g->precision;
     rp.scratch = rb_scratch;
+    rp.split = split;
     ++launches;
     const double el = (double)B * C * Tn;
     prof_begin(0, 2.0 * el * C * blk.k * rp.nconv * np,
@@ -757,15 +758,25 @@ static int forward_impl(ab_generator* g, const float* dev_mel, int64_t B, int64_
       const int nd = (int)blk.dil.size();
       const bool blk_rb = use_tc && !big && rb_mode > 0 && rb_supported(C, blk.k) && tc_conv_supported(C, blk.k);
       if (blk_rb && rb_mode >= 2 && nd <= AB_RB_MAX_PAIRS) {
-        // whole block in one launch when the halo recompute costs less than the per-pair HBM round trips
+        // whole block in one launch when the halo recompute costs less than the per-pair HBM round trips; with the
+        // residual stream resident in TMEM (split accumulators) when that is cheaper still
         const int ncv = blk.c2.empty() ? 1 : 2;
-        const double fused = rb_cost_per_row(C, blk.k, blk.dil.data(), nd, ncv);
+        const double fused = rb_cost_per_row(C, blk.k, blk.dil.data(), nd, ncv, 0);
+        const double fsplit = rb_cost_per_row(C, blk.k, blk.dil.data(), nd, ncv, 1);
         double split = 0.0;
-        for (int p = 0; p < nd; ++p) split += rb_cost_per_row(C, blk.k, &blk.dil[p], 1, ncv);
-        if (fused > 0.0 && (rb_mode == 3 || fused < split)) {
+        for (int p = 0; p < nd; ++p) split += rb_cost_per_row(C, blk.k, &blk.dil[p], 1, ncv, 0);
+        int plan = 0;   // 0 per pair, 1 fused, 2 fused + split accumulators
+        if (rb_mode == 3) plan = fused > 0.0 ? 1 : 0;
+        else if (rb_mode == 4) plan = fsplit > 0.0 ? 2 : (fused > 0.0 ? 1 : 0);
+        else {
+          double best = split;
+          if (fused > 0.0 && fused < best) { best = fused; plan = 1; }
+          if (fsplit > 0.0 && fsplit < best) { best = fsplit; plan = 2; }
+        }
+        if (plan) {
           const bool stage_img = j == nk - 1 && i + 1 < g->stages.size();
           rc = rb_chain(blk, 0, nd, U, u_img, Rout, C, Tn, j > 0 ? Rout : nullptr, j == nk - 1 ? (float)nk : 1.0f,
-                        stage_img ? R16 : nullptr);
+                        stage_img ? R16 : nullptr, plan == 2);
           if (rc != AB_OK) return rc;
           if (stage_img) stage_img_written = true;
           continue;

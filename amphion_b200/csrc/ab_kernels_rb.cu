@@ -49,6 +49,8 @@ struct RbGeom {
   int tiles, ntiles;            // per sequence, total
   int nsteps;                   // convs per tile
   int cps;                      // weight chunks (tap, 32 channels) per stage, in image order (tap-major)
+  int split;                    // 1: conv1 -> D1 (cols 0..127 of the slot), every conv2 accumulates into D2 (cols 128..255),
+                                //    which starts as x (+ branch sum): the residual stream never leaves TMEM
   int skip;                     // debug timing experiments (AB_RB_DEBUG_SKIP bitmask), results are wrong
   int nstages;
   uint32_t stage_bytes, chunk_bytes;
@@ -133,6 +135,15 @@ __global__ void __launch_bounds__(RB_THREADS, 1) rb_kernel(RbParams p, RbGeom g)
     const int st = i / g.Np, c = i - st * g.Np;
     const float* src = b_s[st];
     bias_s[i] = (src != nullptr && c < p.C) ? __ldg(src + c) : 0.f;
+  }
+  // cumulative biases of the residual-closing convs: x_p = D2 + cum[p] when the stream lives in the accumulator
+  for (int c = threadIdx.x; c < g.Np; c += RB_THREADS) {
+    float acc = 0.f;
+    for (int q = 0; q < p.npairs; ++q) {
+      const float* src = b_s[q * p.nconv + p.nconv - 1];
+      acc += (src != nullptr && c < p.C) ? __ldg(src + c) : 0.f;
+      bias_s[(g.nsteps + q) * g.Np + c] = acc;
+    }
   }
   {
     const int c8n = g.Np >> 3;
@@ -255,7 +266,7 @@ __global__ void __launch_bounds__(RB_THREADS, 1) rb_kernel(RbParams p, RbGeom g)
     };
     auto tst16 = [&](uint32_t taddr, const uint32_t (&r)[16]) { if (!sk_tm) tc_st16(taddr, r); };
     // accumulator init of a slot from x (nconv == 1: the first conv accumulates on the residual)
-    auto init_acc_from_x = [&](int slot, int tile_id) {
+    auto init_acc_from_x = [&](int slot, int tile_id, uint32_t col0, bool add_acp) {
       const int b = tile_id / g.tiles, tl = tile_id - b * g.tiles;
       const int tbase = tl * g.V - g.Hlo;
       const uint32_t tslot = tmem + (uint32_t)(slot * RB_SLOT_COLS) + ((uint32_t)(q4 * 32) << 16);
@@ -268,7 +279,7 @@ __global__ void __launch_bounds__(RB_THREADS, 1) rb_kernel(RbParams p, RbGeom g)
         const int64_t off0 = bCT + (int64_t)(ch * 16) * p.T + t;
         float res[16];
         load_x16(res, p.x + off0, inr, ch);
-        if (last_pair == 0 && p.acc_prev != nullptr) {
+        if (add_acp) {
           float acp[16];
           load_acp16(acp, p.acc_prev + off0, inr, ch);
 #pragma unroll
@@ -277,10 +288,14 @@ __global__ void __launch_bounds__(RB_THREADS, 1) rb_kernel(RbParams p, RbGeom g)
         uint32_t r[16];
 #pragma unroll
         for (int e = 0; e < 16; ++e) r[e] = __float_as_uint(res[e]);
-        tst16(tslot + (uint32_t)(i * g.Np + ch * 16), r);
+        tst16(tslot + col0 + (uint32_t)(i * g.Np + ch * 16), r);
       }
       tc_wait_st();
     };
+    // which tiles get their accumulator pre-loaded at tile-load time: single-conv residual steps, and the split layout
+    const bool init_at_load = p.nconv == 1 || g.split;
+    const uint32_t init_col = g.split ? (uint32_t)(RB_SLOT_COLS / 2) : 0u;
+    const bool init_acp = p.acc_prev != nullptr && !g.split && last_pair == 0;   // split: the branch sum joins in the last phase
     auto publish_operand = [&](int slot) {
       cp_async_wait_all();
       fence_proxy_async();
@@ -298,14 +313,14 @@ __global__ void __launch_bounds__(RB_THREADS, 1) rb_kernel(RbParams p, RbGeom g)
         cp_async_commit();
         if (two) load_tile(1, 2 * q0 + 1);
         cp_async_commit();
-        if (p.nconv == 1) init_acc_from_x(0, 2 * q0);
+        if (init_at_load) init_acc_from_x(0, 2 * q0, init_col, init_acp);
         cp_async_wait_group<1>();
         fence_proxy_async();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_opnd(0));
         if (two) {
-          if (p.nconv == 1) init_acc_from_x(1, 2 * q0 + 1);
+          if (init_at_load) init_acc_from_x(1, 2 * q0 + 1, init_col, init_acp);
           publish_operand(1);
         }
       }
@@ -394,7 +409,24 @@ __global__ void __launch_bounds__(RB_THREADS, 1) rb_kernel(RbParams p, RbGeom g)
               for (int e = 0; e < 16; ++e) r[e] = __float_as_uint(res[e]);
               tst16(taddr, r);
             };
-            if (pair > 0 && !add_acp) {
+            if (g.split) {
+              // split layout: D2 already holds the residual stream; only TMEM(D1) -> operand buffer
+              for (Cur c = cur_first(); c.n < nitems; cur_next(c)) {
+                const bool inr = (unsigned)(tl0 + c.i * 128) < (unsigned)p.T;
+                uint32_t r[16];
+                tld16(tslot + (uint32_t)(c.i * g.Np + c.ch * 16), r);
+                float bv[16];
+                load_bias16(bv, bias_c + c.ch * 16);
+                tc_wait_ld();
+                float v[16];
+#pragma unroll
+                for (int e = 0; e < 16; ++e) {
+                  const float a = __uint_as_float(r[e]) + bv[e];
+                  v[e] = inr ? lrelu(a, p.slope) : 0.f;
+                }
+                store_opnd(opnd_off(c.i, c.ch), v);
+              }
+            } else if (pair > 0 && !add_acp) {
               // residual from the scratch: the next item's 64 bytes are requested before this item is processed
               float res0[16], res1[16];
               Cur c0 = cur_first();
@@ -427,13 +459,31 @@ __global__ void __launch_bounds__(RB_THREADS, 1) rb_kernel(RbParams p, RbGeom g)
                 e1_item(c, res);
               }
             }
-            tc_wait_st();
+            if (!g.split) tc_wait_st();
             publish_operand(slot);
           } else if (!final_step) {
             // ---- x_{p+1} = acc + b (the accumulator started from x_p).  nconv == 2: -> scratch for the next
             //      pair's accumulator init; nconv == 1: written straight back as the next conv's start value
             //      (+ the branch sum before the last conv).  lrelu(x_{p+1}) -> operand buffer.
             const bool add_acp = p.nconv == 1 && pair + 1 == last_pair && p.acc_prev != nullptr;
+            if (g.split) {
+              const float* cum = bias_s + (g.nsteps + pair) * g.Np;
+              for (Cur c = cur_first(); c.n < nitems; cur_next(c)) {
+                const bool inr = (unsigned)(tl0 + c.i * 128) < (unsigned)p.T;
+                uint32_t r[16];
+                tld16(tslot + (uint32_t)(RB_SLOT_COLS / 2) + (uint32_t)(c.i * g.Np + c.ch * 16), r);
+                float bv[16];
+                load_bias16(bv, cum + c.ch * 16);
+                tc_wait_ld();
+                float v[16];
+#pragma unroll
+                for (int e = 0; e < 16; ++e) {
+                  const float a = __uint_as_float(r[e]) + bv[e];
+                  v[e] = inr ? lrelu(a, p.slope) : 0.f;
+                }
+                store_opnd(opnd_off(c.i, c.ch), v);
+              }
+            } else
             for (Cur c = cur_first(); c.n < nitems; cur_next(c)) {
               const int t = tl0 + c.i * 128;
               const bool inr = (unsigned)t < (unsigned)p.T;
@@ -476,14 +526,21 @@ __global__ void __launch_bounds__(RB_THREADS, 1) rb_kernel(RbParams p, RbGeom g)
               const int t = tbase + row;
               const bool ok = row >= g.Hlo && row < g.Hlo + g.V && t < p.T;
               const int64_t off0 = bCT + (int64_t)(c.ch * 16) * p.T + t;
+              float acp[16];
+              const bool fin_acp = g.split && p.acc_prev != nullptr;
+              if (fin_acp) load_acp16(acp, p.acc_prev + off0, ok, c.ch);
               uint32_t r[16];
-              tld16(tslot + (uint32_t)(c.i * g.Np + c.ch * 16), r);
+              tld16(tslot + (g.split ? (uint32_t)(RB_SLOT_COLS / 2) : 0u) + (uint32_t)(c.i * g.Np + c.ch * 16), r);
               float bv[16];
-              load_bias16(bv, bias_c + c.ch * 16);
+              load_bias16(bv, (g.split ? bias_s + (g.nsteps + last_pair) * g.Np : bias_c) + c.ch * 16);
               tc_wait_ld();
               float v[16];
 #pragma unroll
-              for (int e = 0; e < 16; ++e) v[e] = (__uint_as_float(r[e]) + bv[e]) * g.out_scale;
+              for (int e = 0; e < 16; ++e) {
+                float a = __uint_as_float(r[e]) + bv[e];
+                if (fin_acp) a += acp[e];
+                v[e] = a * g.out_scale;
+              }
               if (ok && !sk_st) {
                 float* q = p.y + off0;
                 if (cfull || c.ch * 16 + 16 <= p.C) {
@@ -510,7 +567,7 @@ __global__ void __launch_bounds__(RB_THREADS, 1) rb_kernel(RbParams p, RbGeom g)
             }
             ++ntile_done;
             if (have_next) {
-              if (p.nconv == 1) init_acc_from_x(slot, next_tile);
+              if (init_at_load) init_acc_from_x(slot, next_tile, init_col, init_acp);
               publish_operand(slot);
             } else {
               tc_fence_before();
@@ -582,7 +639,7 @@ __global__ void __launch_bounds__(RB_THREADS, 1) rb_kernel(RbParams p, RbGeom g)
           ph_opnd ^= 1u << slot;
           tc_fence_after();
           const uint32_t a16 = (s0 + (uint32_t)slot * g.off_buf1) >> 4;
-          const uint32_t td = tmem + (uint32_t)(slot * RB_SLOT_COLS);
+          const uint32_t td = tmem + (uint32_t)(slot * RB_SLOT_COLS) + ((g.split && !zero_init) ? (uint32_t)(RB_SLOT_COLS / 2) : 0u);
           auto run_conv = [&](auto issue_first, auto issue_rest) {
             int kc = 0;                               // 32-channel K chunk of the current tap
             uint32_t arow = (uint32_t)(g.G - c * dil) * 2u;
@@ -670,7 +727,8 @@ int rb_make_geom(const RbParams& p, RbGeom& g) {
   if (p.npairs < 1 || p.npairs > AB_RB_MAX_PAIRS || (p.nconv != 1 && p.nconv != 2)) return fail(AB_ERR_ARG, "rb: bad chain");
   g.Np = rb_round_up(p.C, 16);
   g.nkc = (g.Np + 31) / 32;
-  g.m = std::min(RB_SLOT_COLS / g.Np, 16);
+  g.split = (p.split && p.nconv == 2 && p.npairs > 1 && g.Np <= 64) ? 1 : 0;
+  g.m = std::min((g.split ? RB_SLOT_COLS / 2 : RB_SLOT_COLS) / g.Np, 16);
   g.R = 128 * g.m;
   const int c = (p.k - 1) / 2;
   int dmax = 1;
@@ -701,7 +759,7 @@ int rb_make_geom(const RbParams& p, RbGeom& g) {
   const uint32_t buf_bytes = (uint32_t)g.RB * (uint32_t)g.Np * 2u;
   g.off_buf1 = (buf_bytes + 1023u) & ~1023u;
   g.off_w = (g.off_buf1 + buf_bytes + 1023u) & ~1023u;
-  const uint32_t tail = (uint32_t)g.nsteps * g.Np * 4u + 8u * (2 * RB_MAX_STAGES + 4) + 32u;
+  const uint32_t tail = (uint32_t)(g.nsteps + p.npairs) * g.Np * 4u + 8u * (2 * RB_MAX_STAGES + 4) + 32u;
   g.stage_bytes = g.chunk_bytes * (uint32_t)g.cps;
   while (g.cps > 1 && g.off_w + 3u * g.stage_bytes + tail > RB_SMEM_LIMIT) {   // keep at least three stages in the ring
     --g.cps;
@@ -710,7 +768,7 @@ int rb_make_geom(const RbParams& p, RbGeom& g) {
   if (g.off_w + 2u * g.stage_bytes + tail > RB_SMEM_LIMIT) return fail(AB_ERR_UNSUPPORTED, "rb: C=%d k=%d does not fit shared memory", p.C, p.k);
   g.nstages = std::min<int>((RB_SMEM_LIMIT - g.off_w - tail) / g.stage_bytes, RB_MAX_STAGES);
   g.off_bias = g.off_w + (uint32_t)g.nstages * g.stage_bytes;
-  g.off_bar = (g.off_bias + (uint32_t)g.nsteps * g.Np * 4u + 15u) & ~15u;
+  g.off_bar = (g.off_bias + (uint32_t)(g.nsteps + p.npairs) * g.Np * 4u + 15u) & ~15u;
   g.smem_bytes = g.off_bar + 8u * (2 * RB_MAX_STAGES + 4) + 16u;
   const uint32_t fmt = p.precision == AB_PREC_TC_BF16 ? 1u : 0u;
   g.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(g.Np >> 3) << 17) | ((128u >> 4) << 24);
@@ -733,15 +791,19 @@ size_t rb_scratch_bytes() { return (size_t)148 * 2 * (size_t)(RB_SLOT_COLS * 128
 // full 32 K-element tile (one pair per launch: ~26.5 k, bound by the HBM round trip of x / y / images), and the two
 // overlap imperfectly: t = max + 0.35 min.  Used to choose between one fused launch per block and one launch per
 // pair.  Returns 0 when the geometry is not served.
-double rb_cost_per_row(int C, int k, const int* dil, int npairs, int nconv) {
+double rb_cost_per_row(int C, int k, const int* dil, int npairs, int nconv, int split) {
   if (!rb_supported(C, k)) return 0.0;
-  const int Np = rb_round_up(C, 16), m = std::min(RB_SLOT_COLS / Np, 16), R = 128 * m;
+  const int Np = rb_round_up(C, 16);
+  if (split && !(nconv == 2 && npairs > 1 && Np <= 64)) return 0.0;
+  const int m = std::min((split ? RB_SLOT_COLS / 2 : RB_SLOT_COLS) / Np, 16), R = 128 * m;
   const int H = rb_halo(k, dil, npairs, nconv) - (k - 1) / 2 * dil[0];
   const int V = (R - rb_round_up(H, 4) - H) / 4 * 4;
   if (V < 32) return 0.0;
   const double fill = (double)(m * Np) / RB_SLOT_COLS;                       // tile elements / 32768
   const double mma = (double)nconv * npairs * k * (Np / 16.0) * m * (48.0 + 0.3 * Np);
-  const double epi = fill * (npairs == 1 ? (nconv == 2 ? 26500.0 : 22000.0) : 8000.0 * (nconv * npairs + 1));
+  const double phase = split ? 5500.0 : 8000.0;                              // split: no residual work in the epilogues
+  const double epi = npairs == 1 ? fill * (nconv == 2 ? 26500.0 : 22000.0)
+                                 : fill * phase * (nconv * npairs + 1) + (split ? 1500.0 * (nconv * npairs + 1) : 0.0);
   return (std::max(mma, epi) + 0.35 * std::min(mma, epi)) / V;
 }
 
@@ -754,7 +816,7 @@ int launch_rb(const RbParams& p, cudaStream_t s) {
   if (rc != AB_OK) return rc;
   for (int i = 0; i < g.nsteps; ++i)
     if (!p.w[i]) return fail(AB_ERR_ARG, "rb: missing weight image %d", i);
-  if (p.npairs > 1 && !p.scratch) return fail(AB_ERR_ARG, "rb: a fused chain needs the scratch buffer");
+  if (p.npairs > 1 && p.nconv == 2 && !g.split && !p.scratch) return fail(AB_ERR_ARG, "rb: a fused chain needs the scratch buffer");
   int dev = 0;
   AB_CUDA_TRY(cudaGetDevice(&dev));
   static DeviceOnce configured;
@@ -788,10 +850,10 @@ int launch_rb(const RbParams& p, cudaStream_t s) {
     const double ideal = (double)g.m * (g.Np / 2.0) * (g.Np / 16.0) * p.k * g.nsteps * a[5];   // 8192 flop/clk/SM
     const double law = (double)g.m * (64.0 + g.Np / 2.0) * (g.Np / 16.0) * p.k * g.nsteps * a[5];
     fprintf(stderr,
-            "[rb_timing] C=%d k=%d d=%d,%d,%d npairs=%d nconv=%d m=%d R=%d V=%d tiles=%d grid=%d stages=%dx%uB (%d chunks) | per CTA: "
+            "[rb_timing] C=%d k=%d d=%d,%d,%d npairs=%d nconv=%d split=%d m=%d R=%d V=%d tiles=%d grid=%d stages=%dx%uB (%d chunks) | per CTA: "
             "total %.0f cycles, %.1f tiles | MMA ideal %.0f law %.0f | issuer waits: operand %.0f weights %.0f | "
             "epilogue waits acc %.0f | producer waits %.0f\n",
-            p.C, p.k, p.dil[0], p.npairs > 1 ? p.dil[1] : 0, p.npairs > 2 ? p.dil[2] : 0, p.npairs, p.nconv, g.m, g.R, g.V,
+            p.C, p.k, p.dil[0], p.npairs > 1 ? p.dil[1] : 0, p.npairs > 2 ? p.dil[2] : 0, p.npairs, p.nconv, g.split, g.m, g.R, g.V,
             g.ntiles, grid, g.nstages, g.stage_bytes, g.cps, a[0], a[5], ideal, law, a[1], a[2], a[3], a[4]);
   }
   return AB_OK;

@@ -100,11 +100,12 @@ struct RbParams {
   int B, C, T, k;
   float slope, img_slope, out_div;
   int precision;
-  float* scratch;          // rb_scratch_bytes() bytes; required when npairs > 1
+  float* scratch;          // rb_scratch_bytes() bytes; required when npairs > 1 (shared-accumulator layout)
+  int split;               // 1: keep the residual stream in TMEM (two accumulators per slot, half the tile rows; C <= 64)
 };
 bool rb_supported(int C, int k);
 size_t rb_scratch_bytes();
-double rb_cost_per_row(int C, int k, const int* dil, int npairs, int nconv);
+double rb_cost_per_row(int C, int k, const int* dil, int npairs, int nconv, int split = 0);
 int launch_rb(const RbParams& p, cudaStream_t s);
 
 int tc_max_channels();

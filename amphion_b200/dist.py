@@ -99,10 +99,17 @@ def sharded_vocoder_inference(cfg, model, mels_local, n_global, group=None, dst=
         if device is None:
             device = next(model.parameters()).device
         mels_local = mels_local.to(device, non_blocking=True)
-        if ws == 1:
-            return model(mels_local).squeeze(1).detach().cpu()
-        wav = _sharded_forward(model, mels_local, n_global, rank, ws, group, dst, chunks)
-        return wav.squeeze(1).detach().cpu() if rank == dst else None
+        wav = model(mels_local) if ws == 1 else _sharded_forward(model, mels_local, n_global, rank, ws, group, dst, chunks)
+        if ws > 1 and rank != dst:
+            return None
+        wav = wav.squeeze(1).detach()
+        if not wav.is_cuda:
+            return wav
+        # a pinned buffer is still a CPU tensor and lets the D2H copy run at full PCIe rate
+        host = torch.empty(wav.shape, dtype=wav.dtype, pin_memory=True)
+        host.copy_(wav, non_blocking=True)
+        torch.cuda.current_stream(wav.device).synchronize()
+        return host
 
 
 def _sharded_forward(model, mel_local, B, rank, ws, group, dst, chunks):

@@ -149,7 +149,8 @@ int ab_generator_set_profiling(ab_generator* g, int32_t enable);
 /* Execution-plan options (no reference counterpart; tuning / test knobs, results stay within the stated tolerance):
  *   "resblock_fusion": 0 = one launch per (c1, c2) pair on the per-tile kernel, 1 = persistent kernel with one
  *   pair per launch, 2 (default) = persistent kernel, a whole ResBlock per launch when the cost model prefers
- *   it, 3 = always a whole ResBlock per launch.
+ *   it (with the residual stream resident in TMEM where that is cheaper still), 3 = always a whole ResBlock per
+ *   launch with the shared accumulator, 4 = always a whole ResBlock per launch, TMEM-resident residual where served.
  *   "nsf_source_frames" (NSF-HiFiGAN, one-shot, consumed by the next forward): frames of the f0 track when it does
  *   not cover the mel; every stage is then truncated to the harmonic source's length as the reference does
  *   (nsfhifigan.py:264-268) and the output holds ab_generator_output_samples() samples per utterance.
