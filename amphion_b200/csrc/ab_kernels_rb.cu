@@ -33,7 +33,7 @@ using namespace tcx;
 
 namespace {
 
-constexpr int RB_EPI_WARPS = 12;               // 3 per TMEM lane quarter; 14 warps -> 128 registers per thread
+constexpr int RB_EPI_WARPS = 12;               // 3 per TMEM lane quarter; 14 warps -> 128 registers per thread (16 warps at 96 registers: slower)
 constexpr int RB_PRODUCER_WARP = RB_EPI_WARPS, RB_MMA_WARP = RB_EPI_WARPS + 1;
 constexpr int RB_EPI_GROUPS = RB_EPI_WARPS / 4;
 constexpr int RB_EPI_THREADS = RB_EPI_WARPS * 32;
@@ -801,9 +801,10 @@ double rb_cost_per_row(int C, int k, const int* dil, int npairs, int nconv, int 
   if (V < 32) return 0.0;
   const double fill = (double)(m * Np) / RB_SLOT_COLS;                       // tile elements / 32768
   const double mma = (double)nconv * npairs * k * (Np / 16.0) * m * (48.0 + 0.3 * Np);
-  const double phase = split ? 5500.0 : 8000.0;                              // split: no residual work in the epilogues
-  const double epi = npairs == 1 ? fill * (nconv == 2 ? 26500.0 : 22000.0)
-                                 : fill * phase * (nconv * npairs + 1) + (split ? 1500.0 * (nconv * npairs + 1) : 0.0);
+  // an epilogue phase costs ~1.6 k cycles of hand-off latency plus ~0.2 cycles per element (measured: the split layout
+  // removes the residual work but halves the tile, so its fixed share doubles — it rarely wins)
+  const double phase = 1600.0 + fill * (split ? 6000.0 : 6400.0);
+  const double epi = npairs == 1 ? fill * (nconv == 2 ? 26500.0 : 22000.0) : phase * (nconv * npairs + 1);
   return (std::max(mma, epi) + 0.35 * std::min(mma, epi)) / V;
 }
 
