@@ -203,6 +203,9 @@ __device__ __forceinline__ float2 cmul(float2 a, float2 b) { return make_float2(
 __device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 __device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
 __device__ __forceinline__ float2 mul_mi(float2 a) { return make_float2(a.y, -a.x); }   // a * (-i)
+// XOR swizzle of the per-warp FFT buffers: every access pattern of the three passes (strides 1, 8 and 64 over 8-byte
+// elements) then takes the minimum two wavefronts; unswizzled, pass 0's stores are 16-way bank conflicts
+__device__ __forceinline__ int fsw(int i) { return i ^ ((i >> 4) & 15); }
 
 // forward 8-point DFT, natural order in and out
 __device__ __forceinline__ void dft8(float2 (&v)[8]) {
@@ -289,7 +292,7 @@ mel_fused_kernel(const float* __restrict__ y, const float* __restrict__ window, 
         }
         dft8(v);
 #pragma unroll
-        for (int r = 0; r < 8; ++r) bufA[8 * j + r] = v[r];
+        for (int r = 0; r < 8; ++r) bufA[fsw(8 * j + r)] = v[r];
       }
       __syncwarp();
       // ---- pass 1 (Ns = 8): twiddle exp(-2 pi i r k / 64), k = j mod 8; out[(j / 8) * 64 + k + 8 r]
@@ -299,13 +302,13 @@ mel_fused_kernel(const float* __restrict__ y, const float* __restrict__ window, 
         float2 v[8];
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
-          const float2 x = bufA[j + 64 * r];
+          const float2 x = bufA[fsw(j + 64 * r)];
           v[r] = r == 0 ? x : cmul(x, sm.w512[r * k * 8]);
         }
         dft8(v);
         const int o = (j >> 3) * 64 + k;
 #pragma unroll
-        for (int r = 0; r < 8; ++r) bufB[o + 8 * r] = v[r];
+        for (int r = 0; r < 8; ++r) bufB[fsw(o + 8 * r)] = v[r];
       }
       __syncwarp();
       // ---- pass 2 (Ns = 64): twiddle exp(-2 pi i r j / 512); out[j + 64 r] = Z in natural order
@@ -315,20 +318,20 @@ mel_fused_kernel(const float* __restrict__ y, const float* __restrict__ window, 
         float2 v[8];
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
-          const float2 x = bufB[j + 64 * r];
+          const float2 x = bufB[fsw(j + 64 * r)];
           v[r] = r == 0 ? x : cmul(x, sm.w512[r * j]);
         }
         dft8(v);
 #pragma unroll
-        for (int r = 0; r < 8; ++r) bufA[j + 64 * r] = v[r];
+        for (int r = 0; r < 8; ++r) bufA[fsw(j + 64 * r)] = v[r];
       }
       __syncwarp();
       // ---- real-FFT post-processing + magnitude: X[k] = Fe + W1024^k Fo, k = 0..512 -> mag in bufB (as floats)
       float* mag = reinterpret_cast<float*>(bufB);
       float e = 0.f;
       for (int k = lane; k <= FZ_H; k += 32) {
-        const float2 a = bufA[k & (FZ_H - 1)];
-        const float2 zb = bufA[(FZ_H - k) & (FZ_H - 1)];
+        const float2 a = bufA[fsw(k & (FZ_H - 1))];
+        const float2 zb = bufA[fsw((FZ_H - k) & (FZ_H - 1))];
         const float2 bc = make_float2(zb.x, -zb.y);
         const float2 fe = make_float2(0.5f * (a.x + bc.x), 0.5f * (a.y + bc.y));
         const float2 d = csub(a, bc);

@@ -22,7 +22,7 @@ def classify(name):
         return "conv1d_fp32"
     if "convT_fp32" in name:
         return "conv_transpose1d_fp32"
-    if "frame_window" in name or "mag_mel" in name or "fft" in name.lower() or "mel_span" in name:
+    if "mel_fused" in name or "frame_window" in name or "mag_mel" in name or "fft" in name.lower() or "mel_span" in name:
         return "mel"
     return None
 
