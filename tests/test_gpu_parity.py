@@ -783,12 +783,12 @@ def test_bucketed_synthesis_and_generate_to_files(tmp_path):
     cfg.preprocess.sample_rate = 16000
     hop = cfg.preprocess.hop_size
     gen = torch.Generator().manual_seed(9)
-    lens = [31, 9, 40, 12, 33, 10]
+    lens = [71, 49, 80, 52, 73, 50]
     mels = [torch.randn(g0["mel"].shape[1], n, generator=gen) for n in lens]
     plain = synthesis_audios(cfg, model, mels, batch_size=2)
     buck = synthesis_audios(cfg, model, mels, batch_size=2, bucket=True)
     assert [a.shape[0] for a in buck] == [n * hop for n in lens]                 # input order, trimmed lengths
-    rf = 20 * hop                                                                # > receptive field of the model
+    rf = 32 * hop      # > receptive field (rates [4, 2], k = 11, d = 1,3,5: 60 samples per block = 15 + 7.5 frames, + conv_pre 3)
     for a, b, n in zip(plain, buck, lens):
         keep = max(n * hop - rf, 0)
         assert torch.equal(a[:keep], b[:keep])
