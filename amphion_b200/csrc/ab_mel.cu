@@ -245,15 +245,26 @@ mel_fused_kernel(const float* __restrict__ y, const float* __restrict__ window, 
     const int wi = n - lpad;
     sm.window[n] = (wi >= 0 && wi < win) ? __ldg(window + wi) : 0.f;
   }
-  if (threadIdx.x == 0) {
-    int off = 0;
-    for (int m = 0; m < n_mel; ++m) {
-      const int2 sp = span_g[m];
-      sm.span[m] = sp;
-      sm.voff[m] = off;
-      off += sp.y - sp.x;
+  if (warp == 0) {
+    // spans and the exclusive prefix sum of their lengths (tap offsets), 32 filters per round
+    int carry = 0;
+    for (int m0 = 0; m0 < n_mel; m0 += 32) {
+      const int m = m0 + lane;
+      const int2 sp = m < n_mel ? span_g[m] : make_int2(0, 0);
+      const int len = sp.y - sp.x;
+      int inc = len;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += v;
+      }
+      if (m < n_mel) {
+        sm.span[m] = sp;
+        sm.voff[m] = carry + inc - len;
+      }
+      carry += __shfl_sync(0xffffffffu, inc, 31);
     }
-    sm.fits = off <= FZ_MAXVAL;
+    if (lane == 0) sm.fits = carry <= FZ_MAXVAL;
   }
   __syncthreads();
   if (sm.fits) {
