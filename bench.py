@@ -277,7 +277,7 @@ def _roofline(prof, ms_total, samples_rank_step, flop, workload, B, T, precision
     return r
 
 
-def measure_generator(workload, args, dev, rank, world, steps, warmup, want_cpu, clocks_on_rank0=True):
+def measure_generator(workload, args, dev, rank, world, steps, warmup, want_cpu, clocks_on_rank0=True, shape=None):
     """One workload on the native path: device-resident `value` (CUDA events, max over ranks), `e2e` through the
     reference-facing call with pinned host buffers, per-class roofline from the C ABI's launch events."""
     import torch
@@ -298,6 +298,8 @@ def measure_generator(workload, args, dev, rank, world, steps, warmup, want_cpu,
     model.precision = args.precision
     B = args.batch if (args.batch and workload == args.workload) else w["batch"]
     T = args.frames if (args.frames and workload == args.workload) else w["frames"]
+    if shape is not None:
+        B, T = shape
     n_mel = w["n_mel"]
     mel = torch.randn(B, n_mel, T, generator=torch.Generator().manual_seed(rank)).to(dev)
     samples_step = world * B * T * HOP
@@ -372,7 +374,7 @@ def measure_generator(workload, args, dev, rank, world, steps, warmup, want_cpu,
         tfl = B * T * HOP * w["flop"] / (ms_step / 1e3) / 1e12
         res["roofline"]["whole_step"] = dict(tflops=tfl, frac_of_tensor_peak=tfl / peaks()["tensor"])
         if want_cpu:
-            sb, st = {"hifigan_v1": (2, T), "bigvgan_base": (1, 256), "bigvgan_large": (1, 128)}[workload]
+            sb, st = {"hifigan_v1": (min(2, B), T), "bigvgan_base": (1, 256), "bigvgan_large": (1, 128)}[workload]
             res["cpu_baseline"] = cpu_oracle_rate(workload, sb, st, repeats=2 if workload == "hifigan_v1" else 1,
                                                   all_cores_too=workload == "hifigan_v1")
         else:
@@ -524,6 +526,10 @@ def run_native(args, rank, local_rank, world):
                 if wl != args.workload:
                     also[wl] = measure_generator(wl, args, dev, rank, world, 3, 3, want_cpu, clocks_on_rank0=False)
             also["mel"] = measure_mel(dev, want_cpu=want_cpu)
+            # BASELINE config 1: HiFi-GAN V1, batch 1, 80x200 mel through the egs/vocoder plumbing (CPU leg timed in full)
+            r = measure_generator("hifigan_v1", args, dev, rank, world, 20, 3, want_cpu, clocks_on_rank0=False, shape=(1, 200))
+            r["baseline_config"] = "config 1 (batch 1, 80x200 mel; the reference runs it on the CPU)"
+            also["hifigan_v1_b1_t200"] = r
             eager = measure_gpu_eager(args, dev)
         elif args.workload != "bigvgan_large":
             # BASELINE config 5: BigVGAN-large, 32 utterances per GPU, 100x2048 mel, gather to rank 0
