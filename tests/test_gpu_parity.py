@@ -831,3 +831,15 @@ def test_in_model_generators_of_jets_and_vits_svc_are_the_registry_class(n_in, t
         got = model(z.to(DEV)).cpu().numpy()
         assert got.shape == (2, 1, 33 * 256)
         assert np.abs(got - want).max() <= tol, (tag, prec, np.abs(got - want).max())
+
+
+@pytest.mark.parametrize("T", [1, 3])
+def test_v1_shorter_than_every_halo(T):
+    """A mel of one or three frames: every tile of every stage is mostly zero padding (the fused kernel's rows are
+    nearly all outside [0, T)); all plans against the CPU oracle."""
+    model, mel, want = _full_size_case("hifigan", HP_V1, 80, 2, T, seed=60 + T)
+    for mode in (0, 2, 3):
+        model.set_option("resblock_fusion", mode)
+        got = model(mel.to(DEV)).cpu().numpy()
+        assert got.shape == want.shape
+        assert np.abs(got - want).max() <= 1e-3, (mode, np.abs(got - want).max())
