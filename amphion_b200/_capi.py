@@ -10,7 +10,7 @@ AB_MAX_STAGES = 8
 AB_MAX_KERNELS = 8
 AB_MAX_DILATIONS = 8
 
-GEN_HIFIGAN, GEN_BIGVGAN, GEN_NSFHIFIGAN = 0, 1, 2
+GEN_HIFIGAN, GEN_BIGVGAN, GEN_NSFHIFIGAN, GEN_TRUNK = 0, 1, 2, 3
 ACT_LRELU, ACT_SNAKE, ACT_SNAKEBETA = 0, 1, 2
 PRECISIONS = {"fp32": 0, "tc_f16": 1, "tc_bf16": 2}
 
@@ -32,6 +32,9 @@ class GeneratorConfig(C.Structure):
         ("snake_logscale", C.c_int32),
         ("gin_channels", C.c_int32),
         ("conv_post_no_bias", C.c_int32),
+        ("trunk_out_channels", C.c_int32),
+        ("trunk_in_kernel", C.c_int32),
+        ("trunk_out_kernel", C.c_int32),
     ]
 
 
@@ -90,6 +93,11 @@ SIGNATURES = {
     "ab_mel_workspace_bytes": (C.c_size_t, [_P, C.c_int64, C.c_int64]),
     "ab_mel_forward": (C.c_int, [_P, _P, C.c_int64, C.c_int64, _P, _P, _P, _P, _P, _P, C.c_size_t, _P]),
     "ab_mel_forward_fused": (C.c_int, [_P, _P, C.c_int64, C.c_int64, _P, _P, _P, _P, _P, C.c_size_t, _P]),
+    "ab_mel_backward_workspace_bytes": (C.c_size_t, [_P, C.c_int64, C.c_int64]),
+    "ab_mel_backward": (C.c_int, [_P, _P, C.c_int64, C.c_int64, _P, _P, _P, _P, _P, C.c_size_t, _P]),
+    "ab_spectral_head_forward": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int64, C.c_int64, _P, _P, _P, _P, _P]),
+    "ab_istft_workspace_bytes": (C.c_size_t, [_P, C.c_int64, C.c_int64]),
+    "ab_istft_forward": (C.c_int, [_P, _P, C.c_int64, C.c_int64, _P, _P, _P, C.c_size_t, _P]),
     "ab_pcm16_workspace_bytes": (C.c_size_t, [C.c_int64]),
     "ab_pcm16_forward": (C.c_int, [_P, C.c_int64, C.c_int64, C.c_int64, _P, C.c_int32, C.c_float, C.c_int64, _P, C.c_int64,
                                    _P, C.c_size_t, _P]),

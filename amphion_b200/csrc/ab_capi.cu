@@ -79,6 +79,7 @@ struct StageRef {
   ConvRef up;   // cin/cout/k, d unused; stride in `u`
   int u = 1;
   int ch = 0;
+  bool has_up = true;   // false: AB_GEN_TRUNK's single stage (no transposed conv in front of the blocks)
   std::vector<BlockRef> blocks;
 };
 
@@ -99,6 +100,8 @@ struct ab_generator {
   int rb_mode = 2;          // "resblock_fusion" option; AB_RB in the environment sets the initial value
   std::vector<cudaEvent_t> tail_events;   // ab_generator_set_tail_events: consumed by the next forward
   int64_t source_frames = 0;              // NSF-HiFiGAN: frames of the f0 track of the next forward (0 = covers the mel)
+
+  std::unordered_map<int, SnakeCoef> act_coef;   // by up-filter slot: host copy of the 12+12 taps, packed (finalize)
 
   ConvRef conv_pre, conv_post;
   int cond_w = -1, cond_b = -1;   // HiFiGAN_vits global conditioning (hifigan.py:424-425)
@@ -177,10 +180,20 @@ ActRef make_act(ab_generator* g, const std::string& prefix, int ch, bool has_bet
 }
 
 int validate_config(const ab_generator_config& c) {
-  if (c.kind != AB_GEN_HIFIGAN && c.kind != AB_GEN_BIGVGAN && c.kind != AB_GEN_NSFHIFIGAN)
+  if (c.kind != AB_GEN_HIFIGAN && c.kind != AB_GEN_BIGVGAN && c.kind != AB_GEN_NSFHIFIGAN && c.kind != AB_GEN_TRUNK)
     return fail(AB_ERR_ARG, "config: unknown generator kind %d", c.kind);
+  const bool trunk = c.kind == AB_GEN_TRUNK;
+  if (trunk) {
+    if (c.num_upsamples != 0) return fail(AB_ERR_ARG, "config: a trunk has no upsampling stages");
+    if (c.trunk_out_channels <= 0 || c.trunk_out_channels > 65536) return fail(AB_ERR_ARG, "config: trunk_out_channels %d out of range", c.trunk_out_channels);
+    if (c.trunk_in_kernel <= 0 || !(c.trunk_in_kernel & 1) || c.trunk_out_kernel <= 0 || !(c.trunk_out_kernel & 1))
+      return fail(AB_ERR_UNSUPPORTED, "config: trunk conv kernels must be odd (got %d, %d)", c.trunk_in_kernel, c.trunk_out_kernel);
+    if (c.resblock != 1) return fail(AB_ERR_UNSUPPORTED, "config: the trunk uses ResBlock1 blocks (apnet.py:113-278)");
+  } else if (c.trunk_out_channels || c.trunk_in_kernel || c.trunk_out_kernel) {
+    return fail(AB_ERR_ARG, "config: trunk_* fields belong to AB_GEN_TRUNK");
+  }
   if (c.n_mel <= 0 || c.upsample_initial_channel <= 0) return fail(AB_ERR_ARG, "config: n_mel / upsample_initial_channel must be positive");
-  if (c.num_upsamples <= 0 || c.num_upsamples > AB_MAX_STAGES) return fail(AB_ERR_ARG, "config: num_upsamples %d out of range", c.num_upsamples);
+  if ((!trunk && c.num_upsamples <= 0) || c.num_upsamples > AB_MAX_STAGES) return fail(AB_ERR_ARG, "config: num_upsamples %d out of range", c.num_upsamples);
   if (c.num_kernels <= 0 || c.num_kernels > AB_MAX_KERNELS) return fail(AB_ERR_ARG, "config: num_kernels %d out of range", c.num_kernels);
   if (c.resblock != 1 && c.resblock != 2) return fail(AB_ERR_ARG, "config: resblock must be 1 or 2");
   if ((c.upsample_initial_channel >> c.num_upsamples) <= 0) return fail(AB_ERR_ARG, "config: upsample_initial_channel too small for %d stages", c.num_upsamples);
@@ -227,9 +240,29 @@ int ab_generator_create(const ab_generator_config* cfg, ab_generator** out) {
   const bool big = cfg->kind == AB_GEN_BIGVGAN;
   const bool has_beta = cfg->activation == AB_ACT_SNAKEBETA;
   const int c0 = cfg->upsample_initial_channel;
-  g->conv_pre = make_conv(g, "conv_pre", cfg->n_mel, c0, 7, 1, false);
+  const bool trunk = cfg->kind == AB_GEN_TRUNK;
+  g->conv_pre = make_conv(g, "conv_pre", cfg->n_mel, c0, trunk ? cfg->trunk_in_kernel : 7, 1, false);
   g->hop = 1;
   int ch = c0;
+  if (trunk) {   // one stage at the input rate: no transposed conv, the ResBlock branches read conv_pre's output
+    StageRef st;
+    st.ch = c0;
+    st.u = 1;
+    st.has_up = false;
+    for (int j = 0; j < cfg->num_kernels; ++j) {
+      BlockRef blk;
+      blk.k = cfg->resblock_kernel_sizes[j];
+      const std::string pre = "resblocks." + std::to_string(j);
+      for (int p = 0; p < cfg->num_dilations[j]; ++p) {
+        const int d = cfg->resblock_dilation_sizes[j][p];
+        blk.dil.push_back(d);
+        blk.c1.push_back(make_conv(g, pre + ".convs1." + std::to_string(p), ch, ch, blk.k, d, false));
+        blk.c2.push_back(make_conv(g, pre + ".convs2." + std::to_string(p), ch, ch, blk.k, 1, false));
+      }
+      st.blocks.push_back(blk);
+    }
+    g->stages.push_back(st);
+  }
   for (int i = 0; i < cfg->num_upsamples; ++i) {
     StageRef st;
     const int cin = c0 >> i;
@@ -266,7 +299,8 @@ int ab_generator_create(const ab_generator_config* cfg, ab_generator** out) {
     g->stages.push_back(st);
   }
   if (big) g->act_post = make_act(g, "activation_post", ch, has_beta);
-  g->conv_post = make_conv(g, "conv_post", ch, 1, 7, 1, false, !cfg->conv_post_no_bias);
+  g->conv_post = make_conv(g, "conv_post", ch, trunk ? cfg->trunk_out_channels : 1, trunk ? cfg->trunk_out_kernel : 7, 1, false,
+                           !cfg->conv_post_no_bias);
   if (cfg->gin_channels > 0) {
     g->cond_w = g->add_slot("cond.weight", SLOT_VEC, {c0, cfg->gin_channels, 1});
     g->cond_b = g->add_slot("cond.bias", SLOT_VEC, {c0});
@@ -400,6 +434,28 @@ int ab_generator_finalize(ab_generator* g, int32_t precision, void* stream) {
         rc = launch_gs_pack_weight(g->fptr((int)i), g->tcptr((int)i), 1, (int)s.shape[0], (int)s.shape[1],
                                    (int)s.shape[2], s.stride, precision, st);
       if (rc != AB_OK) return rc;
+    }
+  }
+  // Activation1d taps: 24 floats per activation go to the host once, so that every later launch carries them by value
+  // (uniform-register operands of the packed FMAs).  The only synchronising step of the handle's life.
+  g->act_coef.clear();
+  {
+    const std::string up_suffix = ".upsample.filter";
+    std::vector<int> ups;
+    for (size_t i = 0; i + 1 < g->slots.size(); ++i) {
+      const std::string& n = g->slots[i].name;
+      if (n.size() > up_suffix.size() && n.compare(n.size() - up_suffix.size(), up_suffix.size(), up_suffix) == 0) ups.push_back((int)i);
+    }
+    std::vector<float> host(ups.size() * 24);
+    for (size_t j = 0; j < ups.size(); ++j) {     // make_act: the down filter is the slot after the up filter
+      if (cudaMemcpyAsync(&host[j * 24], g->fptr(ups[j]), 12 * sizeof(float), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+          cudaMemcpyAsync(&host[j * 24 + 12], g->fptr(ups[j] + 1), 12 * sizeof(float), cudaMemcpyDeviceToHost, st) != cudaSuccess)
+        return fail(AB_ERR_CUDA, "finalize: reading the anti-aliasing filters failed: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+    if (!ups.empty()) {
+      if (cudaStreamSynchronize(st) != cudaSuccess)
+        return fail(AB_ERR_CUDA, "finalize: %s", cudaGetErrorString(cudaGetLastError()));
+      for (size_t j = 0; j < ups.size(); ++j) pack_snake_coef(&host[j * 24], &host[j * 24 + 12], &g->act_coef[ups[j]]);
     }
   }
   g->precision = precision;
@@ -598,6 +654,9 @@ static int forward_impl(ab_generator* g, const float* dev_mel, int64_t B, int64_
     p.yimg = yimg; p.bf16 = g->precision == AB_PREC_TC_BF16;
     p.x = x; p.y = y; p.alpha = g->fptr(a.alpha); p.beta = g->fptr(a.beta);
     p.f_up = g->fptr(a.fup); p.f_down = g->fptr(a.fdown);
+    auto kc = g->act_coef.find(a.fup);
+    if (kc != g->act_coef.end()) { p.kc = kc->second; p.have_kc = 1; }
+    p.fast_snake = g->precision != AB_PREC_FP32;
     p.B = (int)B; p.C = C; p.T = Tn; p.logscale = g->cfg.snake_logscale;
     ++launches;
     prof_begin(3, 0.0, (double)B * C * Tn * (4.0 + (y ? 4.0 : 0.0) + (yimg ? 2.0 : 0.0)));
@@ -694,12 +753,15 @@ static int forward_impl(ab_generator* g, const float* dev_mel, int64_t B, int64_
   for (size_t i = 0; i < g->stages.size(); ++i) {
     const StageRef& sg = g->stages[i];
     // x = leaky_relu(x, 0.1) (HiFi-GAN only) ; x = ups[i](x)   (hifigan.py:206-207, bigvgan.py:316-318)
+    uint16_t* u_img = nullptr;
+    if (!sg.has_up) {
+      std::swap(U, R[cur_r]);   // AB_GEN_TRUNK: the blocks read conv_pre's output in place
+    } else {
     ConvTParams tp;
     tp.x = R[cur_r]; tp.w_t = g->fptr(sg.up.w); tp.bias = g->fptr(sg.up.b); tp.y = U;
     tp.B = (int)B; tp.Cin = cin; tp.Cout = sg.ch; tp.Tin = Tn; tp.k = sg.up.k; tp.u = sg.u;
     tp.pre_slope = big ? 1.0f : 0.1f;
     ++launches;
-    uint16_t* u_img = nullptr;
     {
       const double eo = (double)B * sg.ch * Tn * sg.u;
       prof_begin(2, 2.0 * eo * cin * ((double)sg.up.k / sg.u),
@@ -730,6 +792,7 @@ static int forward_impl(ab_generator* g, const float* dev_mel, int64_t B, int64_
     }
     prof_end();
     if (rc != AB_OK) return rc;
+    }
     Tn *= sg.u;
     const int C = sg.ch;
     {
@@ -880,7 +943,8 @@ static int forward_impl(ab_generator* g, const float* dev_mel, int64_t B, int64_
   for (int ci = 0; ci < nchunk; ++ci) {
     const int64_t b0 = Bfull * ci / nchunk, b1 = Bfull * (ci + 1) / nchunk;
     B = b1 - b0;
-    rc = conv(g->conv_post, xin + b0 * sb, sb, sc, 1, dev_wav + b0 * Tn, Tn, big ? 1.0f : 0.01f, nullptr, nullptr, 1.0f, 1);
+    rc = conv(g->conv_post, xin + b0 * sb, sb, sc, 1, dev_wav + b0 * g->conv_post.cout * Tn, Tn, big ? 1.0f : 0.01f, nullptr,
+              nullptr, 1.0f, g->cfg.kind == AB_GEN_TRUNK ? 0 : 1);
     B = Bfull;
     if (rc != AB_OK) break;
     if (!g->tail_events.empty()) {

@@ -70,7 +70,17 @@ struct ConvTParams {
   float pre_slope;
 };
 
+// Filter taps of one Activation1d as the packed pairs the kernel multiplies with (host-side copy, passed by value so
+// they sit in the constant bank / uniform registers): see snake_segment in ab_kernels_fp32.cu.
+struct SnakeCoef {
+  float2 ce_a[3], co_a[3], ce_b[4], co_b[4], fd2[6];
+};
+void pack_snake_coef(const float* f_up, const float* f_down, SnakeCoef* out);   // host pointers, 12 taps each
+
 struct SnakeParams {
+  SnakeCoef kc;         // valid when have_kc (the generator path); otherwise the kernel reads f_up / f_down
+  int have_kc = 0;
+  int fast_snake = 0;   // image-only launches may use the snake without explicit range reduction (tensor-core generators)
   const float* x;       // contiguous [B, C, T]
   float* y;
   const float* alpha;   // [C]

@@ -405,9 +405,16 @@ int launch_conv_transpose1d_fp32(const ConvTParams& p, cudaStream_t s) {
 // exp / reciprocal computed once per CTA, and a lane-private transposition buffer for the operand image.
 // ===========================================================================
 namespace {
+#ifndef AB_SNAKE_BLOCKS
+#define AB_SNAKE_BLOCKS 3      // CTAs per SM the activation kernel is compiled for (register budget)
+#endif
 constexpr int SN_WS = 120;                 // outputs per warp segment (30 lanes x 4)
 constexpr int SN_XS = 136;                 // xs[m] = xh[t0 - 8 + m]            (34 float4)
-constexpr int SN_XR = 3;                   // x windows in flight per warp (cp.async ring, two channels ahead)
+#ifndef AB_SNAKE_AHEAD
+#define AB_SNAKE_AHEAD 2       // channels whose windows are in flight ahead of the one being computed
+#endif
+constexpr int SN_AHEAD = AB_SNAKE_AHEAD;
+constexpr int SN_XR = SN_AHEAD + 1;        // x windows per warp (cp.async ring)
 constexpr int SN_VS = 256;                 // vs[n] = vh[2*t0 - 7 + n]          (64 groups of 4 = 2 full rounds)
 constexpr int SN_TR = 8 * 32 * 2;          // image transposition: [8 ch][32 lanes] x 8 B, lane-private
 constexpr int WT = 8 * SN_WS;              // outputs per CTA tile (8 warps)
@@ -422,6 +429,43 @@ __device__ __forceinline__ float snake_eval(float u, float a, float invb) {
   return fmaf(invb, sv * sv, u);
 }
 
+// Packed fp32 pairs (sm_100 FFMA2 / FMUL2 / FADD2: one issue slot for two lanes of work).  A pair lives in an
+// aligned 64-bit register; 8- and 16-byte shared-memory loads deliver pairs without any move.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void upk2(f32x2 v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ float hsum2(f32x2 v) {
+  float lo, hi;
+  upk2(v, lo, hi);
+  return lo + hi;
+}
+
+// Two snake evaluations at once, without explicit range reduction: sin.approx multiplies by 1/2pi and the MUFU
+// reduces in turns, so the phase error is ~1.2e-7 * |u a| rad.  Used on the 16-bit operand path only (the operand
+// rounding is 5e-4 relative); the fp32 outputs keep the Cody-Waite reduction of snake_eval.
+__device__ __forceinline__ f32x2 snake_eval2_fast(f32x2 u, f32x2 a2, f32x2 invb2) {
+  float r0, r1;
+  upk2(mul2(u, a2), r0, r1);
+  const f32x2 sv = pk2(__sinf(r0), __sinf(r1));
+  return fma2(mul2(sv, sv), invb2, u);
+}
+
 template <int BF16>
 __device__ __forceinline__ uint32_t cvt_pair(float lo, float hi) {
   uint32_t r;
@@ -433,64 +477,122 @@ __device__ __forceinline__ uint32_t cvt_pair(float lo, float hi) {
 // All 8 channels of one warp segment.  FAST: the whole window [t0-8, t0+128) lies inside the row and rows are
 // 16-byte aligned, so the fetch is one float4 per lane and no index is clamped; otherwise (sequence edges,
 // odd T) every index is replicate-clamped exactly as the reference's padding does.
-template <bool FAST, int BF16>
+// MODE 0: taps from global memory, outputs chosen at run time (the standalone operator).
+// MODE 1: taps pre-packed in the kernel parameters (uniform registers), outputs chosen at run time.
+// MODE 2: as 1, operand image only and the short snake (tensor-core generators).
+template <bool FAST, int BF16, int MODE>
 __device__ __forceinline__ void snake_segment(const SnakeParams& p, const float* __restrict__ xb, int c8, int b, int t0,
                                               const float (*prm)[2], float* xs, float* vs, uint2* tr, int lane) {
+  constexpr bool KP = MODE != 0;
   const int T = p.T, C = p.C;
+  const bool want_y = MODE != 2 && p.y != nullptr;
+  const bool want_img = MODE == 2 || p.yimg != nullptr;
   float fu2[12], fd[12];
 #pragma unroll
-  for (int j = 0; j < 12; ++j) {
-    fu2[j] = 2.0f * __ldg(p.f_up + j);
-    fd[j] = __ldg(p.f_down + j);
+  for (int j = 0; j < 12; ++j) {            // scalar taps: the sequence-edge path (and the pairs below when !KP)
+    fu2[j] = KP ? ((10 - j) % 4 == 0 ? p.kc.ce_a[(10 - j) / 4].x : (10 - j) % 4 == 2 ? p.kc.ce_a[(8 - j) / 4].y
+                   : (11 - j) % 4 == 0 ? p.kc.co_a[(11 - j) / 4].x : p.kc.co_a[(9 - j) / 4].y)
+                : 2.0f * __ldg(p.f_up + j);
+    fd[j] = KP ? (j % 2 == 0 ? p.kc.fd2[j / 2].x : p.kc.fd2[j / 2].y) : __ldg(p.f_down + j);
+  }
+  // coefficient pairs: even-phase taps ce[m] = fu2[10-2m], odd-phase co[m] = fu2[11-2m].  Outputs at input position
+  // q use xs pairs (w[2p], w[2p+1]) with (c[2p], c[2p+1]); those at q+1 use the same pairs with (c[2p-1], c[2p]).
+  f32x2 ce_a[3], co_a[3], ce_b[4], co_b[4], fd2[6];
+  if (KP) {                                  // pre-packed on the host: constant-bank / uniform-register operands
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      ce_a[q] = *reinterpret_cast<const f32x2*>(&p.kc.ce_a[q]);
+      co_a[q] = *reinterpret_cast<const f32x2*>(&p.kc.co_a[q]);
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      ce_b[q] = *reinterpret_cast<const f32x2*>(&p.kc.ce_b[q]);
+      co_b[q] = *reinterpret_cast<const f32x2*>(&p.kc.co_b[q]);
+    }
+#pragma unroll
+    for (int q = 0; q < 6; ++q) fd2[q] = *reinterpret_cast<const f32x2*>(&p.kc.fd2[q]);
+  } else {
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      ce_a[q] = pk2(fu2[10 - 4 * q], fu2[8 - 4 * q]);
+      co_a[q] = pk2(fu2[11 - 4 * q], fu2[9 - 4 * q]);
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      ce_b[q] = pk2(q > 0 ? fu2[12 - 4 * q] : 0.f, q < 3 ? fu2[10 - 4 * q] : 0.f);
+      co_b[q] = pk2(q > 0 ? fu2[13 - 4 * q] : 0.f, q < 3 ? fu2[11 - 4 * q] : 0.f);
+    }
+#pragma unroll
+    for (int q = 0; q < 6; ++q) fd2[q] = pk2(fd[2 * q], fd[2 * q + 1]);
   }
   const int i0 = 2 * t0 - 7, imax = 2 * T - 1;
   const int tl = 4 * lane;
   float ne[5] = {0.f, 0.f, 0.f, 0.f, 0.f};                     // edge path: prefetch registers
-  // FAST: 16-byte cp.async straight into a 3-deep ring of windows, issued two channels ahead (DRAM latency under
-  // load exceeds one channel's compute); one commit group per channel, empty groups keep the count uniform
-  float* const xs_ring = xs;
-  auto fetch = [&](int c, int slot) {
+  // FAST: 16-byte cp.async straight into a ring of SN_XR windows, issued SN_AHEAD channels ahead (DRAM latency under
+  // load exceeds one channel's compute); one commit group per channel, empty groups keep the count uniform.
+  // Source pointer and ring offsets advance by increments (no per-channel multiplies or modulo).
+  const int c_first = c8 * 8;
+  const float* src = xb + (int64_t)c_first * T + (t0 - 8) + 4 * lane;      // FAST: this lane's 16 bytes of channel c
+  const uint32_t ring0 = (uint32_t)__cvta_generic_to_shared(xs) + 16u * lane;
+  constexpr uint32_t SLOT_B = SN_XS * 4;
+  auto fetch_fast = [&](const float* sp, uint32_t slot_off) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(ring0 + slot_off), "l"(sp) : "memory");
+    if (lane < 2)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(ring0 + slot_off + 512u), "l"(sp + 128) : "memory");
+  };
+  auto fetch_edge = [&](int c) {
     const float* xr = xb + (int64_t)c * T;
-    if (FAST) {
-      const float* src = xr + t0 - 8;
-      const uint32_t dst = (uint32_t)__cvta_generic_to_shared(xs_ring + slot * SN_XS);
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16u * lane), "l"(src + 4 * lane) : "memory");
-      if (lane < 2)
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 512u + 16u * lane), "l"(src + 128 + 4 * lane) : "memory");
-    } else {
 #pragma unroll
-      for (int q = 0; q < 5; ++q) {
-        const int m = lane + 32 * q;
-        const int t = min(max(t0 - 8 + m, 0), T - 1);
-        ne[q] = (m < SN_XS) ? __ldg(xr + t) : 0.f;
-      }
+    for (int q = 0; q < 5; ++q) {
+      const int m = lane + 32 * q;
+      const int t = min(max(t0 - 8 + m, 0), T - 1);
+      ne[q] = (m < SN_XS) ? __ldg(xr + t) : 0.f;
     }
   };
-  const int c_first = c8 * 8;
   if (FAST) {
 #pragma unroll
-    for (int pre = 0; pre < 2; ++pre) {
-      if (c_first + pre < C) fetch(c_first + pre, pre);
+    for (int pre = 0; pre < SN_AHEAD; ++pre) {
+      if (c_first + pre < C) fetch_fast(src + (int64_t)pre * T, pre * SLOT_B);
       asm volatile("cp.async.commit_group;" ::: "memory");
     }
   } else if (c_first < C) {
-    fetch(c_first, 0);
+    fetch_edge(c_first);
+  }
+  const float* src_nxt = src + SN_AHEAD * (int64_t)T;          // channel c + SN_AHEAD
+  uint32_t slot_cur = 0, slot_nxt = SN_AHEAD * SLOT_B;         // byte offsets of the windows of channels c and c + SN_AHEAD
+  float* yr = want_y ? p.y + ((int64_t)b * C + c_first) * T + t0 + tl : nullptr;
+  float* const xs_ring = xs;
+  // The 2x-rate window vs is stored by 16-byte units u = n / 4 at position u ^ ((u >> 3) & 1): phase 2 reads units
+  // 2 lane + q, a 32-byte lane stride that would otherwise put lanes l and l + 4 of a quarter warp on the same banks.
+  // Units 2m and 2m + 1 share their group of 8, so a pair keeps its 32 bytes and only swaps halves when the bit is set.
+  const int sw_l = (lane >> 2) & 1;
+  float* const vs_wA = vs + 8 * lane + 4 * sw_l;           // group 2 lane
+  float* const vs_wB = vs + 8 * lane + 4 * (1 - sw_l);     // group 2 lane + 1
+  const float* vs_r[3][2];
+#pragma unroll
+  for (int q = 0; q < 3; ++q) {
+    const int m = lane + q, sm = (m >> 2) & 1;
+    vs_r[q][0] = vs + 8 * m + 4 * sm;
+    vs_r[q][1] = vs + 8 * m + 4 * (1 - sm);
   }
 #pragma unroll 1
   for (int cg = 0; cg < 8; ++cg) {
     const int c = c_first + cg;
     if (c >= C) {
-      if (p.yimg != nullptr) tr[cg * 32 + lane] = make_uint2(0u, 0u);   // padding channels of the image
+      if (want_img) tr[cg * 32 + lane] = make_uint2(0u, 0u);   // padding channels of the image
       continue;
     }
     const float a = prm[cg][0], invb = prm[cg][1];
     if (FAST) {
-      asm volatile("cp.async.wait_group 1;" ::: "memory");   // this channel's window has landed (the next may be in flight)
+      asm volatile("cp.async.wait_group %0;" ::"n"(SN_AHEAD - 1) : "memory");   // this channel's window has landed
       __syncwarp();                                          // ... for every lane; also: phase 2 of cg-1 is done with vs
-      xs = xs_ring + (cg % SN_XR) * SN_XS;
-      // slot (cg + 2) % 3 was read in iteration cg - 1, which every lane has left
-      if (c + 2 < C && cg + 2 < 8) fetch(c + 2, (cg + 2) % SN_XR);
+      xs = reinterpret_cast<float*>(reinterpret_cast<char*>(xs_ring) + slot_cur);
+      // the slot of channel c + SN_AHEAD was read in iteration cg - 1, which every lane has left
+      if (c + SN_AHEAD < C && cg + SN_AHEAD < 8) fetch_fast(src_nxt, slot_nxt);
       asm volatile("cp.async.commit_group;" ::: "memory");
+      src_nxt += T;
+      slot_cur = slot_cur == SN_AHEAD * SLOT_B ? 0u : slot_cur + SLOT_B;
+      slot_nxt = slot_nxt == SN_AHEAD * SLOT_B ? 0u : slot_nxt + SLOT_B;
     } else {
       __syncwarp();
 #pragma unroll
@@ -499,71 +601,89 @@ __device__ __forceinline__ void snake_segment(const SnakeParams& p, const float*
         if (m < SN_XS) xs[m] = ne[q];
       }
       __syncwarp();
-      if (c + 1 < C && cg + 1 < 8) fetch(c + 1, 0);
+      if (c + 1 < C && cg + 1 < 8) fetch_edge(c + 1);
     }
-    // phase 1: 256 samples of the 2x-rate signal = 64 groups of 4 (two rounds).  Group j holds
-    // v[i0 + 4j .. +3] = (u[2q+1], u[2q+2], u[2q+3], u[2q+4]), q = t0 - 4 + 2j, from xh[q-2 .. q+4] = xs[2j+2 .. 2j+8]
-#pragma unroll
-    for (int rnd = 0; rnd < 2; ++rnd) {
-      const int j = lane + 32 * rnd;
-      const int n0 = 4 * j;
-      float v0, v1, v2, v3;
-      if (FAST || (i0 + n0 >= 0 && i0 + n0 + 3 <= imax)) {
-        float w[8];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const float2 t2 = *reinterpret_cast<const float2*>(xs + 2 * j + 2 + 2 * q);
-          w[2 * q] = t2.x;
-          w[2 * q + 1] = t2.y;
-        }
-        float u0 = 0.f, u1 = 0.f, u2 = 0.f, u3 = 0.f;
-#pragma unroll
-        for (int m = 0; m < 6; ++m) {
-          u0 = fmaf(fu2[10 - 2 * m], w[m], u0);
-          u1 = fmaf(fu2[11 - 2 * m], w[m], u1);
-          u2 = fmaf(fu2[10 - 2 * m], w[m + 1], u2);
-          u3 = fmaf(fu2[11 - 2 * m], w[m + 1], u3);
-        }
-        v0 = snake_eval(u0, a, invb);
-        v1 = snake_eval(u1, a, invb);
-        v2 = snake_eval(u2, a, invb);
-        v3 = snake_eval(u3, a, invb);
-      } else {
-        float vv[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {      // sequence edges: replicate-clamped 2x-rate index, generic taps
-          const int ic = min(max(i0 + n0 + k, 0), imax);
-          const int q = ic >> 1, odd = ic & 1;
-          const int xi = min(max(q - 3 + odd - (t0 - 8), 0), SN_XS - 6);
-          const float* xp = xs + xi;
-          float u = 0.f;
-#pragma unroll
-          for (int m = 0; m < 6; ++m) u = fmaf(odd ? fu2[10 - 2 * m] : fu2[11 - 2 * m], xp[m], u);
-          vv[k] = snake_eval(u, a, invb);
-        }
-        v0 = vv[0]; v1 = vv[1]; v2 = vv[2]; v3 = vv[3];
+    const f32x2 a2 = pk2(a, a), invb2 = pk2(invb, invb);
+    // phase 1: 256 samples of the 2x-rate signal = 64 groups of 4; lane l computes the adjacent groups 2l and 2l+1.
+    // Group j holds v[i0 + 4j .. +3] = (u[2q+1], u[2q+2], u[2q+3], u[2q+4]), q = t0 - 4 + 2j, from
+    // xh[q-2 .. q+4] = xs[2j+2 .. 2j+8]: both groups read xs[4l+2 .. 4l+11] (one 8-byte and two 16-byte loads).
+    {
+      f32x2 wp[5];
+      wp[0] = *reinterpret_cast<const f32x2*>(xs + 4 * lane + 2);
+      {
+        const ulonglong2 t4 = *reinterpret_cast<const ulonglong2*>(xs + 4 * lane + 4);
+        wp[1] = t4.x; wp[2] = t4.y;
+        const ulonglong2 t5 = *reinterpret_cast<const ulonglong2*>(xs + 4 * lane + 8);
+        wp[3] = t5.x; wp[4] = t5.y;
       }
-      *reinterpret_cast<float4*>(vs + n0) = make_float4(v0, v1, v2, v3);
+#pragma unroll
+      for (int gq = 0; gq < 2; ++gq) {
+        const int j = 2 * lane + gq;
+        const int n0 = 4 * j;
+        float v0, v1, v2, v3;
+        if (FAST || (i0 + n0 >= 0 && i0 + n0 + 3 <= imax)) {
+          const f32x2* w2 = wp + gq;
+          f32x2 s0 = mul2(ce_a[0], w2[0]), s1 = mul2(co_a[0], w2[0]);
+          f32x2 s2 = mul2(ce_b[0], w2[0]), s3 = mul2(co_b[0], w2[0]);
+#pragma unroll
+          for (int q = 1; q < 3; ++q) {
+            s0 = fma2(ce_a[q], w2[q], s0);
+            s1 = fma2(co_a[q], w2[q], s1);
+          }
+#pragma unroll
+          for (int q = 1; q < 4; ++q) {
+            s2 = fma2(ce_b[q], w2[q], s2);
+            s3 = fma2(co_b[q], w2[q], s3);
+          }
+          const float u0 = hsum2(s0), u1 = hsum2(s1), u2 = hsum2(s2), u3 = hsum2(s3);
+          if (MODE == 2) {
+            upk2(snake_eval2_fast(pk2(u0, u1), a2, invb2), v0, v1);
+            upk2(snake_eval2_fast(pk2(u2, u3), a2, invb2), v2, v3);
+          } else {
+            v0 = snake_eval(u0, a, invb);
+            v1 = snake_eval(u1, a, invb);
+            v2 = snake_eval(u2, a, invb);
+            v3 = snake_eval(u3, a, invb);
+          }
+        } else {
+          float vv[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {      // sequence edges: replicate-clamped 2x-rate index, generic taps
+            const int ic = min(max(i0 + n0 + k, 0), imax);
+            const int q = ic >> 1, odd = ic & 1;
+            const int xi = min(max(q - 3 + odd - (t0 - 8), 0), SN_XS - 6);
+            const float* xp = xs + xi;
+            float u = 0.f;
+#pragma unroll
+            for (int m = 0; m < 6; ++m) u = fmaf(odd ? fu2[10 - 2 * m] : fu2[11 - 2 * m], xp[m], u);
+            vv[k] = snake_eval(u, a, invb);
+          }
+          v0 = vv[0]; v1 = vv[1]; v2 = vv[2]; v3 = vv[3];
+        }
+        *reinterpret_cast<float4*>(gq ? vs_wB : vs_wA) = make_float4(v0, v1, v2, v3);
+      }
     }
     __syncwarp();
-    // phase 2: y[t0 + tl + k] = sum_j fd[j] vs[2*(tl + k) + j + 2]
+    // phase 2: y[t0 + tl + k] = sum_j fd[j] v[2*(tl + k) + j + 2], v = the logical (unswizzled) 2x-rate window
     if (lane < SN_WS / 4) {
-      float w[24];
+      // v[2 tl .. 2 tl + 23] as twelve aligned pairs (three 32-byte unit pairs); y[k] = sum_q fd2[q] . pair[k + 1 + q]
+      f32x2 w2[12];
 #pragma unroll
-      for (int q = 0; q < 6; ++q) {
-        const float4 t4 = *reinterpret_cast<const float4*>(vs + 2 * tl + 4 * q);
-        w[4 * q] = t4.x; w[4 * q + 1] = t4.y; w[4 * q + 2] = t4.z; w[4 * q + 3] = t4.w;
+      for (int q = 0; q < 3; ++q) {
+        const ulonglong2 ta = *reinterpret_cast<const ulonglong2*>(vs_r[q][0]);
+        const ulonglong2 tb = *reinterpret_cast<const ulonglong2*>(vs_r[q][1]);
+        w2[4 * q] = ta.x; w2[4 * q + 1] = ta.y;
+        w2[4 * q + 2] = tb.x; w2[4 * q + 3] = tb.y;
       }
       float y[4];
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        float acc = 0.f;
+        f32x2 acc = mul2(fd2[0], w2[k + 1]);
 #pragma unroll
-        for (int j = 0; j < 12; ++j) acc = fmaf(fd[j], w[2 * k + j + 2], acc);
-        y[k] = acc;
+        for (int q = 1; q < 6; ++q) acc = fma2(fd2[q], w2[k + 1 + q], acc);
+        y[k] = hsum2(acc);
       }
-      if (p.y != nullptr) {
-        float* yr = p.y + ((int64_t)b * C + c) * T + t0 + tl;
+      if (want_y) {
         if (FAST || (t0 + tl + 3 < T && (T & 3) == 0)) {
           *reinterpret_cast<float4*>(yr) = make_float4(y[0], y[1], y[2], y[3]);
         } else {
@@ -572,11 +692,12 @@ __device__ __forceinline__ void snake_segment(const SnakeParams& p, const float*
             if (t0 + tl + k < T) yr[k] = y[k];
         }
       }
-      if (p.yimg != nullptr) tr[cg * 32 + lane] = make_uint2(cvt_pair<BF16>(y[0], y[1]), cvt_pair<BF16>(y[2], y[3]));
+      if (want_img) tr[cg * 32 + lane] = make_uint2(cvt_pair<BF16>(y[0], y[1]), cvt_pair<BF16>(y[2], y[3]));
     }
+    if (want_y) yr += T;
   }
   // operand image: 8 channels = 16 B per time step; every lane re-reads its own 4 rows x 8 channels
-  if (p.yimg != nullptr && lane < SN_WS / 4) {
+  if (want_img && lane < SN_WS / 4) {
     uint2 h[8];
 #pragma unroll
     for (int cg = 0; cg < 8; ++cg) h[cg] = tr[cg * 32 + lane];
@@ -597,8 +718,8 @@ __device__ __forceinline__ void snake_segment(const SnakeParams& p, const float*
   }
 }
 
-template <int BF16>
-__global__ void __launch_bounds__(NT, 3) activation1d_warp_kernel(SnakeParams p) {
+template <int BF16, int MODE>
+__global__ void __launch_bounds__(NT, AB_SNAKE_BLOCKS) activation1d_warp_kernel(const __grid_constant__ SnakeParams p) {
   __shared__ __align__(16) float win_all[8][SN_XR * SN_XS + SN_VS + SN_TR];
   __shared__ float prm[8][2];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -626,10 +747,24 @@ __global__ void __launch_bounds__(NT, 3) activation1d_warp_kernel(SnakeParams p)
   const float* xb = p.x + (int64_t)b * p.C * T;
   const bool fast = t0 >= 8 && t0 + 128 <= T && (T & 3) == 0 && (reinterpret_cast<uintptr_t>(p.x) & 15) == 0 &&
                     (p.y == nullptr || (reinterpret_cast<uintptr_t>(p.y) & 15) == 0);
-  if (fast) snake_segment<true, BF16>(p, xb, c8, b, t0, prm, xs, vs, tr, lane);
-  else snake_segment<false, BF16>(p, xb, c8, b, t0, prm, xs, vs, tr, lane);
+  if (fast) snake_segment<true, BF16, MODE>(p, xb, c8, b, t0, prm, xs, vs, tr, lane);
+  else snake_segment<false, BF16, MODE>(p, xb, c8, b, t0, prm, xs, vs, tr, lane);
 }
 }  // namespace
+
+void pack_snake_coef(const float* f_up, const float* f_down, SnakeCoef* out) {
+  float fu2[12];
+  for (int j = 0; j < 12; ++j) fu2[j] = 2.0f * f_up[j];       // the x2 gain of UpSample1d (resample.py:43), exact
+  for (int q = 0; q < 3; ++q) {
+    out->ce_a[q] = make_float2(fu2[10 - 4 * q], fu2[8 - 4 * q]);
+    out->co_a[q] = make_float2(fu2[11 - 4 * q], fu2[9 - 4 * q]);
+  }
+  for (int q = 0; q < 4; ++q) {
+    out->ce_b[q] = make_float2(q > 0 ? fu2[12 - 4 * q] : 0.f, q < 3 ? fu2[10 - 4 * q] : 0.f);
+    out->co_b[q] = make_float2(q > 0 ? fu2[13 - 4 * q] : 0.f, q < 3 ? fu2[11 - 4 * q] : 0.f);
+  }
+  for (int q = 0; q < 6; ++q) out->fd2[q] = make_float2(f_down[2 * q], f_down[2 * q + 1]);
+}
 
 int launch_activation1d(const SnakeParams& p, cudaStream_t s) {
   if (p.B <= 0 || p.C <= 0 || p.T <= 0) return fail(AB_ERR_ARG, "activation1d: bad shape");
@@ -638,8 +773,17 @@ int launch_activation1d(const SnakeParams& p, cudaStream_t s) {
   // channel groups: the operand image covers ceil16(C) channels (padding groups are written as zeros)
   const int c8n = p.yimg ? (int)(ceil_div(p.C, 16) * 2) : (int)ceil_div(p.C, 8);
   dim3 grid((unsigned)ceil_div(p.T, WT), (unsigned)c8n, (unsigned)p.B);
-  if (p.bf16) activation1d_warp_kernel<1><<<grid, NT, 0, s>>>(p);
-  else activation1d_warp_kernel<0><<<grid, NT, 0, s>>>(p);
+  const int mode = !p.have_kc ? 0 : (p.fast_snake && p.y == nullptr && p.yimg != nullptr) ? 2 : 1;
+  if (mode == 2) {
+    if (p.bf16) activation1d_warp_kernel<1, 2><<<grid, NT, 0, s>>>(p);
+    else activation1d_warp_kernel<0, 2><<<grid, NT, 0, s>>>(p);
+  } else if (mode == 1) {
+    if (p.bf16) activation1d_warp_kernel<1, 1><<<grid, NT, 0, s>>>(p);
+    else activation1d_warp_kernel<0, 1><<<grid, NT, 0, s>>>(p);
+  } else {
+    if (p.bf16) activation1d_warp_kernel<1, 0><<<grid, NT, 0, s>>>(p);
+    else activation1d_warp_kernel<0, 0><<<grid, NT, 0, s>>>(p);
+  }
   AB_LAUNCH_CHECK("activation1d_warp_kernel");
   return AB_OK;
 }

@@ -120,6 +120,156 @@ __global__ void __launch_bounds__(256) mag_mel_kernel(const float2* __restrict__
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Backward of the log-mel output with respect to the waveform (the mel loss of the vocoder trainers,
+// gan_vocoder_trainer.py:368-396: L1 between extract_mel_features(y_gt) and extract_mel_features(y_pred)).
+//   mel = log(max(acc, clamp)), acc = basis . mag, mag = sqrt(re^2 + im^2 + eps), (re, im) = rfft(frame * window)
+// One CTA = FT frames of one batch item, as in mag_mel_kernel.  It turns the spectrum into the cotangent of the
+// spectrum IN PLACE, already in the form cuFFT's C2R expects (interior bins halved: C2R doubles them).
+__global__ void __launch_bounds__(256) mel_bwd_spec_kernel(float2* __restrict__ spec,          // [B*F][bins], in/out
+                                                           const float* __restrict__ basis,   // [n_mel][bins]
+                                                           const int2* __restrict__ span,
+                                                           const float* __restrict__ gmel,    // [B][n_mel][F]
+                                                           int F, int bins, int n_mel, float eps, float clampv) {
+  extern __shared__ float bw_s[];           // mag [bins][FT+1], then gm [n_mel][FT+1]
+  float* mag_s = bw_s;
+  float* gm_s = bw_s + (size_t)bins * (FT + 1);
+  const int b = blockIdx.y, f0 = blockIdx.x * FT;
+  const int nf = min(FT, F - f0);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int f = warp; f < nf; f += 8) {
+    const float2* row = spec + ((int64_t)b * F + f0 + f) * bins;
+    for (int k = lane; k < bins; k += 32) {
+      const float2 c = row[k];
+      const float sq = __fadd_rn(__fadd_rn(__fmul_rn(c.x, c.x), __fmul_rn(c.y, c.y)), eps);
+      mag_s[k * (FT + 1) + f] = __fsqrt_rn(sq);
+    }
+  }
+  __syncthreads();
+  // d log(max(acc, clamp)) = g / acc where acc >= clamp (torch.clamp passes the gradient at the boundary), else 0
+  for (int m = warp; m < n_mel; m += 8) {
+    const int2 sp = span[m];
+    const float* brow = basis + (int64_t)m * bins;
+    float acc = 0.f;
+    if (lane < nf)
+      for (int k = sp.x; k < sp.y; ++k) acc = fmaf(__ldg(brow + k), mag_s[k * (FT + 1) + lane], acc);
+    float g = 0.f;
+    if (lane < nf && acc >= clampv) g = __ldg(gmel + ((int64_t)b * n_mel + m) * F + f0 + lane) / acc;
+    gm_s[m * (FT + 1) + lane] = g;
+  }
+  __syncthreads();
+  // d mag[k] = sum_m basis[m][k] gm[m]; stored as the ratio d mag / mag in place of mag
+  for (int k = warp; k < bins; k += 8) {
+    float acc = 0.f;
+    for (int m = 0; m < n_mel; ++m) {
+      const int2 sp = span[m];                                   // warp-uniform
+      if (k >= sp.x && k < sp.y) acc = fmaf(__ldg(basis + (int64_t)m * bins + k), gm_s[m * (FT + 1) + lane], acc);
+    }
+    const float mg = mag_s[k * (FT + 1) + lane];
+    mag_s[k * (FT + 1) + lane] = mg > 0.f ? acc / mg : 0.f;      // eps = 0 and a silent bin: torch yields NaN, we 0
+  }
+  __syncthreads();
+  const int nyq = bins - 1;
+  for (int f = warp; f < nf; f += 8) {
+    float2* row = spec + ((int64_t)b * F + f0 + f) * bins;
+    for (int k = lane; k < bins; k += 32) {
+      const float2 c = row[k];
+      const float r = mag_s[k * (FT + 1) + f] * ((k == 0 || k == nyq) ? 1.0f : 0.5f);
+      row[k] = make_float2(c.x * r, c.y * r);
+    }
+  }
+}
+
+// grad_wav[b][i] = sum over the padded positions p that reflect onto i, over the frames f covering p:
+//   window_full[p - f hop] * gframes[b F + f][p - f hop]      (adjoint of frame_window_kernel)
+__global__ void __launch_bounds__(256) mel_bwd_ola_kernel(const float* __restrict__ gframes, const float* __restrict__ window,
+                                                          float* __restrict__ gwav, int T, int F, int n_fft, int hop,
+                                                          int win, int pad) {
+  const int b = blockIdx.y;
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= T) return;
+  const int lpad = (n_fft - win) / 2;
+  const float* gb = gframes + (int64_t)b * F * n_fft;
+  const int plen = T + 2 * pad;
+  auto at = [&](int p) -> float {
+    if (p < 0 || p >= plen) return 0.f;
+    float acc = 0.f;
+    int f_hi = p / hop;
+    if (f_hi > F - 1) f_hi = F - 1;
+    for (int f = f_hi; f >= 0; --f) {
+      const int n = p - f * hop;
+      if (n >= n_fft) break;
+      const int wi = n - lpad;
+      if (wi >= 0 && wi < win) acc = fmaf(__ldg(window + wi), __ldg(gb + (int64_t)f * n_fft + n), acc);
+    }
+    return acc;
+  };
+  float g = at(i + pad);
+  // left reflection: padded p in [0, pad) reads y[pad - p]; right: p in [pad + T, plen) reads y[2 (T - 1) - (p - pad)]
+  if (i >= 1 && i <= pad) g += at(pad - i);
+  if (i <= T - 2 && i >= T - 1 - pad) g += at(pad + 2 * (T - 1) - i);
+  gwav[(int64_t)b * T + i] = g;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// iSTFT head (APNet.forward, models/vocoders/gan/generator/apnet.py:378-399, and ISTFT "same", :46-104):
+//   pha = atan2(I, R); rea = exp(logamp) cos(pha); imag = exp(logamp) sin(pha)
+//   audio = overlap-add(irfft(rea + i imag) * window) / overlap-add(window^2), trimmed by (win - hop) / 2 per side.
+// Inputs are [B][bins][F] (frames fastest, as the convolutions write them); the spectrum for cuFFT is
+// [B*F][bins] complex, so the kernel transposes 32 x 32 tiles through shared memory.
+__global__ void __launch_bounds__(256) spectral_head_kernel(const float* __restrict__ logamp, const float* __restrict__ R,
+                                                            const float* __restrict__ I, float* __restrict__ pha_out,
+                                                            float* __restrict__ rea_out, float* __restrict__ imag_out,
+                                                            float2* __restrict__ spec, int bins, int F) {
+  __shared__ float2 tile[32][33];
+  const int b = blockIdx.z, k0 = blockIdx.y * 32, f0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int r = ty; r < 32; r += 8) {
+    const int k = k0 + r, f = f0 + tx;
+    float2 c = make_float2(0.f, 0.f);
+    if (k < bins && f < F) {
+      const int64_t idx = ((int64_t)b * bins + k) * F + f;
+      const float ph = atan2f(__ldg(I + idx), __ldg(R + idx));
+      const float amp = expf(__ldg(logamp + idx));
+      float sn, cs;
+      sincosf(ph, &sn, &cs);
+      c = make_float2(amp * cs, amp * sn);
+      if (pha_out) pha_out[idx] = ph;
+      if (rea_out) rea_out[idx] = c.x;
+      if (imag_out) imag_out[idx] = c.y;
+    }
+    tile[r][tx] = c;
+  }
+  __syncthreads();
+  if (spec != nullptr)
+    for (int r = ty; r < 32; r += 8) {
+      const int f = f0 + r, k = k0 + tx;
+      if (f < F && k < bins) spec[((int64_t)b * F + f) * bins + k] = tile[tx][r];
+    }
+}
+
+// wav[b][i] = sum_f window[p - f hop] frames[b F + f][p - f hop] / n_fft  /  sum_f window[p - f hop]^2,  p = i + pad
+__global__ void __launch_bounds__(256) istft_ola_kernel(const float* __restrict__ frames, const float* __restrict__ window,
+                                                        float* __restrict__ wav, int F, int n_fft, int hop, int pad,
+                                                        int L, float scale) {
+  const int b = blockIdx.y;
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= L) return;
+  const int p = i + pad;
+  const float* fb = frames + (int64_t)b * F * n_fft;
+  float acc = 0.f, env = 0.f;
+  int f_hi = p / hop;
+  if (f_hi > F - 1) f_hi = F - 1;
+  for (int f = f_hi; f >= 0; --f) {
+    const int n = p - f * hop;
+    if (n >= n_fft) break;
+    const float w = __ldg(window + n);
+    acc = fmaf(w * scale, __ldg(fb + (int64_t)f * n_fft + n), acc);
+    env = fmaf(w, w, env);
+  }
+  wav[(int64_t)b * L + i] = acc / env;
+}
+
 const char* cufft_err(cufftResult r) {
   switch (r) {
     case CUFFT_SUCCESS: return "CUFFT_SUCCESS";
@@ -140,8 +290,10 @@ const char* cufft_err(cufftResult r) {
     if (_r != CUFFT_SUCCESS) return fail(AB_ERR_CUDA, "%s failed: %s", #expr, cufft_err(_r)); \
   } while (0)
 
-int get_plan(ab_mel* m, int64_t batch, cufftHandle* plan, size_t* ws) {
+int get_plan(ab_mel* m, int64_t batch, cufftHandle* plan, size_t* ws, bool inverse = false) {
   constexpr size_t kMaxPlans = 8;
+  const int64_t nbatch = batch;
+  if (inverse) batch = -batch;             // cache key: C2R plans live under the negated batch
   auto touch = [&](int64_t b) {
     auto& l = m->plan_lru;
     l.erase(std::remove(l.begin(), l.end(), b), l.end());
@@ -160,13 +312,13 @@ int get_plan(ab_mel* m, int64_t batch, cufftHandle* plan, size_t* ws) {
     auto ev = m->plans.find(old);
     if (ev != m->plans.end()) { cufftDestroy(ev->second); m->plans.erase(ev); m->plan_ws.erase(old); }
   }
-  if (batch > 0x7fffffffll) return fail(AB_ERR_UNSUPPORTED, "mel: too many frames");
+  if (nbatch > 0x7fffffffll) return fail(AB_ERR_UNSUPPORTED, "mel: too many frames");
   cufftHandle h;
   AB_CUFFT_TRY(cufftCreate(&h));
   AB_CUFFT_TRY(cufftSetAutoAllocation(h, 0));
   size_t sz = 0;
   int n[1] = {m->cfg.n_fft};
-  AB_CUFFT_TRY(cufftMakePlanMany(h, 1, n, nullptr, 1, 0, nullptr, 1, 0, CUFFT_R2C, (int)batch, &sz));
+  AB_CUFFT_TRY(cufftMakePlanMany(h, 1, n, nullptr, 1, 0, nullptr, 1, 0, inverse ? CUFFT_C2R : CUFFT_R2C, (int)nbatch, &sz));
   m->plans[batch] = h;
   m->plan_ws[batch] = sz;
   touch(batch);
@@ -475,6 +627,123 @@ int ab_mel_forward(ab_mel* m, const float* dev_wav, int64_t B, int64_t T, const 
   mag_mel_kernel<<<grid, 256, smem, st>>>(spec, dev_mel_basis, span, dev_mag, dev_mel, dev_energy, (int)L.F,
                                           m->bins, m->cfg.n_mel, m->cfg.eps, m->cfg.clamp);
   AB_LAUNCH_CHECK("mag_mel_kernel");
+  return AB_OK;
+}
+
+size_t ab_mel_backward_workspace_bytes(const ab_mel* m, int64_t B, int64_t T) {
+  if (!m || B <= 0 || T <= 0) return 0;
+  MelLayout L;
+  cufftHandle plan;
+  ab_mel* mm = const_cast<ab_mel*>(m);
+  if (mel_layout(mm, B, T, &L, &plan) != AB_OK) return 0;
+  size_t inv_ws = 0;
+  if (get_plan(mm, B * L.F, &plan, &inv_ws, true) != AB_OK) return 0;
+  return L.total + align_up(inv_ws, 256);
+}
+
+int ab_mel_backward(ab_mel* m, const float* dev_wav, int64_t B, int64_t T, const float* dev_window,
+                    const float* dev_mel_basis, const float* dev_grad_mel, float* dev_grad_wav,
+                    void* ws, size_t ws_bytes, void* stream) {
+  if (!m || !dev_wav || !dev_window || !dev_mel_basis || !dev_grad_mel || !dev_grad_wav || !ws)
+    return fail(AB_ERR_ARG, "mel_backward: null argument");
+  if (m->cfg.n_mel <= 0) return fail(AB_ERR_ARG, "mel_backward: the handle has no mel output");
+  if (B <= 0 || B > 65535 || T <= 0 || T > (1ll << 30)) return fail(AB_ERR_ARG, "mel_backward: bad shape");
+  MelLayout L;
+  cufftHandle plan, iplan;
+  int rc = mel_layout(m, B, T, &L, &plan);
+  if (rc != AB_OK) return rc;
+  size_t inv_ws = 0;
+  rc = get_plan(m, B * L.F, &iplan, &inv_ws, true);
+  if (rc != AB_OK) return rc;
+  const size_t need = L.total + align_up(inv_ws, 256);
+  if (ws_bytes < need) return fail(AB_ERR_WORKSPACE, "mel_backward: workspace %zu B < required %zu B", ws_bytes, need);
+  if (reinterpret_cast<uintptr_t>(ws) & 255) return fail(AB_ERR_ARG, "mel_backward: workspace must be 256-byte aligned");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  char* base = static_cast<char*>(ws);
+  float* frames = reinterpret_cast<float*>(base + L.off_frames);
+  float2* spec = reinterpret_cast<float2*>(base + L.off_spec);
+  int2* span = reinterpret_cast<int2*>(base + L.off_span);
+  const int64_t nfr = B * L.F;
+  // recompute the spectrum (cheaper than keeping B*F*bins complex numbers alive between forward and backward)
+  frame_window_kernel<<<(unsigned)nfr, 256, 0, st>>>(dev_wav, dev_window, frames, (int)T, (int)L.F, m->cfg.n_fft,
+                                                    m->cfg.hop, m->cfg.win, m->cfg.pad);
+  AB_LAUNCH_CHECK("frame_window_kernel");
+  AB_CUFFT_TRY(cufftSetStream(plan, st));
+  AB_CUFFT_TRY(cufftSetWorkArea(plan, base + L.off_fft));
+  AB_CUFFT_TRY(cufftExecR2C(plan, frames, reinterpret_cast<cufftComplex*>(spec)));
+  mel_span_kernel<<<(m->cfg.n_mel + 63) / 64, 64, 0, st>>>(dev_mel_basis, m->cfg.n_mel, m->bins, span);
+  AB_LAUNCH_CHECK("mel_span_kernel");
+  const size_t smem = ((size_t)m->bins + m->cfg.n_mel) * (FT + 1) * sizeof(float);
+  if (smem > 200 * 1024) return fail(AB_ERR_UNSUPPORTED, "mel_backward: n_fft=%d / n_mel=%d too large", m->cfg.n_fft, m->cfg.n_mel);
+  static DeviceOnce configured;
+  if (smem > 48 * 1024 && configured.need())
+    AB_CUDA_TRY(cudaFuncSetAttribute(mel_bwd_spec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  dim3 grid((unsigned)ceil_div(L.F, FT), (unsigned)B);
+  mel_bwd_spec_kernel<<<grid, 256, smem, st>>>(spec, dev_mel_basis, span, dev_grad_mel, (int)L.F, m->bins, m->cfg.n_mel,
+                                               m->cfg.eps, m->cfg.clamp);
+  AB_LAUNCH_CHECK("mel_bwd_spec_kernel");
+  AB_CUFFT_TRY(cufftSetStream(iplan, st));
+  AB_CUFFT_TRY(cufftSetWorkArea(iplan, base + L.total));
+  AB_CUFFT_TRY(cufftExecC2R(iplan, reinterpret_cast<cufftComplex*>(spec), frames));
+  dim3 ogrid((unsigned)ceil_div(T, (int64_t)256), (unsigned)B);
+  mel_bwd_ola_kernel<<<ogrid, 256, 0, st>>>(frames, dev_window, dev_grad_wav, (int)T, (int)L.F, m->cfg.n_fft, m->cfg.hop,
+                                            m->cfg.win, m->cfg.pad);
+  AB_LAUNCH_CHECK("mel_bwd_ola_kernel");
+  return AB_OK;
+}
+
+int ab_spectral_head_forward(const float* dev_logamp, const float* dev_r, const float* dev_i, int64_t B, int64_t bins,
+                             int64_t F, float* dev_pha, float* dev_rea, float* dev_imag, float* dev_spec, void* stream) {
+  if (!dev_logamp || !dev_r || !dev_i) return fail(AB_ERR_ARG, "spectral_head: null argument");
+  if (B <= 0 || B > 65535 || bins <= 0 || F <= 0 || bins > (1 << 20) || F > (1ll << 30)) return fail(AB_ERR_ARG, "spectral_head: bad shape");
+  dim3 grid((unsigned)ceil_div(F, (int64_t)32), (unsigned)ceil_div(bins, (int64_t)32), (unsigned)B);
+  spectral_head_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(dev_logamp, dev_r, dev_i, dev_pha, dev_rea, dev_imag,
+                                                                           reinterpret_cast<float2*>(dev_spec), (int)bins, (int)F);
+  AB_LAUNCH_CHECK("spectral_head_kernel");
+  return AB_OK;
+}
+
+static int istft_layout(ab_mel* m, int64_t B, int64_t F, cufftHandle* plan, size_t* off_fft, size_t* total) {
+  if (m->cfg.win != m->cfg.n_fft) return fail(AB_ERR_UNSUPPORTED, "istft: win_size %d != n_fft %d (apnet.py:83 multiplies the n_fft-long frames by the window)", m->cfg.win, m->cfg.n_fft);
+  if (m->cfg.hop > m->cfg.win || ((m->cfg.win - m->cfg.hop) & 1)) return fail(AB_ERR_UNSUPPORTED, "istft: need hop <= win and win - hop even");
+  size_t fftws = 0;
+  int rc = get_plan(m, B * F, plan, &fftws, true);
+  if (rc != AB_OK) return rc;
+  *off_fft = align_up((size_t)B * F * m->cfg.n_fft * sizeof(float), 256);
+  *total = *off_fft + align_up(fftws, 256);
+  return AB_OK;
+}
+
+size_t ab_istft_workspace_bytes(const ab_mel* m, int64_t B, int64_t F) {
+  if (!m || B <= 0 || F <= 0) return 0;
+  cufftHandle plan;
+  size_t off = 0, total = 0;
+  if (istft_layout(const_cast<ab_mel*>(m), B, F, &plan, &off, &total) != AB_OK) return 0;
+  return total;
+}
+
+int ab_istft_forward(ab_mel* m, float* dev_spec, int64_t B, int64_t F, const float* dev_window, float* dev_wav,
+                     void* ws, size_t ws_bytes, void* stream) {
+  if (!m || !dev_spec || !dev_window || !dev_wav || !ws) return fail(AB_ERR_ARG, "istft: null argument");
+  if (B <= 0 || B > 65535 || F <= 0 || F * (int64_t)m->cfg.hop > (1ll << 30)) return fail(AB_ERR_ARG, "istft: bad shape");
+  cufftHandle plan;
+  size_t off_fft = 0, total = 0;
+  int rc = istft_layout(m, B, F, &plan, &off_fft, &total);
+  if (rc != AB_OK) return rc;
+  if (ws_bytes < total) return fail(AB_ERR_WORKSPACE, "istft: workspace %zu B < required %zu B", ws_bytes, total);
+  if (reinterpret_cast<uintptr_t>(ws) & 255) return fail(AB_ERR_ARG, "istft: workspace must be 256-byte aligned");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  char* base = static_cast<char*>(ws);
+  float* frames = reinterpret_cast<float*>(base);
+  AB_CUFFT_TRY(cufftSetStream(plan, st));
+  AB_CUFFT_TRY(cufftSetWorkArea(plan, base + off_fft));
+  AB_CUFFT_TRY(cufftExecC2R(plan, reinterpret_cast<cufftComplex*>(dev_spec), frames));
+  const int pad = (m->cfg.win - m->cfg.hop) / 2;
+  const int64_t L = (F - 1) * m->cfg.hop + m->cfg.win - 2 * pad;
+  dim3 grid((unsigned)ceil_div(L, (int64_t)256), (unsigned)B);
+  istft_ola_kernel<<<grid, 256, 0, st>>>(frames, dev_window, dev_wav, (int)F, m->cfg.n_fft, m->cfg.hop, pad, (int)L,
+                                         1.0f / (float)m->cfg.n_fft);
+  AB_LAUNCH_CHECK("istft_ola_kernel");
   return AB_OK;
 }
 

@@ -60,27 +60,84 @@ def _warn_range(y):
         print("max value is ", torch.max(y))
 
 
+def _handle_for(n_fft, hop, win, n_mel, pad, eps, clamp, device):
+    # cuFFT plans belong to a device: one handle per (configuration, device)
+    key = (n_fft, hop, win, n_mel, pad, float(eps), float(clamp), str(device))
+    if key not in _handles:
+        h = C.c_void_p()
+        cfg = _capi.MelConfig(n_fft, hop, win, n_mel, pad, eps, clamp)
+        _capi.check(_capi.lib.ab_mel_create(C.byref(cfg), C.byref(h)), "ab_mel_create")
+        _handles[key] = h
+    return _handles[key]
+
+
+def _workspace(device, need):
+    ws = _workspaces.get(str(device))
+    if ws is None or ws.numel() < need + 256:
+        ws = torch.empty(need + 256, dtype=torch.uint8, device=device)
+        _workspaces[str(device)] = ws
+    return (ws.data_ptr() + 255) // 256 * 256
+
+
+class _LogMel(torch.autograd.Function):
+    """log-mel with a native backward (``ab_mel_backward``): what the trainers' mel loss differentiates
+    (gan_vocoder_trainer.py:368-396, ``extract_mel_features(y_pred.squeeze(1), cfg.preprocess)``)."""
+
+    @staticmethod
+    def forward(ctx, y, window, basis, n_fft, hop, win, pad, eps, clamp):
+        y = y.contiguous().float()
+        mel = _stft_mel_forward(y, n_fft, hop, win, window, basis, pad, eps, False, True, False, clamp, False)[1]
+        ctx.save_for_backward(y, window, basis)
+        ctx.geom = (n_fft, hop, win, pad, eps, clamp)
+        return mel
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g):
+        y, window, basis = ctx.saved_tensors
+        n_fft, hop, win, pad, eps, clamp = ctx.geom
+        B, T = y.shape
+        lib = _capi.lib
+        h = _handle_for(n_fft, hop, win, int(basis.shape[0]), pad, eps, clamp, y.device)
+        g = g.contiguous().float()
+        gy = torch.empty_like(y)
+        with torch.cuda.device(y.device):
+            need = lib.ab_mel_backward_workspace_bytes(h, B, T)
+            wbase = _workspace(y.device, need)
+            window = window.to(device=y.device, dtype=torch.float32).contiguous()
+            bt = basis.to(device=y.device, dtype=torch.float32).contiguous()
+            _capi.check(lib.ab_mel_backward(h, _capi.ptr(y), B, T, _capi.ptr(window), _capi.ptr(bt), _capi.ptr(g),
+                                            _capi.ptr(gy), C.c_void_p(wbase), need, _capi.stream_ptr()), "ab_mel_backward")
+        return gy, None, None, None, None, None, None, None, None
+
+
 def native_stft_mel(y, n_fft, hop, win, window, basis, pad, eps, want_mag=False, want_mel=True,
                     want_energy=False, clamp=1e-5, fused=False):
     """y [B, T] CUDA fp32 -> (magnitude [B,bins,F] | None, mel [B,n_mel,F] | None, energy [B,F] | None).
 
     ``fused=True`` asks for the one-kernel front end (own FFT, n_fft = 1024, no magnitude output): the wav is read
     once and only mel / energy are written.  The default is the cuFFT pipeline, whose spectrum is bit-identical to
-    ``torch.stft`` on the same device."""
+    ``torch.stft`` on the same device.  When ``y`` requires grad the log-mel output is differentiable (native
+    backward); magnitude and energy are returned detached."""
     _capi.require_cuda(y, "mel front end")
     if y.dim() != 2:
         raise ValueError("expected audio of shape [B, T]")
+    if torch.is_grad_enabled() and y.requires_grad and want_mel and basis is not None:
+        mel = _LogMel.apply(y, window, basis, n_fft, hop, win, pad, eps, clamp)
+        mag, en = None, None
+        if want_mag or want_energy:
+            mag, _, en = _stft_mel_forward(y.detach(), n_fft, hop, win, window, None, pad, eps, want_mag, False,
+                                           want_energy, clamp, False)
+        return mag, mel, en
+    return _stft_mel_forward(y.detach(), n_fft, hop, win, window, basis, pad, eps, want_mag, want_mel, want_energy,
+                             clamp, fused)
+
+
+def _stft_mel_forward(y, n_fft, hop, win, window, basis, pad, eps, want_mag, want_mel, want_energy, clamp, fused):
     y = y.contiguous().float()
     B, T = y.shape
     n_mel = int(basis.shape[0]) if (want_mel and basis is not None) else 0
-    # cuFFT plans belong to a device: one handle per (configuration, device)
-    key = (n_fft, hop, win, n_mel, pad, float(eps), float(clamp), str(y.device))
-    if key not in _handles:
-        h = C.c_void_p()
-        cfg = _capi.MelConfig(n_fft, hop, win, n_mel, pad, eps, clamp)
-        _capi.check(_capi.lib.ab_mel_create(C.byref(cfg), C.byref(h)), "ab_mel_create")
-        _handles[key] = h
-    h = _handles[key]
+    h = _handle_for(n_fft, hop, win, n_mel, pad, eps, clamp, y.device)
     lib = _capi.lib
     F = lib.ab_mel_num_frames(h, T)
     if F <= 0:
@@ -88,11 +145,7 @@ def native_stft_mel(y, n_fft, hop, win, window, basis, pad, eps, want_mag=False,
     with torch.cuda.device(y.device):
         fused = bool(fused) and n_fft == 1024 and not want_mag and 0 < n_mel <= 128
         need = 4096 if fused else lib.ab_mel_workspace_bytes(h, B, T)
-        ws = _workspaces.get(str(y.device))
-        if ws is None or ws.numel() < need + 256:
-            ws = torch.empty(need + 256, dtype=torch.uint8, device=y.device)
-            _workspaces[str(y.device)] = ws
-        wbase = (ws.data_ptr() + 255) // 256 * 256
+        wbase = _workspace(y.device, need)
         bins = n_fft // 2 + 1
         mag = torch.empty(B, bins, F, device=y.device) if want_mag else None
         mel = torch.empty(B, n_mel, F, device=y.device) if n_mel else None

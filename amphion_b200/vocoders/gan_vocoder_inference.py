@@ -12,14 +12,14 @@ def vocoder_inference(cfg, model, mels, f0s=None, device=None, fast_inference=Fa
     """mels [B, n_mel, T] (any device / strides) -> audios [B, T*hop] on the CPU,
     detached fp32 — the reference's output contract (:38).  ``fast_inference``
     is accepted and ignored, as in the reference."""
-    if getattr(cfg.preprocess, "extract_amplitude_phase", False):
-        raise NotImplementedError("amphion_b200: amplitude/phase generators (APNet) are not on this path yet")
     model.eval()
     with torch.no_grad():
         if device is None:
             device = next(model.parameters()).device
         mels = mels.to(device, non_blocking=True)
-        if f0s is None:
+        if f0s is None and getattr(cfg.preprocess, "extract_amplitude_phase", False):
+            _, _, _, _, output = model.forward(mels)     # amplitude/phase generators (APNet), :27-34
+        elif f0s is None:
             output = model.forward(mels)
         else:  # f0-conditioned generators (NSF-HiFiGAN), :36
             output = model.forward(mels, f0s.to(device, non_blocking=True))

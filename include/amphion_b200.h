@@ -44,8 +44,13 @@ extern "C" {
  * noise-conv result, so every stage computes x = ups(x) + ups(x).  The native path reproduces exactly that: the
  * HiFi-GAN pipeline with the transposed-conv weights and biases doubled at load time (exact, power of two); the
  * tensor list is HiFi-GAN's (m_source.* / noise_convs.* do not influence the samples).  Configurations whose
- * noise conv would come out shorter than the stage (odd product of the later upsample rates, :264-266) are refused. */
-enum ab_generator_kind { AB_GEN_HIFIGAN = 0, AB_GEN_BIGVGAN = 1, AB_GEN_NSFHIFIGAN = 2 };
+ * noise conv would come out shorter than the stage (odd product of the later upsample rates, :264-266) are refused.
+ * AB_GEN_TRUNK: the frame-rate ResNet trunk of the iSTFT-head generators — APNet's amplitude / phase streams
+ * (models/vocoders/gan/generator/apnet.py:283-375): x = conv_pre(mel) [k = trunk_in_kernel]; xs = sum_j ResBlock1_j(x)
+ * / num_kernels; y = conv_post(leaky_relu(xs, 0.01)) [C -> trunk_out_channels, k = trunk_out_kernel], no tanh.
+ * num_upsamples = 0, upsample_initial_channel = the trunk width; tensors "conv_pre", "resblocks.j.convs{1,2}.p",
+ * "conv_post" (the caller maps ASP_input_conv / ASP_ResNet.j / ASP_output_conv ... onto them). */
+enum ab_generator_kind { AB_GEN_HIFIGAN = 0, AB_GEN_BIGVGAN = 1, AB_GEN_NSFHIFIGAN = 2, AB_GEN_TRUNK = 3 };
 enum ab_activation { AB_ACT_LRELU = 0, AB_ACT_SNAKE = 1, AB_ACT_SNAKEBETA = 2 };
 /* arithmetic of the k-tap channel-mixing convolutions */
 enum ab_precision {
@@ -85,6 +90,10 @@ typedef struct ab_generator_config {
   /* HiFiGAN_vits (hifigan.py:376-449, the decoder inside VITS): kind AB_GEN_HIFIGAN plus */
   int32_t gin_channels;                         /* > 0: tensors "cond.weight" [C0, gin, 1], "cond.bias" [C0] (:424-425) */
   int32_t conv_post_no_bias;                    /* 1: conv_post = Conv1d(ch, 1, 7, bias=False) (:421), no "conv_post.bias" */
+  /* AB_GEN_TRUNK only (0 elsewhere) */
+  int32_t trunk_out_channels;                   /* conv_post output channels (n_fft/2+1, or 2*(n_fft/2+1) for R|I) */
+  int32_t trunk_in_kernel;                      /* conv_pre kernel size (odd) */
+  int32_t trunk_out_kernel;                     /* conv_post kernel size (odd) */
 } ab_generator_config;
 
 int ab_generator_create(const ab_generator_config* cfg, ab_generator** out);
@@ -119,7 +128,7 @@ int ab_generator_finalize(ab_generator* g, int32_t precision, void* stream);
 size_t ab_generator_workspace_bytes(const ab_generator* g, int64_t batch, int64_t frames);
 /* mel [B, n_mel, T] fp32 with arbitrary element strides (the reference feeds
  * transposed views: models/vocoders/vocoder_inference.py:349,505)
- * -> wav [B, 1, T*prod(upsample_rates)] fp32 contiguous. */
+ * -> wav [B, 1, T*prod(upsample_rates)] fp32 contiguous ([B, trunk_out_channels, T] for AB_GEN_TRUNK). */
 int ab_generator_forward(ab_generator* g, const float* dev_mel, int64_t batch, int64_t frames,
                          const int64_t mel_strides[3], float* dev_wav, void* dev_workspace,
                          size_t workspace_bytes, void* stream);
@@ -232,6 +241,28 @@ int ab_mel_forward(ab_mel* m, const float* dev_wav, int64_t batch, int64_t sampl
                    const float* dev_window, const float* dev_mel_basis, float* dev_magnitude,
                    float* dev_mel, float* dev_energy, void* dev_workspace, size_t workspace_bytes,
                    void* stream);
+/* Gradient of ab_mel_forward's log-mel output with respect to the waveform (the mel loss of the vocoder trainers,
+ * models/vocoders/gan/gan_vocoder_trainer.py:368-396): grad_mel [B, n_mel, F] in, grad_wav [B, T] out (overwritten).
+ * The spectrum is recomputed from wav, turned into its cotangent in place, taken back with cuFFT C2R and
+ * overlap-added through the window and the reflect padding.  The clamp passes the gradient where the mel value
+ * is >= clamp, as torch.clamp does.  Workspace: ab_mel_backward_workspace_bytes, 256-byte aligned. */
+size_t ab_mel_backward_workspace_bytes(const ab_mel* m, int64_t batch, int64_t samples);
+int ab_mel_backward(ab_mel* m, const float* dev_wav, int64_t batch, int64_t samples,
+                    const float* dev_window, const float* dev_mel_basis, const float* dev_grad_mel,
+                    float* dev_grad_wav, void* dev_workspace, size_t workspace_bytes, void* stream);
+/* iSTFT head of the amplitude/phase generators (APNet.forward, models/vocoders/gan/generator/apnet.py:378-399):
+ * logamp, R, I [B, bins, F] -> pha = atan2(I, R), rea = exp(logamp) cos(pha), imag = exp(logamp) sin(pha)
+ * (each output [B, bins, F], may be NULL) and the complex spectrum [B*F][bins] (interleaved re, im; may be NULL)
+ * laid out for ab_istft_forward. */
+int ab_spectral_head_forward(const float* dev_logamp, const float* dev_r, const float* dev_i, int64_t batch, int64_t bins,
+                             int64_t frames, float* dev_pha, float* dev_rea, float* dev_imag, float* dev_spec, void* stream);
+/* ISTFT.forward with padding="same" (apnet.py:46-104): irfft (norm "backward") of every frame, times the window,
+ * overlap-add, divided by the overlap-added squared window, trimmed by (win - hop)/2 per side.
+ * spec [B*F][n_fft/2+1] complex interleaved (overwritten), window [win], wav [B, F*hop].  The handle supplies
+ * n_fft / hop / win (win == n_fft, as the reference's broadcast requires); 256-byte aligned workspace. */
+size_t ab_istft_workspace_bytes(const ab_mel* m, int64_t batch, int64_t frames);
+int ab_istft_forward(ab_mel* m, float* dev_spec, int64_t batch, int64_t frames, const float* dev_window, float* dev_wav,
+                     void* dev_workspace, size_t workspace_bytes, void* stream);
 /* Same mel / energy outputs from ONE kernel for n_fft = 1024 (the 22.05 / 24 kHz configs): frame, window, an in-kernel
  * 512-point complex FFT of the even/odd-packed frame, real-FFT post-processing, |.|, mel filterbank, log — the wav is
  * the only HBM read and mel / energy the only writes (utils/stft.py:259-278, utils/mel.py:145-169).  fp32 with an own

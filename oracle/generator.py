@@ -384,6 +384,55 @@ def nsfhifigan_forward(params, hp, mel, f0, return_stages=False):
     return (out, stages) if return_stages else out
 
 
+def istft_same(rea, imag, n_fft, hop, win):
+    """ISTFT.forward with padding="same" (apnet.py:46-104), from the definitions: numpy irfft (norm "backward"),
+    periodic hann window, overlap-add by explicit accumulation, divided by the overlap-added squared window,
+    (win - hop) // 2 samples trimmed per side.  rea / imag [B, N, T] -> [B, T * hop] float32."""
+    rea, imag = np.asarray(rea, np.float64), np.asarray(imag, np.float64)
+    B, _, T = rea.shape
+    n = np.arange(win)
+    window = (0.5 - 0.5 * np.cos(2 * np.pi * n / win)).astype(np.float32).astype(np.float64)   # torch.hann_window (periodic)
+    frames = np.fft.irfft(rea + 1j * imag, n_fft, axis=1) * window[None, :, None]               # [B, n_fft, T]
+    size = (T - 1) * hop + win
+    y, env = np.zeros((B, size)), np.zeros(size)
+    for t in range(T):
+        y[:, t * hop: t * hop + win] += frames[:, :, t]
+        env[t * hop: t * hop + win] += window ** 2
+    pad = (win - hop) // 2
+    y, env = y[:, pad: size - pad], env[pad: size - pad]
+    assert (env > 1e-11).all()
+    return (y / env).astype(np.float32)
+
+
+def apnet_forward(params, hp, mel, n_fft, hop, win):
+    """apnet.py:357-399.  ``hp`` = cfg.model.apnet as a dict.  Returns (logamp, pha, rea, imag, audio [B, 1, T*hop])."""
+    x = _t(np.asarray(mel, np.float32)) if not isinstance(mel, torch.Tensor) else mel.float()
+
+    def stream(s):
+        k_in = hp[f"{s}_input_conv_kernel_size"]
+        h = conv1d(x, get_weight(params, f"{s}_input_conv"), _bias(params, f"{s}_input_conv"), padding=get_padding(k_in, 1))
+        acc = None
+        ks, ds = hp[f"{s}_resblock_kernel_sizes"], hp[f"{s}_resblock_dilation_sizes"]
+        for j in range(len(ks)):
+            r = resblock1(params, f"{s}_ResNet.{j}", h, ks[j], ds[j])      # ASPResBlock / PSPResBlock = ResBlock1 (:113-278)
+            acc = r if acc is None else acc + r
+        return F.leaky_relu(acc / len(ks))                                   # default slope 0.01 (:366, :377)
+
+    with torch.no_grad():
+        a = stream("ASP")
+        k = hp["ASP_output_conv_kernel_size"]
+        logamp = conv1d(a, get_weight(params, "ASP_output_conv"), _bias(params, "ASP_output_conv"), padding=get_padding(k, 1))
+        p = stream("PSP")
+        kr, ki = hp["PSP_output_R_conv_kernel_size"], hp["PSP_output_I_conv_kernel_size"]
+        R = conv1d(p, get_weight(params, "PSP_output_R_conv"), _bias(params, "PSP_output_R_conv"), padding=get_padding(kr, 1))
+        I = conv1d(p, get_weight(params, "PSP_output_I_conv"), _bias(params, "PSP_output_I_conv"), padding=get_padding(ki, 1))
+        pha = torch.atan2(I, R)
+        rea = torch.exp(logamp) * torch.cos(pha)
+        imag = torch.exp(logamp) * torch.sin(pha)
+    audio = istft_same(rea.numpy(), imag.numpy(), n_fft, hop, win)
+    return logamp.numpy(), pha.numpy(), rea.numpy(), imag.numpy(), audio[:, None, :]
+
+
 def generator_forward(kind, params, hp, mel, return_stages=False, f0=None):
     if kind == "nsfhifigan":
         return nsfhifigan_forward(params, hp, mel, f0, return_stages)

@@ -118,6 +118,39 @@ def extract_mel_features(y, mel_basis, n_fft, hop, win, eps=1e-9):
     return log_compress(mel)
 
 
+def extract_mel_features_vjp(y, mel_basis, grad_mel, n_fft, hop, win, eps=1e-9, clip=1e-5):
+    """Cotangent of the waveform for a cotangent ``grad_mel`` [B, n_mel, F] of ``extract_mel_features`` — what
+    autograd computes through utils/mel.py:145-169 when the trainers differentiate the mel loss
+    (models/vocoders/gan/gan_vocoder_trainer.py:368-396).  Written from the definitions in float64: explicit
+    cos/sin DFT matrices, ``d sqrt``, ``torch.clamp`` semantics (gradient passes where the value is >= clip),
+    scatter-add through the frame and reflect-pad index maps.  Pinned against the reference's own autograd result
+    in tests/golden/mel_grad.npz (tests/test_oracle.py).  y [B, T] -> [B, T] float64."""
+    y = np.asarray(y, np.float64)
+    B, T = y.shape
+    pad = (n_fft - hop) // 2
+    ridx = np.pad(np.arange(T), (pad, pad), mode="reflect")              # padded position -> sample index
+    nfr = 1 + (T + 2 * pad - n_fft) // hop
+    w = pad_center(hann_periodic(win).astype(np.float32), n_fft).astype(np.float64)
+    idx = np.arange(n_fft)[None, :] + hop * np.arange(nfr)[:, None]       # [F, n_fft] padded positions
+    frames = y[:, ridx[idx]] * w[None, None, :]                           # [B, F, n_fft]
+    k = np.arange(n_fft // 2 + 1)[:, None] * np.arange(n_fft)[None, :]
+    cosm, sinm = np.cos(2 * np.pi * k / n_fft), np.sin(2 * np.pi * k / n_fft)
+    re = frames @ cosm.T                                                  # [B, F, bins]
+    im = -(frames @ sinm.T)
+    mag = np.sqrt(re * re + im * im + eps)
+    basis = np.asarray(mel_basis, np.float64)
+    acc = np.einsum("mk,bfk->bmf", basis, mag)
+    g_acc = np.where(acc >= clip, np.asarray(grad_mel, np.float64) / np.maximum(acc, 1e-300), 0.0)
+    g_mag = np.einsum("mk,bmf->bfk", basis, g_acc)
+    g_re, g_im = g_mag * re / mag, g_mag * im / mag
+    g_frames = (g_re @ cosm - g_im @ sinm) * w[None, None, :]            # [B, F, n_fft]
+    gy = np.zeros((B, T))
+    tgt = ridx[idx]                                                       # [F, n_fft] sample index of every frame tap
+    for b in range(B):
+        np.add.at(gy[b], tgt.reshape(-1), g_frames[b].reshape(-1))
+    return gy
+
+
 # --------------------------------------------------------------------------
 # utils/stft.py TacotronSTFT
 # --------------------------------------------------------------------------

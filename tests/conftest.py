@@ -56,6 +56,14 @@ GOLDEN_NSF = ("nsfhifigan", dict(resblock="1", harmonic_num=8, upsample_rates=[4
                                  resblock_dilation_sizes=[[1, 3, 5]] * 3), 20)
 
 
+# APNet fixture (tests/golden/gen_golden.py:gen_apnet): cfg.model.apnet and cfg.preprocess
+GOLDEN_APNET = (dict(ASP_channel=32, ASP_resblock_kernel_sizes=[3, 7, 11], ASP_resblock_dilation_sizes=[[1, 3, 5]] * 3,
+                     ASP_input_conv_kernel_size=7, ASP_output_conv_kernel_size=7,
+                     PSP_channel=48, PSP_resblock_kernel_sizes=[3, 7], PSP_resblock_dilation_sizes=[[1, 3, 5], [1, 2, 4]],
+                     PSP_input_conv_kernel_size=5, PSP_output_R_conv_kernel_size=7, PSP_output_I_conv_kernel_size=7),
+                dict(n_mel=12, n_fft=64, hop_size=16, win_size=64, extract_amplitude_phase=True, sample_rate=16000))
+
+
 # HiFiGAN_vits fixtures (positional constructor; tests/golden/gen_golden.py:gen_hifigan_vits)
 GOLDEN_VITS = {
     "a": dict(initial_channel=24, resblock="1", resblock_kernel_sizes=[3, 7, 11], resblock_dilation_sizes=[[1, 3, 5]] * 3,

@@ -266,6 +266,63 @@ def gen_mel():
     print("mel", out["extract_mel_features"].shape, out["taco_mel"].shape, out["extract_mel_features2"].shape)
 
 
+def gen_mel_grad():
+    """The trainers' mel loss differentiated by the reference itself (gan_vocoder_trainer.py:368-396:
+    L1(extract_mel_features(y_gt), extract_mel_features(y_pred)) * 45), plus a plain random cotangent."""
+    out = {}
+    g = torch.Generator().manual_seed(17)
+    for tag, cfgp, B, T in (("a", NS(sample_rate=22050, n_fft=1024, n_mel=80, fmin=0, fmax=8000, win_size=1024, hop_size=256), 2, 6144),
+                            ("b", NS(sample_rate=16000, n_fft=512, n_mel=40, fmin=50, fmax=7600, win_size=400, hop_size=160), 3, 2000)):
+        y_gt = (torch.rand(B, T, generator=g) * 2 - 1) * 0.8
+        y_pred = (y_gt + 0.2 * torch.randn(B, T, generator=g)).clamp(-1, 1)
+        y_pred[0, T // 3: T // 3 + 3 * cfgp.n_fft] = 0.0                 # silence: frames below the log clamp (zero gradient)
+        y_pred.requires_grad_(True)
+        rmel.mel_basis.clear(); rmel.hann_window.clear()
+        mel_gt = rmel.extract_mel_features(y_gt, cfgp)
+        mel_pred = rmel.extract_mel_features(y_pred, cfgp)
+        loss = torch.nn.L1Loss(reduction="mean")(mel_gt, mel_pred) * 45
+        (gl,) = torch.autograd.grad(loss, y_pred, retain_graph=True)
+        cot = torch.randn(mel_pred.shape, generator=g)
+        (gc,) = torch.autograd.grad(mel_pred, y_pred, cot)
+        basis = omel.slaney_mel_filterbank(cfgp.sample_rate, cfgp.n_fft, cfgp.n_mel, cfgp.fmin, cfgp.fmax)
+        out.update({f"{tag}_y_gt": y_gt.numpy(), f"{tag}_y_pred": y_pred.detach().numpy(), f"{tag}_loss": loss.detach().numpy(),
+                    f"{tag}_grad_loss": gl.numpy(), f"{tag}_cot": cot.numpy(), f"{tag}_grad_cot": gc.numpy(),
+                    f"{tag}_mel_basis": basis, f"{tag}_geom": np.array([cfgp.n_fft, cfgp.hop_size, cfgp.win_size, cfgp.n_mel])})
+        print("mel_grad", tag, float(loss), float(gl.abs().max()), float(gc.abs().max()))
+    np.savez(os.path.join(HERE, "mel_grad.npz"), **out)
+
+
+HP_APNET = dict(ASP_channel=32, ASP_resblock_kernel_sizes=[3, 7, 11], ASP_resblock_dilation_sizes=[[1, 3, 5]] * 3,
+                ASP_input_conv_kernel_size=7, ASP_output_conv_kernel_size=7,
+                PSP_channel=48, PSP_resblock_kernel_sizes=[3, 7], PSP_resblock_dilation_sizes=[[1, 3, 5], [1, 2, 4]],
+                PSP_input_conv_kernel_size=5, PSP_output_R_conv_kernel_size=7, PSP_output_I_conv_kernel_size=7)
+APNET_PRE = dict(n_mel=12, n_fft=64, hop_size=16, win_size=64, extract_amplitude_phase=True)
+
+
+def gen_apnet():
+    """APNet.forward (apnet.py:357-399) and the inference plumbing that unpacks its fifth output."""
+    from models.vocoders.gan.generator.apnet import APNet
+    import models.vocoders.gan.gan_vocoder_inference as gvi
+    cfg = NS(preprocess=NS(**APNET_PRE), model=NS(generator="apnet", apnet=NS(**HP_APNET)))
+    torch.manual_seed(77)
+    model = APNet(cfg).eval()
+    g = torch.Generator().manual_seed(78)
+    with torch.no_grad():   # the output convolutions are initialised with std 0.01: scale them so the phase is generic
+        for conv, gain in ((model.ASP_output_conv, 3.0), (model.PSP_output_R_conv, 20.0), (model.PSP_output_I_conv, 20.0)):
+            conv.weight_g.mul_(gain)
+            conv.bias.copy_(torch.randn(conv.bias.shape, generator=g) * 0.3)
+    mel = torch.randn(2, APNET_PRE["n_mel"], 23, generator=g)
+    with torch.no_grad():
+        logamp, pha, rea, imag, audio = model(mel)
+    out = {"mel": mel.numpy(), "logamp": logamp.numpy(), "pha": pha.numpy(), "rea": rea.numpy(), "imag": imag.numpy(),
+           "audio": audio.numpy()}
+    out["inference"] = gvi.vocoder_inference(cfg, model, mel, device="cpu").numpy()
+    for k, v in sd_np(model).items():
+        out["sd:" + k] = v
+    np.savez(os.path.join(HERE, "apnet.npz"), **out)
+    print("apnet", audio.shape, float(audio.abs().max()), float(logamp.abs().max()), os.path.getsize(os.path.join(HERE, "apnet.npz")))
+
+
 def gen_plumbing(cfg, model):
     import models.vocoders.gan.gan_vocoder_inference as gvi
     g = torch.Generator().manual_seed(5)
@@ -281,7 +338,8 @@ def gen_plumbing(cfg, model):
 
 
 if __name__ == "__main__":
-    LATER = {"nsfhifigan": gen_nsfhifigan, "save_audio": gen_save_audio, "hifigan_vits": gen_hifigan_vits}
+    LATER = {"nsfhifigan": gen_nsfhifigan, "save_audio": gen_save_audio, "hifigan_vits": gen_hifigan_vits,
+             "mel_grad": gen_mel_grad, "apnet": gen_apnet}
     if sys.argv[1:] and set(sys.argv[1:]) <= set(LATER):   # later additions regenerate alone
         for name in sys.argv[1:]:
             LATER[name]()
@@ -296,3 +354,5 @@ if __name__ == "__main__":
     gen_nsfhifigan()
     gen_save_audio()
     gen_hifigan_vits()
+    gen_mel_grad()
+    gen_apnet()

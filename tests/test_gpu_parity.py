@@ -3,6 +3,7 @@ mirrors of the reference interface) against the CPU oracle and the committed
 reference-generated golden fixtures.  Tolerances are stated per test; the
 north-star bar is 1e-3 max-abs on the generator output, fp32."""
 import ctypes as C
+import os
 
 import numpy as np
 import pytest
@@ -843,3 +844,184 @@ def test_v1_shorter_than_every_halo(T):
         got = model(mel.to(DEV)).cpu().numpy()
         assert got.shape == want.shape
         assert np.abs(got - want).max() <= 1e-3, (mode, np.abs(got - want).max())
+
+
+# ---------------------------------------------------------------------------
+# (f)4: the mel front end under autograd (the trainers' mel loss, gan_vocoder_trainer.py:368-396)
+# ---------------------------------------------------------------------------
+_MEL_GRAD_CFG = {"a": dict(sample_rate=22050, n_fft=1024, n_mel=80, fmin=0, fmax=8000, win_size=1024, hop_size=256),
+                 "b": dict(sample_rate=16000, n_fft=512, n_mel=40, fmin=50, fmax=7600, win_size=400, hop_size=160)}
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_mel_loss_gradient_matches_reference_autograd(tag):
+    """L1(mel(y_gt), mel(y_pred)) * 45 differentiated through the native backward equals what torch autograd gave
+    through the reference's extract_mel_features (tests/golden/mel_grad.npz), and a random cotangent likewise."""
+    from types import SimpleNamespace as NS
+    from amphion_b200 import mel
+    g, _ = load_golden("mel_grad")
+    cfgp = NS(**_MEL_GRAD_CFG[tag])
+    y_gt = torch.from_numpy(g[tag + "_y_gt"]).to(DEV)
+    y_pred = torch.from_numpy(g[tag + "_y_pred"]).to(DEV).requires_grad_(True)
+    mel_gt = mel.extract_mel_features(y_gt, cfgp)
+    mel_pred = mel.extract_mel_features(y_pred, cfgp)
+    assert mel_pred.requires_grad and not mel_gt.requires_grad
+    loss = torch.nn.L1Loss(reduction="mean")(mel_gt, mel_pred) * 45
+    np.testing.assert_allclose(loss.item(), g[tag + "_loss"], rtol=1e-4)
+    (gl,) = torch.autograd.grad(loss, y_pred, retain_graph=True)
+    want = g[tag + "_grad_loss"]
+    # sign(pred - gt) may flip where the two mels agree to the last bits: compare in the aggregate and pointwise loosely
+    err = np.abs(gl.cpu().numpy() - want)
+    assert err.max() <= 2e-2 * np.abs(want).max() and err.mean() <= 1e-4 * np.abs(want).max(), (err.max(), err.mean())
+    (gc,) = torch.autograd.grad(mel_pred, y_pred, torch.from_numpy(g[tag + "_cot"]).to(DEV))
+    want = g[tag + "_grad_cot"]
+    assert np.abs(gc.cpu().numpy() - want).max() <= 5e-4 * np.abs(want).max()
+    silent = slice(y_pred.shape[1] // 3 + cfgp.n_fft, y_pred.shape[1] // 3 + 2 * cfgp.n_fft)
+    assert np.abs(gc[0, silent].cpu().numpy()).max() <= 1e-3 * np.abs(want).max()      # frames below the log clamp
+
+
+def test_mel_gradient_odd_lengths_and_the_1e6_variant_match_the_oracle():
+    """Edge geometry (length not a multiple of the hop, one frame only) and mel_spectrogram_torch's eps = 1e-6."""
+    from types import SimpleNamespace as NS
+    from amphion_b200 import mel
+    from oracle import mel as om
+    cfgp = NS(**_MEL_GRAD_CFG["a"])
+    basis = om.slaney_mel_filterbank(22050, 1024, 80, 0, 8000)
+    rng = np.random.default_rng(5)
+    for T, eps, fn in ((2999, 1e-9, mel.extract_mel_features), (1024 - 256 + 3, 1e-9, mel.extract_mel_features),
+                       (4100, 1e-6, mel.mel_spectrogram_torch)):
+        y = ((rng.random((2, T)) * 2 - 1) * 0.7).astype(np.float32)
+        yt = torch.from_numpy(y).to(DEV).requires_grad_(True)
+        m = fn(yt, cfgp)
+        cot = rng.standard_normal(tuple(m.shape)).astype(np.float32)
+        (gy,) = torch.autograd.grad(m, yt, torch.from_numpy(cot).to(DEV))
+        want = om.extract_mel_features_vjp(y, basis, cot, 1024, 256, 1024, eps=eps)
+        assert gy.shape == yt.shape
+        assert np.abs(gy.cpu().numpy() - want).max() <= 5e-4 * np.abs(want).max(), (T, eps)
+    # no graph, no gradient: the inference path is untouched
+    with torch.no_grad():
+        assert not mel.extract_mel_features(yt, cfgp).requires_grad
+
+
+def test_feature_directory_round_trip(tmp_path):
+    """(f)4 data format: wav -> native mel -> <processed_dir>/<dataset>/mels/<uid>.npy (reference layout, float32
+    [n_mel, T]) -> VocoderDataset -> batched synthesis to <uid>.wav.  The stored mel equals the oracle's, and the
+    files equal those written from the in-memory mels."""
+    import wave
+    from types import SimpleNamespace as NS
+    from amphion_b200 import features
+    from amphion_b200.vocoders import synthesize_to_files
+    from oracle import mel as om
+    kind, hp, g0, sd, model = golden_model("hifigan_rb1")
+    model = model.to(DEV)
+    n_mel = g0["mel"].shape[1]
+    root = str(tmp_path / "processed_data")
+    pre = model.cfg.preprocess
+    pre.sample_rate, pre.n_fft, pre.win_size, pre.fmin, pre.fmax = 16000, 256, 256, 0, 8000
+    pre.processed_dir, pre.train_file, pre.valid_file, pre.mel_dir = root, "train.json", "valid.json", "mels"
+    pre.use_mel, pre.use_frame_pitch, pre.extract_mel = True, False, True
+    hop = pre.hop_size
+    rng = np.random.default_rng(3)
+    utts = [{"Dataset": "toy", "Uid": f"utt{i:02d}"} for i in range(5)]
+    basis = om.slaney_mel_filterbank(16000, 256, n_mel, 0, 8000)
+    mels = []
+    for u, n in zip(utts, (40, 57, 33, 64, 48)):
+        wav = ((rng.random(n * hop) * 2 - 1) * 0.6).astype(np.float32)
+        m = features.extract_utt_mel_features(os.path.join(root, "toy"), model.cfg, u, torch.from_numpy(wav).to(DEV))
+        stored = np.load(os.path.join(root, "toy", "mels", u["Uid"] + ".npy"))
+        assert stored.dtype == np.float32 and stored.shape == (n_mel, n)
+        np.testing.assert_array_equal(stored, m.cpu().numpy())
+        np.testing.assert_allclose(stored, om.extract_mel_features(wav[None], basis, 256, hop, 256)[0], atol=2e-4)
+        mels.append(torch.from_numpy(stored))
+    features.write_metadata(root, "toy", utts, "valid.json")
+    ds = features.VocoderDataset(model.cfg, "toy", is_valid=True)
+    out = features.synthesize_dataset(model.cfg, model, ds, str(tmp_path / "out"), batch_size=2)
+    ref_paths = [str(tmp_path / f"ref{i}.wav") for i in range(len(mels))]
+    synthesize_to_files(model.cfg, model, mels, ref_paths, batch_size=2, bucket=True)
+    for p, q, u in zip(out, ref_paths, utts):
+        assert os.path.basename(p) == u["Uid"] + ".wav"
+        with wave.open(p) as f, wave.open(q) as h:
+            assert f.getframerate() == 16000 and f.getnframes() == h.getnframes()
+            assert f.readframes(f.getnframes()) == h.readframes(h.getnframes())
+
+
+# ---------------------------------------------------------------------------
+# (f)4: iSTFT-head generator (APNet, apnet.py:283-399)
+# ---------------------------------------------------------------------------
+def _apnet_model(hp, pre, sd=None, seed=None):
+    from types import SimpleNamespace as NS
+    from amphion_b200.vocoders import APNet
+    if seed is not None:
+        torch.manual_seed(seed)
+    m = APNet(NS(preprocess=NS(**pre), model=NS(generator="apnet", apnet=NS(**hp))))
+    if sd is not None:
+        m.load_state_dict({k: torch.as_tensor(v) for k, v in sd.items()}, strict=True)
+    return m.eval().to(DEV)
+
+
+def _phase_err(a, b):
+    d = np.abs(a - b)
+    return np.minimum(d, 2 * np.pi - d)
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 5e-5), ("tc_f16", 1e-3)])
+def test_apnet_matches_reference_fixture(precision, tol):
+    from conftest import GOLDEN_APNET
+    from amphion_b200.vocoders import vocoder_inference
+    hp, pre = GOLDEN_APNET
+    g, sd = load_golden("apnet")
+    model = _apnet_model(hp, pre, sd)
+    model.precision = precision
+    logamp, pha, rea, imag, audio = model(torch.from_numpy(g["mel"]).to(DEV))
+    assert audio.shape == (2, 1, 23 * pre["hop_size"]) and audio.is_cuda
+    assert np.abs(logamp.cpu().numpy() - g["logamp"]).max() <= tol * 3
+    amp = np.exp(g["logamp"])
+    assert (np.abs(rea.cpu().numpy() - g["rea"]) / (1 + amp)).max() <= tol * 3
+    assert (np.abs(imag.cpu().numpy() - g["imag"]) / (1 + amp)).max() <= tol * 3
+    # the phase is ill-conditioned where |R + iI| is small: compare it weighted by that modulus (what reaches the audio)
+    if precision == "fp32":
+        assert _phase_err(pha.cpu().numpy(), g["pha"]).max() <= 2e-2
+    assert np.abs(audio.cpu().numpy() - g["audio"]).max() <= tol
+    from types import SimpleNamespace as NS
+    out = vocoder_inference(model.cfg, model, torch.from_numpy(g["mel"]))
+    assert not out.is_cuda and np.abs(out.numpy() - g["inference"]).max() <= tol
+
+
+def test_istft_module_matches_the_oracle():
+    """ISTFT "same" (apnet.py:46-104) on a random complex spectrum, two geometries."""
+    from amphion_b200.vocoders.apnet import ISTFT
+    from oracle import generator as og
+    rng = np.random.default_rng(11)
+    for n_fft, hop, B, T in ((64, 16, 3, 9), (1024, 256, 2, 37), (256, 64, 1, 1)):
+        re = rng.standard_normal((B, n_fft // 2 + 1, T)).astype(np.float32)
+        im = rng.standard_normal((B, n_fft // 2 + 1, T)).astype(np.float32)
+        spec = torch.complex(torch.from_numpy(re), torch.from_numpy(im)).to(DEV)
+        got = ISTFT(n_fft, hop, n_fft)(spec, torch.hann_window(n_fft))
+        want = og.istft_same(re, im, n_fft, hop, n_fft)
+        assert got.shape == want.shape == (B, T * hop)
+        assert np.abs(got.cpu().numpy() - want).max() <= 2e-5 * max(1.0, np.abs(want).max())
+
+
+def test_apnet_recipe_width_matches_the_oracle():
+    """egs/vocoder/gan/apnet/exp_config.json: 512-channel streams, n_fft 1024, hop 256, 80 mels (the wide ResBlocks run
+    on the streaming tensor-core kernel).  Random weights with the output convolutions scaled to a generic phase."""
+    from helpers import sd_numpy
+    from oracle import generator as og
+    hp = dict(ASP_channel=512, ASP_resblock_kernel_sizes=[3, 7, 11], ASP_resblock_dilation_sizes=[[1, 3, 5]] * 3,
+              ASP_input_conv_kernel_size=7, ASP_output_conv_kernel_size=7,
+              PSP_channel=512, PSP_resblock_kernel_sizes=[3, 7, 11], PSP_resblock_dilation_sizes=[[1, 3, 5]] * 3,
+              PSP_input_conv_kernel_size=7, PSP_output_R_conv_kernel_size=7, PSP_output_I_conv_kernel_size=7)
+    pre = dict(n_mel=80, n_fft=1024, hop_size=256, win_size=1024, extract_amplitude_phase=True, sample_rate=22050)
+    model = _apnet_model(hp, pre, seed=5)
+    with torch.no_grad():
+        for conv, gain in ((model.ASP_output_conv, 3.0), (model.PSP_output_R_conv, 20.0), (model.PSP_output_I_conv, 20.0)):
+            conv.weight_g.mul_(gain)
+    mel = torch.randn(2, 80, 40, generator=torch.Generator().manual_seed(6))
+    want = og.apnet_forward(sd_numpy(model), hp, mel.numpy(), 1024, 256, 1024)
+    for precision, tol in (("fp32", 1e-4), ("tc_f16", 1e-3)):
+        model.precision = precision
+        logamp, pha, rea, imag, audio = model(mel.to(DEV))
+        scale = max(1.0, float(np.abs(want[4]).max()))
+        assert np.abs(logamp.cpu().numpy() - want[0]).max() <= 3 * tol, precision
+        assert np.abs(audio.cpu().numpy() - want[4]).max() <= tol * scale, (precision, np.abs(audio.cpu().numpy() - want[4]).max())
+    assert model.last_launches > 0

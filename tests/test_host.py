@@ -286,3 +286,58 @@ def test_native_state_is_not_copied_or_pickled(tmp_path):
     m._arena_key = ("fake",)
     m.invalidate()
     assert m._arena_key is None
+
+
+def test_feature_files_keep_the_reference_layout(tmp_path):
+    """utils/io.py:12-30 + vocoder_dataset.py:20-197: <processed_dir>/<dataset>/mels/<uid>.npy [n_mel, T] float32,
+    metadata json, __getitem__ contract, overrides=False keeps an existing file."""
+    from types import SimpleNamespace as NS
+    from amphion_b200 import features
+    root = str(tmp_path / "processed_data")
+    pre = NS(processed_dir=root, train_file="train.json", valid_file="valid.json", mel_dir="mels", pitch_dir="pitches",
+             n_mel=4, use_mel=True, use_frame_pitch=True)
+    cfg = NS(preprocess=pre)
+    rng = np.random.default_rng(0)
+    utts = [{"Dataset": "toy", "Uid": f"u{i}", "Duration": 1.0} for i in range(3)]
+    mels = [rng.standard_normal((4, t)).astype(np.float32) for t in (5, 9, 7)]
+    for u, m in zip(utts, mels):
+        p = features.save_feature(os.path.join(root, "toy"), "mels", u["Uid"], torch.from_numpy(m))
+        assert p == os.path.join(root, "toy", "mels", u["Uid"] + ".npy")
+        features.save_feature(os.path.join(root, "toy"), "pitches", u["Uid"], np.arange(m.shape[1] + 2, dtype=np.float32))
+    features.save_feature(os.path.join(root, "toy"), "mels", "u0", np.zeros((4, 5), np.float32), overrides=False)
+    features.write_metadata(root, "toy", utts, "valid.json")
+    ds = features.VocoderDataset(cfg, "toy", is_valid=True)
+    assert len(ds) == 3 and ds.get_dataset_name() == "toy"
+    for i, m in enumerate(mels):
+        item = ds[i]
+        np.testing.assert_array_equal(item["mel"], m)                      # u0 was not overwritten
+        assert item["mel"].dtype == np.float32 and item["target_len"] == m.shape[1]
+        np.testing.assert_array_equal(item["frame_pitch"], np.arange(m.shape[1], dtype=np.float32))
+    np.testing.assert_array_equal(features.align_length(np.ones(3, np.float32), 5), [1, 1, 1, 0, 0])
+    assert features.align_length(np.ones((2, 6)), 4).shape == (2, 4)
+
+
+def test_apnet_state_dict_matches_the_reference_layout():
+    """Keys, order and shapes of APNet's state dict equal the reference module's (fixture made from
+    models/vocoders/gan/generator/apnet.py), so its checkpoints load unchanged."""
+    from types import SimpleNamespace as NS
+    from conftest import GOLDEN_APNET
+    from amphion_b200.vocoders import APNet, _vocoders
+    hp, pre = GOLDEN_APNET
+    g, sd = load_golden("apnet")
+    model = APNet(NS(preprocess=NS(**pre), model=NS(generator="apnet", apnet=NS(**hp))))
+    assert _vocoders["apnet"] is APNet
+    own = model.state_dict()
+    assert list(own.keys()) == list(sd.keys())
+    for k, v in sd.items():
+        assert tuple(own[k].shape) == tuple(v.shape), k
+    model.load_state_dict({k: torch.as_tensor(v) for k, v in sd.items()}, strict=True)
+    # the trunks see effective weights under the native names; R and I filters stacked
+    t = model._trunk_tensors("PSP")
+    assert t["conv_post.weight"].shape == (2 * 33, hp["PSP_channel"], 7) and t["conv_pre.weight"].shape == (48, 12, 5)
+    w = torch.as_tensor(sd["PSP_output_I_conv.weight_v"])
+    gg = torch.as_tensor(sd["PSP_output_I_conv.weight_g"])
+    want = w * (gg / w.flatten(1).norm(dim=1).view(-1, 1, 1))
+    torch.testing.assert_close(t["conv_post.weight"][33:], want)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        model(torch.zeros(1, 12, 8))

@@ -3,7 +3,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import GOLDEN_MODELS, GOLDEN_NSF, GOLDEN_VITS, load_golden, load_golden_vits
+from conftest import GOLDEN_APNET, GOLDEN_MODELS, GOLDEN_NSF, GOLDEN_VITS, load_golden, load_golden_vits
 from oracle import generator as og
 from oracle import io as oio
 from oracle import mel as om
@@ -107,6 +107,28 @@ def test_mel_oracle_matches_reference():
     np.testing.assert_allclose(m2, g["extract_mel_features2"], atol=1e-4)
 
 
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_mel_vjp_oracle_matches_reference_autograd(tag):
+    """oracle.mel.extract_mel_features_vjp against what torch autograd computed through the reference's
+    extract_mel_features (fixture made by tests/golden/gen_golden.py mel_grad)."""
+    g, _ = load_golden("mel_grad")
+    n_fft, hop, win, n_mel = (int(v) for v in g[tag + "_geom"])
+    y, mb = g[tag + "_y_pred"], g[tag + "_mel_basis"]
+    got = om.extract_mel_features_vjp(y, mb, g[tag + "_cot"], n_fft, hop, win)
+    want = g[tag + "_grad_cot"]
+    assert np.abs(got - want).max() <= 2e-4 * np.abs(want).max()
+    # the trainers' loss: 45 * mean |mel_gt - mel_pred|  ->  cotangent 45 * sign(pred - gt) / numel
+    mel_gt = om.extract_mel_features(g[tag + "_y_gt"], mb, n_fft, hop, win)
+    mel_pred = om.extract_mel_features(y, mb, n_fft, hop, win)
+    np.testing.assert_allclose(45 * np.abs(mel_gt - mel_pred).mean(), g[tag + "_loss"], rtol=1e-4)
+    cot = 45.0 * np.sign(mel_pred - mel_gt) / mel_pred.size
+    got = om.extract_mel_features_vjp(y, mb, cot, n_fft, hop, win)
+    want = g[tag + "_grad_loss"]
+    assert np.abs(got - want).max() <= 5e-4 * np.abs(want).max()
+    silent = slice(y.shape[1] // 3 + n_fft, y.shape[1] // 3 + 2 * n_fft)   # frames wholly inside the zeroed span
+    assert np.abs(want[0, silent]).max() < 1e-3 * np.abs(want).max()
+
+
 def test_tacotron_oracle_matches_reference():
     g, _ = load_golden("mel")
     np.testing.assert_array_equal(g["taco_mel_basis"], g["mel_basis"])
@@ -144,3 +166,19 @@ def test_hifigan_vits_oracle_matches_reference(tag):
     np.testing.assert_allclose(og.hifigan_vits_forward(sd, hp, g["x"]), g["wav"], atol=1e-6, rtol=0)
     if "g" in g:
         np.testing.assert_allclose(og.hifigan_vits_forward(sd, hp, g["x"], g["g"]), g["wav_g"], atol=1e-6, rtol=0)
+
+
+def test_apnet_oracle_matches_reference():
+    """oracle.generator.apnet_forward / istft_same against APNet.forward of the reference (apnet.py:357-399)."""
+    from oracle import generator as og
+    hp, pre = GOLDEN_APNET
+    g, sd = load_golden("apnet")
+    logamp, pha, rea, imag, audio = og.apnet_forward(sd, hp, g["mel"], pre["n_fft"], pre["hop_size"], pre["win_size"])
+    np.testing.assert_allclose(logamp, g["logamp"], atol=2e-5)
+    np.testing.assert_allclose(rea, g["rea"], atol=2e-4, rtol=1e-4)
+    np.testing.assert_allclose(imag, g["imag"], atol=2e-4, rtol=1e-4)
+    d = np.abs(pha - g["pha"])
+    assert np.minimum(d, 2 * np.pi - d).max() < 1e-3                     # the branch cut at +-pi
+    assert audio.shape == g["audio"].shape == (2, 1, 23 * pre["hop_size"])
+    np.testing.assert_allclose(audio, g["audio"], atol=2e-5)
+    np.testing.assert_allclose(audio[:, 0], g["inference"], atol=2e-5)     # vocoder_inference takes the fifth output
