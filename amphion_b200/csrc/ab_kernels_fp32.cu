@@ -406,7 +406,7 @@ int launch_conv_transpose1d_fp32(const ConvTParams& p, cudaStream_t s) {
 // ===========================================================================
 namespace {
 #ifndef AB_SNAKE_BLOCKS
-#define AB_SNAKE_BLOCKS 3      // CTAs per SM the activation kernel is compiled for (register budget)
+#define AB_SNAKE_BLOCKS 4      // CTAs per SM the activation kernel is compiled for (64 registers: measured best of 2..5)
 #endif
 constexpr int SN_WS = 120;                 // outputs per warp segment (30 lanes x 4)
 constexpr int SN_XS = 136;                 // xs[m] = xh[t0 - 8 + m]            (34 float4)

@@ -283,7 +283,8 @@ def measure_generator(workload, args, dev, rank, world, steps, warmup, want_cpu,
     import torch
     import torch.distributed as dist
     from amphion_b200.dist import sharded_vocoder_inference, _sharded_forward
-    from amphion_b200.vocoders import _vocoders, vocoder_inference
+    from amphion_b200.vocoders import _vocoders
+    from amphion_b200.vocoders.gan_vocoder_inference import vocoder_inference
 
     w = WORKLOADS[workload]
     cfg = make_cfg(workload)

@@ -341,3 +341,15 @@ def test_apnet_state_dict_matches_the_reference_layout():
     torch.testing.assert_close(t["conv_post.weight"][33:], want)
     with pytest.raises(RuntimeError, match="CUDA"):
         model(torch.zeros(1, 12, 8))
+
+
+def test_vocoder_inference_names_follow_the_reference_layout():
+    """models/vocoders/vocoder_inference.py is a module (synthesis, load_nnvocoder); the function vocoder_inference
+    lives in gan/gan_vocoder_inference.py.  The package attribute is the module whatever was imported first."""
+    import types
+    import amphion_b200.vocoders as v
+    from amphion_b200.vocoders import load_nnvocoder, synthesis
+    from amphion_b200.vocoders.gan_vocoder_inference import vocoder_inference
+    assert isinstance(v.vocoder_inference, types.ModuleType) and v.vocoder_inference.synthesis is synthesis
+    assert callable(vocoder_inference) and callable(load_nnvocoder)
+    assert v._vocoder_forward_funcs["hifigan"] is vocoder_inference
