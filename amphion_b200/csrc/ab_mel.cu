@@ -220,7 +220,7 @@ __global__ void __launch_bounds__(256) mel_bwd_ola_kernel(const float* __restric
 __global__ void __launch_bounds__(256) spectral_head_kernel(const float* __restrict__ logamp, const float* __restrict__ R,
                                                             const float* __restrict__ I, float* __restrict__ pha_out,
                                                             float* __restrict__ rea_out, float* __restrict__ imag_out,
-                                                            float2* __restrict__ spec, int bins, int F) {
+                                                            float2* __restrict__ spec, int bins, int F, float amp_max) {
   __shared__ float2 tile[32][33];
   const int b = blockIdx.z, k0 = blockIdx.y * 32, f0 = blockIdx.x * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -229,8 +229,10 @@ __global__ void __launch_bounds__(256) spectral_head_kernel(const float* __restr
     float2 c = make_float2(0.f, 0.f);
     if (k < bins && f < F) {
       const int64_t idx = ((int64_t)b * bins + k) * F + f;
-      const float ph = atan2f(__ldg(I + idx), __ldg(R + idx));
-      const float amp = expf(__ldg(logamp + idx));
+      // I == null: R already holds the phase (Vocos' ISTFTHead, vocos.py:333-361: S = clip(exp(mag), max) e^{ip})
+      const float ph = I != nullptr ? atan2f(__ldg(I + idx), __ldg(R + idx)) : __ldg(R + idx);
+      float amp = expf(__ldg(logamp + idx));
+      if (amp_max > 0.f) amp = fminf(amp, amp_max);
       float sn, cs;
       sincosf(ph, &sn, &cs);
       c = make_float2(amp * cs, amp * sn);
@@ -693,12 +695,13 @@ int ab_mel_backward(ab_mel* m, const float* dev_wav, int64_t B, int64_t T, const
 }
 
 int ab_spectral_head_forward(const float* dev_logamp, const float* dev_r, const float* dev_i, int64_t B, int64_t bins,
-                             int64_t F, float* dev_pha, float* dev_rea, float* dev_imag, float* dev_spec, void* stream) {
-  if (!dev_logamp || !dev_r || !dev_i) return fail(AB_ERR_ARG, "spectral_head: null argument");
+                             int64_t F, float amp_max, float* dev_pha, float* dev_rea, float* dev_imag, float* dev_spec,
+                             void* stream) {
+  if (!dev_logamp || !dev_r) return fail(AB_ERR_ARG, "spectral_head: null argument");
   if (B <= 0 || B > 65535 || bins <= 0 || F <= 0 || bins > (1 << 20) || F > (1ll << 30)) return fail(AB_ERR_ARG, "spectral_head: bad shape");
   dim3 grid((unsigned)ceil_div(F, (int64_t)32), (unsigned)ceil_div(bins, (int64_t)32), (unsigned)B);
   spectral_head_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(dev_logamp, dev_r, dev_i, dev_pha, dev_rea, dev_imag,
-                                                                           reinterpret_cast<float2*>(dev_spec), (int)bins, (int)F);
+                                                                           reinterpret_cast<float2*>(dev_spec), (int)bins, (int)F, amp_max);
   AB_LAUNCH_CHECK("spectral_head_kernel");
   return AB_OK;
 }

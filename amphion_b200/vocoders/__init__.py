@@ -1,6 +1,6 @@
 """Native GAN vocoders behind the reference's registry/dispatch surface
 (models/vocoders/vocoder_inference.py:39-75)."""
-from .apnet import APNet
+from .apnet import APNet, ISTFT, ISTFTHead
 from .bigvgan import BigVGAN
 from .hifigan import HiFiGAN, HiFiGAN_vits
 from .nsfhifigan import NSFHiFiGAN
@@ -12,7 +12,7 @@ _vocoders = {"hifigan": HiFiGAN, "bigvgan": BigVGAN, "nsfhifigan": NSFHiFiGAN, "
 _vocoder_forward_funcs = {k: _gan_vocoder_inference for k in _vocoders}
 _vocoder_infer_funcs = {k: synthesis_audios for k in _vocoders}
 
-__all__ = ["HiFiGAN", "HiFiGAN_vits", "BigVGAN", "NSFHiFiGAN", "APNet", "synthesis_audios", "synthesize_to_files", "_vocoders",
+__all__ = ["HiFiGAN", "HiFiGAN_vits", "BigVGAN", "NSFHiFiGAN", "APNet", "ISTFT", "ISTFTHead", "synthesis_audios", "synthesize_to_files", "_vocoders",
            "_vocoder_forward_funcs", "_vocoder_infer_funcs"]
 
 # `amphion_b200.vocoders.vocoder_inference` is the MODULE (synthesis, load_nnvocoder), as

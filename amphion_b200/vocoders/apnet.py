@@ -231,7 +231,7 @@ class APNet(nn.Module):
             else:   # R and I of one utterance are adjacent, not the batch: split once (a view would need a row stride)
                 r, i = ri[:, :bins].contiguous(), ri[:, bins:].contiguous()
                 r_ptr, i_ptr = _capi.ptr(r), _capi.ptr(i)
-            _capi.check(_capi.lib.ab_spectral_head_forward(_capi.ptr(logamp), r_ptr, i_ptr, B, bins, T, _capi.ptr(pha),
+            _capi.check(_capi.lib.ab_spectral_head_forward(_capi.ptr(logamp), r_ptr, i_ptr, B, bins, T, 0.0, _capi.ptr(pha),
                                                            _capi.ptr(rea), _capi.ptr(imag), _capi.ptr(spec), _capi.stream_ptr()),
                         "ab_spectral_head_forward")
         key = (int(self.cfg.preprocess.win_size), str(mel.device))
@@ -254,3 +254,32 @@ class APNet(nn.Module):
     def __setstate__(self, state):
         self.__dict__.update(state)
         self._trunks = {"ASP": _Trunk(self, "ASP"), "PSP": _Trunk(self, "PSP")}
+
+
+class ISTFTHead(nn.Module):
+    """Vocos' iSTFT head (models/codec/kmeans/vocos.py:313-361): ``out = Linear(dim, n_fft + 2)``; the first half of
+    the outputs is the log-magnitude (exp, clipped at 1e2), the second half the phase; S = mag (cos p + i sin p);
+    ISTFT with "same" padding.  x [B, L, H] -> audio [B, L * hop].  The linear layer is a library GEMM; magnitude /
+    phase -> spectrum and the inverse STFT are the native kernels APNet uses."""
+
+    def __init__(self, dim: int, n_fft: int, hop_length: int, padding: str = "same"):
+        super().__init__()
+        self.out = nn.Linear(dim, n_fft + 2)
+        self.istft = ISTFT(n_fft=n_fft, hop_length=hop_length, win_length=n_fft, padding=padding)
+        self.register_buffer("window", torch.hann_window(n_fft), persistent=False)
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        _capi.require_cuda(x, "ISTFTHead.forward")
+        y = self.out(x).transpose(1, 2).contiguous().float()        # [B, n_fft + 2, L]
+        B, two_bins, L = y.shape
+        bins = two_bins // 2
+        spec = torch.empty(B * L, bins, 2, dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            if B == 1:
+                m_ptr, p_ptr = _capi.ptr(y), C.c_void_p(y.data_ptr() + bins * L * 4)
+            else:
+                mag, pha = y[:, :bins].contiguous(), y[:, bins:].contiguous()
+                m_ptr, p_ptr = _capi.ptr(mag), _capi.ptr(pha)
+            _capi.check(_capi.lib.ab_spectral_head_forward(m_ptr, p_ptr, None, B, bins, L, 1e2, None, None, None,
+                                                           _capi.ptr(spec), _capi.stream_ptr()), "ab_spectral_head_forward")
+        return self.istft.forward_interleaved(spec, B, L, self.window)

@@ -253,9 +253,11 @@ int ab_mel_backward(ab_mel* m, const float* dev_wav, int64_t batch, int64_t samp
 /* iSTFT head of the amplitude/phase generators (APNet.forward, models/vocoders/gan/generator/apnet.py:378-399):
  * logamp, R, I [B, bins, F] -> pha = atan2(I, R), rea = exp(logamp) cos(pha), imag = exp(logamp) sin(pha)
  * (each output [B, bins, F], may be NULL) and the complex spectrum [B*F][bins] (interleaved re, im; may be NULL)
- * laid out for ab_istft_forward. */
+ * laid out for ab_istft_forward.  dev_i == NULL: dev_r already is the phase, and amp_max > 0 clips exp(logamp) —
+ * Vocos' ISTFTHead (models/codec/kmeans/vocos.py:333-361: S = clip(exp(mag), max=1e2) (cos p + i sin p)). */
 int ab_spectral_head_forward(const float* dev_logamp, const float* dev_r, const float* dev_i, int64_t batch, int64_t bins,
-                             int64_t frames, float* dev_pha, float* dev_rea, float* dev_imag, float* dev_spec, void* stream);
+                             int64_t frames, float amp_max, float* dev_pha, float* dev_rea, float* dev_imag, float* dev_spec,
+                             void* stream);
 /* ISTFT.forward with padding="same" (apnet.py:46-104): irfft (norm "backward") of every frame, times the window,
  * overlap-add, divided by the overlap-added squared window, trimmed by (win - hop)/2 per side.
  * spec [B*F][n_fft/2+1] complex interleaved (overwritten), window [win], wav [B, F*hop].  The handle supplies

@@ -1034,3 +1034,22 @@ def test_apnet_recipe_width_matches_the_oracle():
         assert e_log <= 3 * tol, (precision, e_log)
         assert e_aud <= tol * scale, (precision, e_aud)
     assert model.last_launches > 0
+
+
+def test_vocos_istft_head_matches_the_oracle():
+    """ISTFTHead.forward (models/codec/kmeans/vocos.py:333-361) on the codec's geometry (n_fft 800, hop 200: a
+    non-power-of-two FFT) with the magnitude clip exercised."""
+    from amphion_b200.vocoders import ISTFTHead
+    from oracle import generator as og
+    torch.manual_seed(3)
+    head = ISTFTHead(dim=48, n_fft=800, hop_length=200).to(DEV)
+    with torch.no_grad():
+        head.out.weight.mul_(8.0)                                   # some log-magnitudes beyond log(1e2)
+    x = torch.randn(2, 21, 48, generator=torch.Generator().manual_seed(4))
+    got = head(x.to(DEV))
+    y = (x.double() @ head.out.weight.detach().cpu().double().T + head.out.bias.detach().cpu().double()).transpose(1, 2).numpy()
+    mag = np.minimum(np.exp(y[:, :401]), 1e2)
+    assert (mag == 1e2).any() and (mag < 1e2).any()
+    want = og.istft_same(mag * np.cos(y[:, 401:]), mag * np.sin(y[:, 401:]), 800, 200, 800)
+    assert got.shape == want.shape == (2, 21 * 200)
+    assert np.abs(got.cpu().numpy() - want).max() <= 1e-3 * max(1.0, np.abs(want).max())   # TF32-free fp32 GEMM + fp32 FFT
