@@ -48,6 +48,7 @@ struct GcGeom {
   int Tout;        // output length
   int pad;         // convT: (k-u)/2
   int grouped;     // convT: 8-channel-group epilogue (u in {2,4,8}, cc % 8 == 0)
+  int ctas;        // CTAs per SM this geometry was sized for (1 or 2): TMEM columns = 512 / ctas, shared memory likewise
   uint32_t idesc;
 };
 
@@ -105,7 +106,10 @@ __device__ __forceinline__ void convT_group_store(const P& p, const G& g, uint32
   }
 }
 
-__global__ void __launch_bounds__(GC_THREADS, 1) gemmconv_kernel(GcParams p, GcGeom g) {
+// MINB = 2: two co-resident CTAs per SM (half the TMEM columns and shared memory each), so that one CTA's operand load
+// and store phases run under the other's MMAs — the phases of ONE CTA are serial.
+template <int MINB>
+__global__ void __launch_bounds__(GC_THREADS, MINB) gemmconv_kernel(GcParams p, GcGeom g) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.x / g.tiles, tile = blockIdx.x - b * g.tiles;
@@ -139,7 +143,7 @@ __global__ void __launch_bounds__(GC_THREADS, 1) gemmconv_kernel(GcParams p, GcG
   }
   if (warp == GC_WORKER_WARPS + 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                 "r"(512u)
+                 "r"(512u / MINB)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -321,7 +325,7 @@ __global__ void __launch_bounds__(GC_THREADS, 1) gemmconv_kernel(GcParams p, GcG
   __syncthreads();
   if (warp == GC_WORKER_WARPS + 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u / MINB) : "memory");
   }
 }
 
@@ -408,16 +412,19 @@ int gc_layer_geom(int mode, int cin, int cout, int k, int d_or_u, GcGeom& g) {
   return AB_OK;
 }
 
-int gc_full_geom(const GcParams& p, GcGeom& g) {
+int gc_full_geom(const GcParams& p, GcGeom& g, int ctas = 1) {
   int rc = gc_layer_geom(p.mode, p.Cin, p.Cout, p.k, p.mode ? p.u : p.d, g);
   if (rc != AB_OK) return rc;
-  g.nbuf = g.NB > 1 ? 2 : 1;
+  g.ctas = ctas;
+  const int tmem_cols = 512 / ctas;
+  const uint32_t smem_limit = ctas == 1 ? GC_SMEM_LIMIT : (GC_SMEM_LIMIT - 2048u) / 2u;
+  g.nbuf = (g.NB > 1 && 2 * g.Nb <= tmem_cols) ? 2 : 1;
   const int maxshift = p.mode ? (g.ntaps - 1) : (p.k - 1) * p.d;
   g.row0_time = p.mode ? (g.ntaps - 1) : maxshift / 2;
   if (!p.mode && (maxshift & 1)) return fail(AB_ERR_UNSUPPORTED, "gemmconv: (k-1)*dilation must be even");
   const int rows_total = p.mode ? p.Tin + 1 : p.Tin;
   g.Tout = p.mode ? p.Tin * p.u : p.Tin;
-  int m = 512 / (g.nbuf * g.Nb);
+  int m = tmem_cols / (g.nbuf * g.Nb);
   if (m < 1) return fail(AB_ERR_UNSUPPORTED, "gemmconv: N block %d too wide", g.Nb);
   if (m > 16) m = 16;
   while (m > 1 && (m - 1) * 128 >= rows_total) --m;
@@ -427,9 +434,9 @@ int gc_full_geom(const GcParams& p, GcGeom& g) {
     if (m < 1) return fail(AB_ERR_UNSUPPORTED, "gemmconv: Cin=%d does not fit shared memory", p.Cin);
     g.rowsA = rup(m * 128 + maxshift, 8);
     const uint32_t abytes = (uint32_t)g.rowsA * (uint32_t)g.Kp * 2u;
-    if (abytes + 2u * g.stage_bytes + misc + 1280u > GC_SMEM_LIMIT) continue;
+    if (abytes + 2u * g.stage_bytes + misc + 1280u > smem_limit) continue;
     g.m = m;
-    int ns = (int)((GC_SMEM_LIMIT - abytes - misc - 1280u) / g.stage_bytes);
+    int ns = (int)((smem_limit - abytes - misc - 1280u) / g.stage_bytes);
     g.nstages = std::min(ns, GC_MAX_STAGES);
     g.off_w = (abytes + 1023u) & ~1023u;
     g.off_bias = g.off_w + (uint32_t)g.nstages * g.stage_bytes;
@@ -851,19 +858,35 @@ int launch_gemmconv(const GcParams& p, cudaStream_t s) {
   if (p.ximg && (p.Cin % 16) != 0) return fail(AB_ERR_UNSUPPORTED, "gemmconv: operand-image input needs C_in %% 16 == 0");
   if (p.B <= 0 || p.Tin <= 0) return fail(AB_ERR_ARG, "gemmconv: bad shape");
   if (p.precision != AB_PREC_TC_F16 && p.precision != AB_PREC_TC_BF16) return fail(AB_ERR_ARG, "gemmconv: bad precision");
+  // AB_GC_CTAS (debug / A-B knob): 1 = one CTA per SM with the whole TMEM (round-1 layout), 2 = two half-size CTAs
+  // where the layer fits (default)
+  static const int want_ctas = [] { const char* e = getenv("AB_GC_CTAS"); return e ? atoi(e) : 2; }();
   GcGeom g;
-  int rc = gc_full_geom(p, g);
+  int rc = AB_ERR_UNSUPPORTED;
+  if (want_ctas >= 2) {
+    rc = gc_full_geom(p, g, 2);
+    // enough tiles to fill both slots of every SM, and rows per tile not cut below one M tile's worth of work
+    if (rc == AB_OK && (int64_t)p.B * g.tiles < 2 * 148) rc = AB_ERR_UNSUPPORTED;
+  }
+  if (rc != AB_OK) rc = gc_full_geom(p, g, 1);
   if (rc != AB_OK) return rc;
   if (p.yimg != nullptr && !(p.mode == 1 && g.grouped && (p.Cout % 16) == 0))
     return fail(AB_ERR_UNSUPPORTED, "gemmconv: cannot emit an operand image for this layer");
   static DeviceOnce configured;
   if (configured.need()) {
-    AB_CUDA_TRY(cudaFuncSetAttribute(gemmconv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GC_SMEM_LIMIT));
+    AB_CUDA_TRY(cudaFuncSetAttribute(gemmconv_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GC_SMEM_LIMIT));
+    AB_CUDA_TRY(cudaFuncSetAttribute(gemmconv_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GC_SMEM_LIMIT / 2));
   }
   const int64_t grid = (int64_t)p.B * g.tiles;
   if (grid > 0x7fffffffll) return fail(AB_ERR_UNSUPPORTED, "gemmconv: grid too large");
-  const uint32_t smem = std::max<uint32_t>(g.smem_bytes, 120u * 1024u);
-  gemmconv_kernel<<<(unsigned)grid, GC_THREADS, smem, s>>>(p, g);
+  if (g.ctas == 2) {
+    // at least 76 KB: never more than two CTAs per SM (each allocates 256 TMEM columns)
+    const uint32_t smem = std::max<uint32_t>(g.smem_bytes, 76u * 1024u);
+    gemmconv_kernel<2><<<(unsigned)grid, GC_THREADS, smem, s>>>(p, g);
+  } else {
+    const uint32_t smem = std::max<uint32_t>(g.smem_bytes, 120u * 1024u);
+    gemmconv_kernel<1><<<(unsigned)grid, GC_THREADS, smem, s>>>(p, g);
+  }
   AB_LAUNCH_CHECK("gemmconv_kernel");
   return AB_OK;
 }
