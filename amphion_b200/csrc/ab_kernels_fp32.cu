@@ -253,34 +253,37 @@ __global__ void __launch_bounds__(NT) conv_post_vec_kernel(ConvParams p) {
   const float* xb = p.x + (int64_t)b * p.xsb;
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
   const int tl = 4 * threadIdx.x;
+  // All of a chunk's 16-byte groups are in flight at once: a thread owns groups tid, tid + 256, ... of the flattened
+  // [PCI][XG] tile (loading row by row exposed one DRAM latency per row), and the NEXT chunk's groups are requested
+  // before the current chunk is multiplied, so the latency hides under the FMAs.
+  constexpr int NG = (PCI * XG + NT - 1) / NT;
+  float4 v[NG];
+  auto request = [&](int ci0) {
+#pragma unroll
+    for (int i = 0; i < NG; ++i) {
+      const int idx = threadIdx.x + NT * i;
+      const int ci = idx / XG, q = idx - ci * XG;
+      const int t = t0 - 4 + 4 * q;
+      v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (idx < PCI * XG && ci0 + ci < p.Cin && t >= 0 && t < p.T)
+        v[i] = __ldg(reinterpret_cast<const float4*>(xb + (int64_t)(ci0 + ci) * p.xsc + (t0 - 4)) + q);
+    }
+  };
+  request(0);
   for (int ci0 = 0; ci0 < p.Cin; ci0 += PCI) {
     __syncthreads();
-    {
-      // all of the chunk's 16-byte groups in flight at once: a thread owns groups tid, tid + 256, ... of the
-      // flattened [PCI][XG] tile (loading row by row exposed one DRAM latency per row)
-      constexpr int NG = (PCI * XG + NT - 1) / NT;
-      float4 v[NG];
 #pragma unroll
-      for (int i = 0; i < NG; ++i) {
-        const int idx = threadIdx.x + NT * i;
-        const int ci = idx / XG, q = idx - ci * XG;
-        const int t = t0 - 4 + 4 * q;
-        v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (idx < PCI * XG && ci0 + ci < p.Cin && t >= 0 && t < p.T)
-          v[i] = __ldg(reinterpret_cast<const float4*>(xb + (int64_t)(ci0 + ci) * p.xsc + (t0 - 4)) + q);
-      }
-#pragma unroll
-      for (int i = 0; i < NG; ++i) {
-        const int idx = threadIdx.x + NT * i;
-        const int ci = idx / XG, q = idx - ci * XG;
-        float4 w = v[i];
-        w.x = w.x >= 0.f ? w.x : w.x * slope;
-        w.y = w.y >= 0.f ? w.y : w.y * slope;
-        w.z = w.z >= 0.f ? w.z : w.z * slope;
-        w.w = w.w >= 0.f ? w.w : w.w * slope;
-        if (idx < PCI * XG) *reinterpret_cast<float4*>(&xs[ci][4 * q]) = w;
-      }
+    for (int i = 0; i < NG; ++i) {
+      const int idx = threadIdx.x + NT * i;
+      const int ci = idx / XG, q = idx - ci * XG;
+      float4 w = v[i];
+      w.x = w.x >= 0.f ? w.x : w.x * slope;
+      w.y = w.y >= 0.f ? w.y : w.y * slope;
+      w.z = w.z >= 0.f ? w.z : w.z * slope;
+      w.w = w.w >= 0.f ? w.w : w.w * slope;
+      if (idx < PCI * XG) *reinterpret_cast<float4*>(&xs[ci][4 * q]) = w;
     }
+    if (ci0 + PCI < p.Cin) request(ci0 + PCI);
     if (threadIdx.x < PCI * 8) {
       const int ci = threadIdx.x >> 3, j = threadIdx.x & 7;
       ws[threadIdx.x] = (ci0 + ci < p.Cin && j < K) ? __ldg(p.w_t + (int64_t)(ci0 + ci) * K + j) : 0.f;   // [Cin][K][1]
