@@ -70,6 +70,42 @@ struct ConvTParams {
   float pre_slope;
 };
 
+#ifdef __CUDACC__
+// Packed fp32 pairs (sm_100 FFMA2 / FMUL2 / FADD2: one issue slot for two lanes of work).  A pair lives in an
+// aligned 64-bit register; 8- and 16-byte shared-memory loads deliver pairs without any move.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void upk2(f32x2 v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ float hsum2(f32x2 v) {
+  float lo, hi;
+  upk2(v, lo, hi);
+  return lo + hi;
+}
+
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+
+#endif
+
 // Filter taps of one Activation1d as the packed pairs the kernel multiplies with (host-side copy, passed by value so
 // they sit in the constant bank / uniform registers): see snake_segment in ab_kernels_fp32.cu.
 struct SnakeCoef {

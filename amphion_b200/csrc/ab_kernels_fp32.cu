@@ -519,33 +519,6 @@ __device__ __forceinline__ float snake_eval(float u, float a, float invb) {
   return fmaf(invb, sv * sv, u);
 }
 
-// Packed fp32 pairs (sm_100 FFMA2 / FMUL2 / FADD2: one issue slot for two lanes of work).  A pair lives in an
-// aligned 64-bit register; 8- and 16-byte shared-memory loads deliver pairs without any move.
-typedef unsigned long long f32x2;
-__device__ __forceinline__ f32x2 pk2(float lo, float hi) {
-  f32x2 r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-  return r;
-}
-__device__ __forceinline__ void upk2(f32x2 v, float& lo, float& hi) {
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
-}
-__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
-  f32x2 r;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
-  return r;
-}
-__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
-  f32x2 r;
-  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-  return r;
-}
-__device__ __forceinline__ float hsum2(f32x2 v) {
-  float lo, hi;
-  upk2(v, lo, hi);
-  return lo + hi;
-}
-
 // Two snake evaluations at once, without explicit range reduction: sin.approx multiplies by 1/2pi and the MUFU
 // reduces in turns, so the phase error is ~1.2e-7 * |u a| rad.  Used on the 16-bit operand path only (the operand
 // rounding is 5e-4 relative); the fp32 outputs keep the Cody-Waite reduction of snake_eval.

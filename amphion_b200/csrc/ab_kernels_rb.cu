@@ -85,6 +85,25 @@ __device__ __forceinline__ void store_operand16(uint8_t* buf, int RBrows, int ch
   }
 }
 
+// Epilogue arithmetic on packed fp32 pairs (add / mul.f32x2: IEEE round-to-nearest per lane, i.e. the same results as
+// the scalar FADD / FMUL they replace, at half the issue slots).
+__device__ __forceinline__ void add_bias16(const uint32_t (&r)[16], const float (&bv)[16], float (&a)[16]) {
+#pragma unroll
+  for (int e = 0; e < 16; e += 2)
+    upk2(add2(pk2(__uint_as_float(r[e]), __uint_as_float(r[e + 1])), pk2(bv[e], bv[e + 1])), a[e], a[e + 1]);
+}
+// leaky_relu for 0 <= slope <= 1: max(v, slope * v)
+__device__ __forceinline__ void lrelu16(const float (&a)[16], float slope, float (&v)[16]) {
+  const f32x2 s2 = pk2(slope, slope);
+#pragma unroll
+  for (int e = 0; e < 16; e += 2) {
+    float t0, t1;
+    upk2(mul2(pk2(a[e], a[e + 1]), s2), t0, t1);
+    v[e] = fmaxf(a[e], t0);
+    v[e + 1] = fmaxf(a[e + 1], t1);
+  }
+}
+
 template <int BF16>
 __global__ void __launch_bounds__(RB_THREADS, 1) rb_kernel(RbParams p, RbGeom g) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -398,13 +417,13 @@ __global__ void __launch_bounds__(RB_THREADS, 1) rb_kernel(RbParams p, RbGeom g)
               float bv[16];
               load_bias16(bv, bias_c + c.ch * 16);
               tc_wait_ld();
-              float v[16];
-#pragma unroll
-              for (int e = 0; e < 16; ++e) {
-                const float a = __uint_as_float(r[e]) + bv[e];
-                v[e] = inr ? lrelu(a, p.slope) : 0.f;
+              // rows outside [0, T) keep the zeros the tile load put there (conv2's zero padding): no store
+              if (inr) {
+                float a[16], v[16];
+                add_bias16(r, bv, a);
+                lrelu16(a, p.slope, v);
+                store_opnd(opnd_off(c.i, c.ch), v);
               }
-              store_opnd(opnd_off(c.i, c.ch), v);
 #pragma unroll
               for (int e = 0; e < 16; ++e) r[e] = __float_as_uint(res[e]);
               tst16(taddr, r);
@@ -418,13 +437,12 @@ __global__ void __launch_bounds__(RB_THREADS, 1) rb_kernel(RbParams p, RbGeom g)
                 float bv[16];
                 load_bias16(bv, bias_c + c.ch * 16);
                 tc_wait_ld();
-                float v[16];
-#pragma unroll
-                for (int e = 0; e < 16; ++e) {
-                  const float a = __uint_as_float(r[e]) + bv[e];
-                  v[e] = inr ? lrelu(a, p.slope) : 0.f;
+                if (inr) {
+                  float a[16], v[16];
+                  add_bias16(r, bv, a);
+                  lrelu16(a, p.slope, v);
+                  store_opnd(opnd_off(c.i, c.ch), v);
                 }
-                store_opnd(opnd_off(c.i, c.ch), v);
               }
             } else if (pair > 0 && !add_acp) {
               // residual from the scratch: the next item's 64 bytes are requested before this item is processed
@@ -475,13 +493,12 @@ __global__ void __launch_bounds__(RB_THREADS, 1) rb_kernel(RbParams p, RbGeom g)
                 float bv[16];
                 load_bias16(bv, cum + c.ch * 16);
                 tc_wait_ld();
-                float v[16];
-#pragma unroll
-                for (int e = 0; e < 16; ++e) {
-                  const float a = __uint_as_float(r[e]) + bv[e];
-                  v[e] = inr ? lrelu(a, p.slope) : 0.f;
+                if (inr) {
+                  float a[16], v[16];
+                  add_bias16(r, bv, a);
+                  lrelu16(a, p.slope, v);
+                  store_opnd(opnd_off(c.i, c.ch), v);
                 }
-                store_opnd(opnd_off(c.i, c.ch), v);
               }
             } else
             for (Cur c = cur_first(); c.n < nitems; cur_next(c)) {
@@ -495,12 +512,8 @@ __global__ void __launch_bounds__(RB_THREADS, 1) rb_kernel(RbParams p, RbGeom g)
               float bv[16];
               load_bias16(bv, bias_c + c.ch * 16);
               tc_wait_ld();
-              float a[16], v[16];
-#pragma unroll
-              for (int e = 0; e < 16; ++e) {
-                a[e] = __uint_as_float(r[e]) + bv[e];
-                v[e] = inr ? lrelu(a[e], p.slope) : 0.f;
-              }
+              float a[16];
+              add_bias16(r, bv, a);
               if (p.nconv == 2) {
                 float4* sp = reinterpret_cast<float4*>(scr_lane + (size_t)c.n * scr_item);
 #pragma unroll
@@ -511,7 +524,11 @@ __global__ void __launch_bounds__(RB_THREADS, 1) rb_kernel(RbParams p, RbGeom g)
                 for (int e = 0; e < 16; ++e) r[e] = __float_as_uint(add_acp ? a[e] + acp[e] : a[e]);
                 tst16(taddr, r);
               }
-              store_opnd(opnd_off(c.i, c.ch), v);
+              if (inr) {
+                float v[16];
+                lrelu16(a, p.slope, v);
+                store_opnd(opnd_off(c.i, c.ch), v);
+              }
             }
             if (p.nconv == 1) tc_wait_st();
             publish_operand(slot);
@@ -535,11 +552,16 @@ __global__ void __launch_bounds__(RB_THREADS, 1) rb_kernel(RbParams p, RbGeom g)
               load_bias16(bv, (g.split ? bias_s + (g.nsteps + last_pair) * g.Np : bias_c) + c.ch * 16);
               tc_wait_ld();
               float v[16];
+              {
+                float a[16];
+                add_bias16(r, bv, a);
+                const f32x2 sc2 = pk2(g.out_scale, g.out_scale);
 #pragma unroll
-              for (int e = 0; e < 16; ++e) {
-                float a = __uint_as_float(r[e]) + bv[e];
-                if (fin_acp) a += acp[e];
-                v[e] = a * g.out_scale;
+                for (int e = 0; e < 16; e += 2) {
+                  f32x2 a2 = pk2(a[e], a[e + 1]);
+                  if (fin_acp) a2 = add2(a2, pk2(acp[e], acp[e + 1]));
+                  upk2(mul2(a2, sc2), v[e], v[e + 1]);
+                }
               }
               if (ok && !sk_st) {
                 float* q = p.y + off0;
@@ -554,12 +576,15 @@ __global__ void __launch_bounds__(RB_THREADS, 1) rb_kernel(RbParams p, RbGeom g)
                 if (p.yimg != nullptr) {
                   uint16_t* yi = p.yimg + (((size_t)b * c8n + (size_t)c.ch * 2) * p.T + (size_t)t) * 8;
 #pragma unroll
+                  float w[16];
+                  lrelu16(v, p.img_slope, w);
+#pragma unroll
                   for (int h = 0; h < 2; ++h) {
                     uint4 qv;
-                    qv.x = pack2t<BF16>(lrelu(v[8 * h + 0], p.img_slope), lrelu(v[8 * h + 1], p.img_slope));
-                    qv.y = pack2t<BF16>(lrelu(v[8 * h + 2], p.img_slope), lrelu(v[8 * h + 3], p.img_slope));
-                    qv.z = pack2t<BF16>(lrelu(v[8 * h + 4], p.img_slope), lrelu(v[8 * h + 5], p.img_slope));
-                    qv.w = pack2t<BF16>(lrelu(v[8 * h + 6], p.img_slope), lrelu(v[8 * h + 7], p.img_slope));
+                    qv.x = pack2t<BF16>(w[8 * h + 0], w[8 * h + 1]);
+                    qv.y = pack2t<BF16>(w[8 * h + 2], w[8 * h + 3]);
+                    qv.z = pack2t<BF16>(w[8 * h + 4], w[8 * h + 5]);
+                    qv.w = pack2t<BF16>(w[8 * h + 6], w[8 * h + 7]);
                     *reinterpret_cast<uint4*>(yi + (size_t)h * p.T * 8) = qv;
                   }
                 }

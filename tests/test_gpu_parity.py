@@ -1053,3 +1053,28 @@ def test_vocos_istft_head_matches_the_oracle():
     want = og.istft_same(mag * np.cos(y[:, 401:]), mag * np.sin(y[:, 401:]), 800, 200, 800)
     assert got.shape == want.shape == (2, 21 * 200)
     assert np.abs(got.cpu().numpy() - want).max() <= 1e-3 * max(1.0, np.abs(want).max())   # TF32-free fp32 GEMM + fp32 FFT
+
+
+@pytest.mark.parametrize("B,T", [(1, 1), (3, 5), (1, 130)])
+def test_apnet_odd_shapes(B, T):
+    """Channel counts that are not multiples of 16, a single frame, a tile boundary: against the oracle."""
+    from helpers import sd_numpy
+    from oracle import generator as og
+    hp = dict(ASP_channel=24, ASP_resblock_kernel_sizes=[3, 5], ASP_resblock_dilation_sizes=[[1, 3, 5], [1, 2, 4]],
+              ASP_input_conv_kernel_size=3, ASP_output_conv_kernel_size=5,
+              PSP_channel=40, PSP_resblock_kernel_sizes=[7], PSP_resblock_dilation_sizes=[[1, 3, 5]],
+              PSP_input_conv_kernel_size=7, PSP_output_R_conv_kernel_size=3, PSP_output_I_conv_kernel_size=3)
+    pre = dict(n_mel=10, n_fft=32, hop_size=8, win_size=32, extract_amplitude_phase=True, sample_rate=16000)
+    model = _apnet_model(hp, pre, seed=21)
+    with torch.no_grad():
+        for conv, gain in ((model.ASP_output_conv, 3.0), (model.PSP_output_R_conv, 20.0), (model.PSP_output_I_conv, 20.0)):
+            conv.weight_g.mul_(gain)
+    mel = torch.randn(B, 10, T, generator=torch.Generator().manual_seed(22))
+    want = og.apnet_forward(sd_numpy(model), hp, mel.numpy(), 32, 8, 32)
+    for precision, tol in (("fp32", 1e-4), ("tc_f16", 2e-3)):
+        model.precision = precision
+        got = model(mel.to(DEV))
+        assert got[4].shape == (B, 1, T * 8)
+        scale = max(1.0, float(np.abs(want[4]).max()))
+        assert np.abs(got[0].cpu().numpy() - want[0]).max() <= 3 * tol, precision
+        assert np.abs(got[4].cpu().numpy() - want[4]).max() <= tol * scale, precision
