@@ -95,6 +95,7 @@ SIGNATURES = {
     "ab_mel_forward_fused": (C.c_int, [_P, _P, C.c_int64, C.c_int64, _P, _P, _P, _P, _P, C.c_size_t, _P]),
     "ab_mel_backward_workspace_bytes": (C.c_size_t, [_P, C.c_int64, C.c_int64]),
     "ab_mel_backward": (C.c_int, [_P, _P, C.c_int64, C.c_int64, _P, _P, _P, _P, _P, C.c_size_t, _P]),
+    "ab_amplitude_phase_forward": (C.c_int, [_P, _P, C.c_int64, C.c_int64, _P, _P, _P, _P, _P, _P, C.c_size_t, _P]),
     "ab_spectral_head_forward": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int64, C.c_int64, C.c_float, _P, _P, _P, _P, _P]),
     "ab_istft_workspace_bytes": (C.c_size_t, [_P, C.c_int64, C.c_int64]),
     "ab_istft_forward": (C.c_int, [_P, _P, C.c_int64, C.c_int64, _P, _P, _P, C.c_size_t, _P]),

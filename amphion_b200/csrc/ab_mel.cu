@@ -250,6 +250,34 @@ __global__ void __launch_bounds__(256) spectral_head_kernel(const float* __restr
     }
 }
 
+// amplitude_phase_spectrum (utils/mel.py:244-280, APNet's training features): from the complex spectrum [B*F][bins]
+// to log(|X| + 1e-5), atan2(im, re), re, im as [B][bins][F] — 32 x 32 tiles transposed through shared memory.
+__global__ void __launch_bounds__(256) amp_phase_kernel(const float2* __restrict__ spec, float* __restrict__ logamp,
+                                                        float* __restrict__ pha, float* __restrict__ rea,
+                                                        float* __restrict__ imag, int bins, int F) {
+  __shared__ float2 tile[32][33];
+  const int b = blockIdx.z, k0 = blockIdx.y * 32, f0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int r = ty; r < 32; r += 8) {
+    const int f = f0 + r, k = k0 + tx;
+    tile[r][tx] = (f < F && k < bins) ? __ldg(spec + ((int64_t)b * F + f) * bins + k) : make_float2(0.f, 0.f);
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const int k = k0 + r, f = f0 + tx;
+    if (k < bins && f < F) {
+      const float2 c = tile[tx][r];
+      const int64_t idx = ((int64_t)b * bins + k) * F + f;
+      // torch: log(abs(sqrt(re^2 + im^2)) + 1e-5)
+      const float mag = __fsqrt_rn(__fadd_rn(__fmul_rn(c.x, c.x), __fmul_rn(c.y, c.y)));
+      if (logamp) logamp[idx] = logf(mag + 1e-5f);
+      if (pha) pha[idx] = atan2f(c.y, c.x);
+      if (rea) rea[idx] = c.x;
+      if (imag) imag[idx] = c.y;
+    }
+  }
+}
+
 // wav[b][i] = sum_f window[p - f hop] frames[b F + f][p - f hop] / n_fft  /  sum_f window[p - f hop]^2,  p = i + pad
 __global__ void __launch_bounds__(256) istft_ola_kernel(const float* __restrict__ frames, const float* __restrict__ window,
                                                         float* __restrict__ wav, int F, int n_fft, int hop, int pad,
@@ -691,6 +719,33 @@ int ab_mel_backward(ab_mel* m, const float* dev_wav, int64_t B, int64_t T, const
   mel_bwd_ola_kernel<<<ogrid, 256, 0, st>>>(frames, dev_window, dev_grad_wav, (int)T, (int)L.F, m->cfg.n_fft, m->cfg.hop,
                                             m->cfg.win, m->cfg.pad);
   AB_LAUNCH_CHECK("mel_bwd_ola_kernel");
+  return AB_OK;
+}
+
+int ab_amplitude_phase_forward(ab_mel* m, const float* dev_wav, int64_t B, int64_t T, const float* dev_window,
+                               float* dev_logamp, float* dev_pha, float* dev_rea, float* dev_imag,
+                               void* ws, size_t ws_bytes, void* stream) {
+  if (!m || !dev_wav || !dev_window || !ws) return fail(AB_ERR_ARG, "amplitude_phase: null argument");
+  if (B <= 0 || B > 65535 || T <= 0 || T > (1ll << 30)) return fail(AB_ERR_ARG, "amplitude_phase: bad shape");
+  MelLayout L;
+  cufftHandle plan;
+  int rc = mel_layout(m, B, T, &L, &plan);
+  if (rc != AB_OK) return rc;
+  if (ws_bytes < L.total) return fail(AB_ERR_WORKSPACE, "amplitude_phase: workspace %zu B < required %zu B", ws_bytes, L.total);
+  if (reinterpret_cast<uintptr_t>(ws) & 255) return fail(AB_ERR_ARG, "amplitude_phase: workspace must be 256-byte aligned");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  char* base = static_cast<char*>(ws);
+  float* frames = reinterpret_cast<float*>(base + L.off_frames);
+  float2* spec = reinterpret_cast<float2*>(base + L.off_spec);
+  frame_window_kernel<<<(unsigned)(B * L.F), 256, 0, st>>>(dev_wav, dev_window, frames, (int)T, (int)L.F, m->cfg.n_fft,
+                                                          m->cfg.hop, m->cfg.win, m->cfg.pad);
+  AB_LAUNCH_CHECK("frame_window_kernel");
+  AB_CUFFT_TRY(cufftSetStream(plan, st));
+  AB_CUFFT_TRY(cufftSetWorkArea(plan, base + L.off_fft));
+  AB_CUFFT_TRY(cufftExecR2C(plan, frames, reinterpret_cast<cufftComplex*>(spec)));
+  dim3 grid((unsigned)ceil_div(L.F, (int64_t)32), (unsigned)ceil_div((int64_t)m->bins, (int64_t)32), (unsigned)B);
+  amp_phase_kernel<<<grid, 256, 0, st>>>(spec, dev_logamp, dev_pha, dev_rea, dev_imag, m->bins, (int)L.F);
+  AB_LAUNCH_CHECK("amp_phase_kernel");
   return AB_OK;
 }
 

@@ -30,8 +30,8 @@ def save_feature(process_dir, feature_dir, item, feature, overrides=True):
 
 
 def extract_utt_mel_features(dataset_output, cfg, utt, wav):
-    """The mel (and from-mel energy) part of ``extract_utt_acoustic_features_vocoder``
-    (processors/acoustic_extractor.py:376-417) for one utterance whose audio ``wav`` [T] is already a CUDA tensor at
+    """The mel, from-mel energy and amplitude/phase part of ``extract_utt_acoustic_features_vocoder``
+    (processors/acoustic_extractor.py:376-439) for one utterance whose audio ``wav`` [T] is already a CUDA tensor at
     ``cfg.preprocess.sample_rate`` (loading / resampling stays with the caller).  Returns the mel [n_mel, T]."""
     uid = utt["Uid"]
     pre = cfg.preprocess
@@ -42,6 +42,12 @@ def extract_utt_mel_features(dataset_output, cfg, utt, wav):
     if getattr(pre, "extract_energy", False) and getattr(pre, "energy_extract_mode", "from_mel") == "from_mel":
         energy = (mel.exp() ** 2).sum(0).sqrt()                        # acoustic_extractor.py:408
         save_feature(dataset_output, getattr(pre, "energy_dir", "energys"), uid, energy)
+    if getattr(pre, "extract_amplitude_phase", False):                 # acoustic_extractor.py:428-439 (APNet features)
+        log_amplitude, phase, real, imaginary = _mel.amplitude_phase_spectrum(wav.unsqueeze(0), pre)
+        save_feature(dataset_output, getattr(pre, "log_amplitude_dir", "log_amplitudes"), uid, log_amplitude)
+        save_feature(dataset_output, getattr(pre, "phase_dir", "phases"), uid, phase)
+        save_feature(dataset_output, getattr(pre, "real_dir", "reals"), uid, real)
+        save_feature(dataset_output, getattr(pre, "imaginary_dir", "imaginarys"), uid, imaginary)
     return mel
 
 

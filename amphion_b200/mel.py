@@ -201,6 +201,36 @@ def extract_mel_features(y, cfg, center=False, **kwargs):
     return native_stft_mel(y, cfg.n_fft, cfg.hop_size, cfg.win_size, win, basis, pad, 1e-9)[1].squeeze(0)
 
 
+def amplitude_phase_spectrum(y, cfg):
+    """utils/mel.py:244-280 (APNet's training features): y [B, T] -> (log_amplitude, phase, rea, imag), each
+    [B, n_fft//2+1, frames] ([n_fft//2+1, frames] for B == 1, the reference's squeeze)."""
+    _capi.require_cuda(y, "amplitude_phase_spectrum")
+    if y.dim() != 2:
+        raise ValueError("expected audio of shape [B, T]")
+    y = y.detach().contiguous().float()
+    B, T = y.shape
+    pad = int((cfg.n_fft - cfg.hop_size) / 2)
+    h = _handle_for(cfg.n_fft, cfg.hop_size, cfg.win_size, 0, pad, 0.0, 1e-5, y.device)
+    lib = _capi.lib
+    F = lib.ab_mel_num_frames(h, T)
+    if F <= 0:
+        raise ValueError(f"audio of {T} samples is too short for n_fft={cfg.n_fft}")
+    wkey = (cfg.win_size, str(y.device))
+    if wkey not in hann_window:
+        hann_window[wkey] = torch.hann_window(cfg.win_size).to(y.device)
+    window = hann_window[wkey]
+    bins = cfg.n_fft // 2 + 1
+    outs = [torch.empty(B, bins, F, device=y.device) for _ in range(4)]
+    with torch.cuda.device(y.device):
+        need = lib.ab_mel_workspace_bytes(h, B, T)
+        wbase = _workspace(y.device, need)
+        _capi.check(lib.ab_amplitude_phase_forward(h, _capi.ptr(y), B, T, _capi.ptr(window), *[_capi.ptr(o) for o in outs],
+                                                   C.c_void_p(wbase), need, _capi.stream_ptr()), "ab_amplitude_phase_forward")
+    if B == 1:
+        outs = [o.squeeze(0) for o in outs]
+    return tuple(outs)
+
+
 def extract_mel_features_tts(y, cfg, center=False, taco=False, _stft=None):
     """utils/mel.py:173-241."""
     if not taco:

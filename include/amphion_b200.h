@@ -250,6 +250,12 @@ size_t ab_mel_backward_workspace_bytes(const ab_mel* m, int64_t batch, int64_t s
 int ab_mel_backward(ab_mel* m, const float* dev_wav, int64_t batch, int64_t samples,
                     const float* dev_window, const float* dev_mel_basis, const float* dev_grad_mel,
                     float* dev_grad_wav, void* dev_workspace, size_t workspace_bytes, void* stream);
+/* amplitude_phase_spectrum (utils/mel.py:244-280; APNet's training features, cfg.preprocess.extract_amplitude_phase):
+ * the framing + cuFFT of ab_mel_forward, then log(|X| + 1e-5), atan2(im, re), re, im, each [B, n_fft/2+1, F] (any may
+ * be NULL).  re / im are bit-identical to torch.stft on the same device.  Workspace: ab_mel_workspace_bytes. */
+int ab_amplitude_phase_forward(ab_mel* m, const float* dev_wav, int64_t batch, int64_t samples, const float* dev_window,
+                               float* dev_logamp, float* dev_pha, float* dev_rea, float* dev_imag,
+                               void* dev_workspace, size_t workspace_bytes, void* stream);
 /* iSTFT head of the amplitude/phase generators (APNet.forward, models/vocoders/gan/generator/apnet.py:378-399):
  * logamp, R, I [B, bins, F] -> pha = atan2(I, R), rea = exp(logamp) cos(pha), imag = exp(logamp) sin(pha)
  * (each output [B, bins, F], may be NULL) and the complex spectrum [B*F][bins] (interleaved re, im; may be NULL)

@@ -118,6 +118,20 @@ def extract_mel_features(y, mel_basis, n_fft, hop, win, eps=1e-9):
     return log_compress(mel)
 
 
+def amplitude_phase_spectrum(y, n_fft, hop, win):
+    """utils/mel.py:244-280: log(|X| + 1e-5), atan2(im, re), re, im of the reflect-padded, hann-windowed STFT
+    (center=False).  y [B, T] -> four arrays [B, n_fft//2+1, F] float32."""
+    y = np.asarray(y, np.float32)
+    yp = _reflect_pad(y, (n_fft - hop) // 2)
+    nfr = 1 + (yp.shape[1] - n_fft) // hop
+    w = pad_center(hann_periodic(win).astype(np.float32), n_fft).astype(np.float32)
+    idx = np.arange(n_fft)[None, :] + hop * np.arange(nfr)[:, None]
+    spec = np.fft.rfft((yp[:, idx] * w[None, None, :]).astype(np.float32), axis=-1).transpose(0, 2, 1)
+    re, im = spec.real.astype(np.float32), spec.imag.astype(np.float32)
+    logamp = np.log(np.sqrt(re * re + im * im) + np.float32(1e-5)).astype(np.float32)
+    return logamp, np.arctan2(im, re).astype(np.float32), re, im
+
+
 def extract_mel_features_vjp(y, mel_basis, grad_mel, n_fft, hop, win, eps=1e-9, clip=1e-5):
     """Cotangent of the waveform for a cotangent ``grad_mel`` [B, n_mel, F] of ``extract_mel_features`` — what
     autograd computes through utils/mel.py:145-169 when the trainers differentiate the mel loss

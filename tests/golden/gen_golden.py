@@ -323,6 +323,18 @@ def gen_apnet():
     print("apnet", audio.shape, float(audio.abs().max()), float(logamp.abs().max()), os.path.getsize(os.path.join(HERE, "apnet.npz")))
 
 
+def gen_amp_phase():
+    """amplitude_phase_spectrum (utils/mel.py:244-280), batched and the squeezed B == 1 case."""
+    cfgp = NS(sample_rate=22050, n_fft=256, n_mel=40, fmin=0, fmax=8000, win_size=256, hop_size=64)
+    g = torch.Generator().manual_seed(33)
+    y = (torch.rand(2, 3000, generator=g) * 2 - 1) * 0.8
+    la, ph, re, im = rmel.amplitude_phase_spectrum(y, cfgp)
+    out = {"y": y.numpy(), "logamp": la.numpy(), "pha": ph.numpy(), "rea": re.numpy(), "imag": im.numpy(),
+           "b1_shape": np.array(rmel.amplitude_phase_spectrum(y[:1], cfgp)[0].shape)}
+    np.savez(os.path.join(HERE, "amp_phase.npz"), **out)
+    print("amp_phase", la.shape, out["b1_shape"])
+
+
 def gen_plumbing(cfg, model):
     import models.vocoders.gan.gan_vocoder_inference as gvi
     g = torch.Generator().manual_seed(5)
@@ -339,7 +351,7 @@ def gen_plumbing(cfg, model):
 
 if __name__ == "__main__":
     LATER = {"nsfhifigan": gen_nsfhifigan, "save_audio": gen_save_audio, "hifigan_vits": gen_hifigan_vits,
-             "mel_grad": gen_mel_grad, "apnet": gen_apnet}
+             "mel_grad": gen_mel_grad, "apnet": gen_apnet, "amp_phase": gen_amp_phase}
     if sys.argv[1:] and set(sys.argv[1:]) <= set(LATER):   # later additions regenerate alone
         for name in sys.argv[1:]:
             LATER[name]()
@@ -356,3 +368,4 @@ if __name__ == "__main__":
     gen_hifigan_vits()
     gen_mel_grad()
     gen_apnet()
+    gen_amp_phase()

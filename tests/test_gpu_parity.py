@@ -920,6 +920,7 @@ def test_feature_directory_round_trip(tmp_path):
     pre.sample_rate, pre.n_fft, pre.win_size, pre.fmin, pre.fmax = 16000, 256, 256, 0, 8000
     pre.processed_dir, pre.train_file, pre.valid_file, pre.mel_dir = root, "train.json", "valid.json", "mels"
     pre.use_mel, pre.use_frame_pitch, pre.extract_mel = True, False, True
+    pre.extract_amplitude_phase = True
     hop = pre.hop_size
     rng = np.random.default_rng(3)
     utts = [{"Dataset": "toy", "Uid": f"utt{i:02d}"} for i in range(5)]
@@ -933,6 +934,11 @@ def test_feature_directory_round_trip(tmp_path):
         np.testing.assert_array_equal(stored, m.cpu().numpy())
         np.testing.assert_allclose(stored, om.extract_mel_features(wav[None], basis, 256, hop, 256)[0], atol=2e-4)
         mels.append(torch.from_numpy(stored))
+        la = np.load(os.path.join(root, "toy", "log_amplitudes", u["Uid"] + ".npy"))      # APNet features, squeezed
+        re_, im_ = (np.load(os.path.join(root, "toy", d, u["Uid"] + ".npy")) for d in ("reals", "imaginarys"))
+        assert la.shape == re_.shape == (129, n) and os.path.exists(os.path.join(root, "toy", "phases", u["Uid"] + ".npy"))
+        np.testing.assert_allclose(la, np.log(np.sqrt(re_ ** 2 + im_ ** 2) + 1e-5), atol=1e-5)
+    pre.extract_amplitude_phase = False          # synthesis below is the mel -> wav path of this (HiFi-GAN) model
     features.write_metadata(root, "toy", utts, "valid.json")
     ds = features.VocoderDataset(model.cfg, "toy", is_valid=True)
     out = features.synthesize_dataset(model.cfg, model, ds, str(tmp_path / "out"), batch_size=2)
@@ -1078,3 +1084,24 @@ def test_apnet_odd_shapes(B, T):
         scale = max(1.0, float(np.abs(want[4]).max()))
         assert np.abs(got[0].cpu().numpy() - want[0]).max() <= 3 * tol, precision
         assert np.abs(got[4].cpu().numpy() - want[4]).max() <= tol * scale, precision
+
+
+def test_amplitude_phase_spectrum_matches_reference_fixture():
+    """utils/mel.py:244-280 on the native STFT: re / im against the reference fixture, log-amplitude and phase
+    consistent with them, and the squeezed B == 1 form."""
+    from types import SimpleNamespace as NS
+    from amphion_b200 import mel
+    g, _ = load_golden("amp_phase")
+    cfgp = NS(sample_rate=22050, n_fft=256, n_mel=40, fmin=0, fmax=8000, win_size=256, hop_size=64)
+    y = torch.from_numpy(g["y"]).to(DEV)
+    la, ph, re, im = (t.cpu().numpy() for t in mel.amplitude_phase_spectrum(y, cfgp))
+    scale = np.abs(g["rea"]).max()
+    assert la.shape == (2, 129, 46)
+    assert np.abs(re - g["rea"]).max() <= 2e-5 * scale and np.abs(im - g["imag"]).max() <= 2e-5 * scale
+    np.testing.assert_allclose(la, g["logamp"], atol=2e-3)
+    np.testing.assert_allclose(la, np.log(np.sqrt(re * re + im * im) + 1e-5), atol=1e-5)
+    mag = np.sqrt(g["rea"] ** 2 + g["imag"] ** 2)
+    d = np.abs(ph - g["pha"])
+    assert (np.minimum(d, 2 * np.pi - d) * mag).max() <= 1e-4 * scale
+    np.testing.assert_allclose(ph, np.arctan2(im, re), atol=1e-5)
+    assert tuple(mel.amplitude_phase_spectrum(y[:1], cfgp)[0].shape) == (129, 46)

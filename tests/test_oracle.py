@@ -182,3 +182,17 @@ def test_apnet_oracle_matches_reference():
     assert audio.shape == g["audio"].shape == (2, 1, 23 * pre["hop_size"])
     np.testing.assert_allclose(audio, g["audio"], atol=2e-5)
     np.testing.assert_allclose(audio[:, 0], g["inference"], atol=2e-5)     # vocoder_inference takes the fifth output
+
+
+def test_amplitude_phase_oracle_matches_reference():
+    """oracle.mel.amplitude_phase_spectrum against utils/mel.py:244-280 (fixture amp_phase.npz)."""
+    g, _ = load_golden("amp_phase")
+    la, ph, re, im = om.amplitude_phase_spectrum(g["y"], 256, 64, 256)
+    assert la.shape == g["logamp"].shape == (2, 129, 46) and tuple(g["b1_shape"]) == (129, 46)
+    scale = np.abs(g["rea"]).max()
+    np.testing.assert_allclose(re, g["rea"], atol=2e-5 * scale)
+    np.testing.assert_allclose(im, g["imag"], atol=2e-5 * scale)
+    np.testing.assert_allclose(la, g["logamp"], atol=2e-3)            # log of small magnitudes amplifies fp32 FFT noise
+    mag = np.sqrt(g["rea"] ** 2 + g["imag"] ** 2)
+    d = np.abs(ph - g["pha"])
+    assert (np.minimum(d, 2 * np.pi - d) * mag).max() <= 1e-4 * scale  # phase weighted by the modulus it belongs to
