@@ -20,6 +20,9 @@ def vocoder_inference(cfg, model, mels, f0s=None, device=None, fast_inference=Fa
         if f0s is None and getattr(cfg.preprocess, "extract_amplitude_phase", False):
             _, _, _, _, output = model.forward(mels)     # amplitude/phase generators (APNet), :27-34
         elif f0s is None:
+            host = _forward_chunked_to_host(model, mels)
+            if host is not None:
+                return host
             output = model.forward(mels)
         else:  # f0-conditioned generators (NSF-HiFiGAN), :36
             output = model.forward(mels, f0s.to(device, non_blocking=True))
@@ -30,6 +33,42 @@ def vocoder_inference(cfg, model, mels, f0s=None, device=None, fast_inference=Fa
         host.copy_(output, non_blocking=True)
         torch.cuda.current_stream(output.device).synchronize()
         return host
+
+
+_D2H_CHUNKS = 4
+_copy_streams = {}
+
+
+def _forward_chunked_to_host(model, mels):
+    """Native generators run their last layer in batch chunks with an event after each
+    (``forward(..., tail_events=...)``): the D2H copy of chunk i then runs on a side stream under the last layer of
+    chunk i + 1 instead of after the whole forward.  Returns the pinned CPU tensor [B, T*hop], or None when the
+    model has no such hook (the caller then copies after the forward, as the reference's ``.cpu()`` does)."""
+    import inspect
+    try:
+        hooked = "tail_events" in inspect.signature(model.forward).parameters
+    except (TypeError, ValueError):
+        hooked = False
+    B = mels.shape[0]
+    if not (hooked and mels.is_cuda and B >= 2):
+        return None
+    n = min(_D2H_CHUNKS, B)
+    dev = mels.device
+    events = [torch.cuda.Event() for _ in range(n)]
+    output = model.forward(mels, tail_events=events)          # [B, 1, L] on the current stream
+    main = torch.cuda.current_stream(dev)
+    side = _copy_streams.setdefault(str(dev), torch.cuda.Stream(device=dev))
+    host = torch.empty((B, output.shape[-1]), dtype=output.dtype, pin_memory=True)
+    flat = output.detach().squeeze(1)
+    with torch.cuda.stream(side):
+        for i in range(n):
+            b0, b1 = B * i // n, B * (i + 1) // n                # the chunk bounds of ab_generator_set_tail_events
+            side.wait_event(events[i])
+            host[b0:b1].copy_(flat[b0:b1], non_blocking=True)
+    output.record_stream(side)
+    side.synchronize()
+    main.synchronize()
+    return host
 
 
 def _batches(cfg, model, mels, f0s, batch_size, bucket):
