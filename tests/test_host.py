@@ -353,3 +353,24 @@ def test_vocoder_inference_names_follow_the_reference_layout():
     assert isinstance(v.vocoder_inference, types.ModuleType) and v.vocoder_inference.synthesis is synthesis
     assert callable(vocoder_inference) and callable(load_nnvocoder)
     assert v._vocoder_forward_funcs["hifigan"] is vocoder_inference
+
+
+def test_apnet_copies_and_pickles_without_native_state():
+    """The two trunk handles are derived state: deepcopy / pickle rebuild them, parameters survive."""
+    import copy
+    import pickle
+    from types import SimpleNamespace as NS
+    from conftest import GOLDEN_APNET
+    from amphion_b200.vocoders import APNet
+    hp, pre = GOLDEN_APNET
+    torch.manual_seed(1)
+    model = APNet(NS(preprocess=NS(**pre), model=NS(generator="apnet", apnet=NS(**hp))))
+    model.remove_weight_norm()
+    for clone in (copy.deepcopy(model), pickle.loads(pickle.dumps(model))):
+        assert set(clone._trunks) == {"ASP", "PSP"} and clone._trunks["ASP"]._owner is clone
+        assert clone._trunks["ASP"]._handle is None
+        for (ka, va), (kb, vb) in zip(model.state_dict().items(), clone.state_dict().items()):
+            assert ka == kb and torch.equal(va, vb)
+    # without weight norm the trunk sees the plain weights
+    t = model._trunk_tensors("ASP")
+    assert torch.equal(t["conv_pre.weight"], model.ASP_input_conv.weight.detach())
