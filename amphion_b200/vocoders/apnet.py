@@ -30,20 +30,22 @@ class ISTFT(nn.Module):
         if padding != "same":
             raise NotImplementedError("amphion_b200: ISTFT runs the 'same' padding mode (the one APNet constructs)")
         self.padding, self.n_fft, self.hop_length, self.win_length = padding, n_fft, hop_length, win_length
-        self._handle = None
+        self._handles = {}            # cuFFT plans belong to a device: one native handle per device
 
-    def _mel_handle(self):
-        if self._handle is None:
+    def _mel_handle(self, device):
+        key = str(device)
+        if key not in self._handles:
             h = C.c_void_p()
             cfg = _capi.MelConfig(self.n_fft, self.hop_length, self.win_length, 0, 0, 0.0, 0.0)
             _capi.check(_capi.lib.ab_mel_create(C.byref(cfg), C.byref(h)), "ab_mel_create")
-            self._handle = h
-        return self._handle
+            self._handles[key] = h
+        return self._handles[key]
 
     def forward_interleaved(self, spec_ri, B, T, window):
         """spec_ri: fp32 [B*T, N, 2] (frames-major, overwritten) -> audio [B, T*hop]."""
-        lib, h = _capi.lib, self._mel_handle()
+        lib = _capi.lib
         with torch.cuda.device(spec_ri.device):
+            h = self._mel_handle(spec_ri.device)
             need = lib.ab_istft_workspace_bytes(h, B, T)
             if need == 0:
                 raise RuntimeError("amphion_b200: " + _capi.last_error())
@@ -64,10 +66,15 @@ class ISTFT(nn.Module):
         ri = torch.view_as_real(spec.to(torch.complex64)).permute(0, 2, 1, 3).contiguous().view(B * T, N, 2)
         return self.forward_interleaved(ri, B, T, window)
 
+    def __getstate__(self):
+        state = self.__dict__.copy()
+        state["_handles"] = {}        # ctypes handles are derived state
+        return state
+
     def __del__(self):
         try:
-            if self._handle is not None:
-                _capi.lib.ab_mel_destroy(self._handle)
+            for h in self._handles.values():
+                _capi.lib.ab_mel_destroy(h)
         except Exception:
             pass
 
